@@ -1,0 +1,407 @@
+"""TEST INFRASTRUCTURE ONLY — NumPy restatement of OptionsLab's Monte Carlo hot path.
+
+This file is the parity oracle for the CUDA engine.  It is never imported by
+``optionslab_b200``; see ``oracle/__init__.py`` for who may use it.
+
+Every function restates one piece of the reference's arithmetic in FP64 with
+the SAME floating-point expression shape (so that on the same NumPy build the
+results are bit-identical to the reference; ``tests/test_oracle_golden.py``
+checks that against ``tests/golden/reference_goldens.json``).  Citations are
+relative to the reference repository root.
+"""
+
+from __future__ import annotations
+
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import numpy as np
+
+# --------------------------------------------------------------------------
+# Normal draws, exactly as the reference obtains them
+# --------------------------------------------------------------------------
+
+
+def normals_generator(seed: int, shape) -> np.ndarray:
+    """PCG64 + ziggurat draws used by the European simulators.
+
+    src/simulation/gbm_numpy.py:32,43 (``default_rng(seed).standard_normal((N, n))``),
+    :77 (shape ``(N,)`` for the single-step variant) and
+    src/pricing_models/monte_carlo_unified.py:321,329 (shape ``(n_opt, N, n)``).
+    """
+    return np.random.default_rng(seed).standard_normal(shape)
+
+
+def normals_legacy(seed: Optional[int], shape) -> np.ndarray:
+    """Legacy MT19937 draws used by the exotic path generator.
+
+    src/pricing_models/exotic_options.py:51-52,59 seeds the *global* legacy
+    state; ``RandomState(seed)`` yields the identical stream without touching
+    global state.
+    """
+    return np.random.RandomState(seed).standard_normal(shape)
+
+
+# --------------------------------------------------------------------------
+# European: terminal prices, payoff, discounted mean, standard error
+# --------------------------------------------------------------------------
+
+
+def gbm_terminal_from_normals(S, T, r, sigma, q, Z, antithetic: bool = True) -> np.ndarray:
+    """Terminal prices from a given ``Z`` of shape ``(N, n_steps)``.
+
+    src/simulation/gbm_numpy.py:35-53: per-step drift and vol, the log-price is
+    ``ln S + drift*n + vol*sum_j Z_ij`` (NumPy pairwise row sum); the mirrored
+    paths use ``- vol*sum``; output is ``[+Z paths..., -Z paths...]``.
+    """
+    n_steps = Z.shape[1]
+    dt = T / n_steps
+    drift = (r - q - 0.5 * sigma * sigma) * dt
+    vol = sigma * np.sqrt(dt)
+    total_drift = drift * n_steps
+    log_S0 = np.log(S)
+    W = np.sum(Z, axis=1)
+    up = log_S0 + total_drift + vol * W
+    if not antithetic:
+        return np.exp(up)
+    down = log_S0 + total_drift - vol * W
+    return np.concatenate([np.exp(up), np.exp(down)])
+
+
+def gbm_terminal_single_step(S, T, r, sigma, q, Z) -> np.ndarray:
+    """Single-step closed form, ``Z`` of shape ``(N,)``.
+
+    src/simulation/gbm_numpy.py:71-83.
+    """
+    drift = (r - q - 0.5 * sigma * sigma) * T
+    vol = sigma * np.sqrt(T)
+    log_S0 = np.log(S)
+    return np.concatenate([np.exp(log_S0 + drift + vol * Z), np.exp(log_S0 + drift - vol * Z)])
+
+
+def vanilla_payoffs(terminal: np.ndarray, K, option_type: str) -> np.ndarray:
+    """src/pricing_models/monte_carlo.py:140-143 (also monte_carlo_unified.py:503-506)."""
+    if option_type == "call":
+        return np.maximum(terminal - K, 0.0)
+    return np.maximum(K - terminal, 0.0)
+
+
+def discounted_mean(payoffs: np.ndarray, r, T) -> float:
+    """src/pricing_models/monte_carlo.py:145-146."""
+    return float(np.exp(-r * T) * np.mean(payoffs))
+
+
+def discounted_std_error(payoffs: np.ndarray, r, T) -> float:
+    """Population std (ddof=0) over all 2N antithetic samples / sqrt(2N).
+
+    src/pricing_models/monte_carlo.py:148-150.
+    """
+    return float(np.exp(-r * T) * np.std(payoffs) / np.sqrt(len(payoffs)))
+
+
+@dataclass
+class OracleResult:
+    price: float
+    std_error: float
+    n_paths: int
+    payoffs: np.ndarray
+
+
+def european_price(S, K, T, r, sigma, option_type, q=0.0, *, num_simulations, num_steps, seed) -> OracleResult:
+    """``MonteCarloPricer(num_simulations, num_steps, seed).price(..., return_error=True)``.
+
+    src/pricing_models/monte_carlo.py:74-106 (dispatch: ``num_steps == 1`` takes
+    the single-step simulator), :133-152.
+    """
+    if T <= 0:
+        intrinsic = max(S - K, 0) if option_type == "call" else max(K - S, 0)
+        return OracleResult(intrinsic, 0.0, 0, np.empty(0))
+    if num_steps == 1:
+        Z = normals_generator(seed, num_simulations)
+        terminal = gbm_terminal_single_step(S, T, r, sigma, q, Z)
+    else:
+        Z = normals_generator(seed, (num_simulations, num_steps))
+        terminal = gbm_terminal_from_normals(S, T, r, sigma, q, Z)
+    pay = vanilla_payoffs(terminal, K, option_type)
+    return OracleResult(discounted_mean(pay, r, T), discounted_std_error(pay, r, T), len(pay), pay)
+
+
+# --------------------------------------------------------------------------
+# MonteCarloPricerUni: batched terminals (NumPy backend)
+# --------------------------------------------------------------------------
+
+
+def uni_terminal_from_normals(S_arr, T_arr, r_arr, sigma_arr, q_arr, Z) -> np.ndarray:
+    """``Z`` of shape ``(n_opt, N, n_steps)`` -> terminals ``(n_opt, 2N)``.
+
+    src/pricing_models/monte_carlo_unified.py:324-343: per-option drift/vol,
+    sequential ``cumsum`` of the increments along the step axis (once for +Z,
+    once for -Z), last column, ``exp``.
+    """
+    n_steps = Z.shape[2]
+    dt = T_arr / n_steps
+    drift = (r_arr - q_arr - 0.5 * sigma_arr**2)[:, None] * dt[:, None]
+    vol = sigma_arr[:, None] * np.sqrt(dt[:, None])
+    log_S = np.log(S_arr)[:, None, None]
+    pos = log_S + np.cumsum(drift[:, None, :] + vol[:, None, :] * Z, axis=2)
+    neg = log_S + np.cumsum(drift[:, None, :] - vol[:, None, :] * Z, axis=2)
+    return np.concatenate([np.exp(pos[:, :, -1]), np.exp(neg[:, :, -1])], axis=1)
+
+
+def uni_price_batch(S_vals, K_vals, T_vals, r_vals, sigma_vals, option_type, q_vals=0.0, *,
+                    num_simulations, num_steps, seed) -> np.ndarray:
+    """``MonteCarloPricerUni(..., use_numba=False).price_batch``.
+
+    src/pricing_models/monte_carlo_unified.py:601-631.
+    """
+    S_vals = np.asarray(S_vals, dtype=np.float64)
+    K_vals = np.asarray(K_vals, dtype=np.float64)
+    T_vals = np.asarray(T_vals, dtype=np.float64)
+    r_vals = np.asarray(r_vals, dtype=np.float64)
+    sigma_vals = np.asarray(sigma_vals, dtype=np.float64)
+    if isinstance(q_vals, (int, float)):
+        q_vals = np.full_like(S_vals, q_vals)
+    else:
+        q_vals = np.asarray(q_vals, dtype=np.float64)
+    Z = normals_generator(seed, (len(S_vals), num_simulations, num_steps))
+    terminal = uni_terminal_from_normals(S_vals, T_vals, r_vals, sigma_vals, q_vals, Z)
+    if option_type == "call":
+        pay = np.maximum(terminal - K_vals[:, None], 0.0)
+    else:
+        pay = np.maximum(K_vals[:, None] - terminal, 0.0)
+    return np.exp(-r_vals * T_vals) * np.mean(pay, axis=1)
+
+
+def uni_price(S, K, T, r, sigma, option_type, q=0.0, *, num_simulations, num_steps, seed) -> float:
+    """``MonteCarloPricerUni.price`` (src/pricing_models/monte_carlo_unified.py:493-508)."""
+    Z = normals_generator(seed, (1, num_simulations, num_steps))
+    terminal = uni_terminal_from_normals(np.array([S]), np.array([T]), np.array([r]),
+                                         np.array([sigma]), np.array([q]), Z)[0]
+    pay = vanilla_payoffs(terminal, K, option_type)
+    return float(np.exp(-r * T) * np.mean(pay))
+
+
+def central_delta_gamma(price_up, price_mid, price_down, h):
+    """src/pricing_models/monte_carlo_unified.py:557-558 / :684-685."""
+    return (price_up - price_down) / (2 * h), (price_up - 2 * price_mid + price_down) / (h**2)
+
+
+# --------------------------------------------------------------------------
+# Exotics: full paths, Asian / barrier / lookback payoffs
+# --------------------------------------------------------------------------
+
+
+def exotic_paths_from_normals(S, T, r, sigma, q, Z) -> np.ndarray:
+    """Full path array ``(N, n_steps+1)`` with column 0 = S.
+
+    src/pricing_models/exotic_options.py:54-67: sequential cumsum of
+    ``drift + diffusion*Z`` added to ``ln S``, then ``exp`` of everything.
+    """
+    n_paths, n_steps = Z.shape
+    dt = T / n_steps
+    drift = (r - q - 0.5 * sigma**2) * dt
+    diffusion = sigma * np.sqrt(dt)
+    log_S = np.zeros((n_paths, n_steps + 1))
+    log_S[:, 0] = np.log(S)
+    log_S[:, 1:] = np.log(S) + np.cumsum(drift + diffusion * Z, axis=1)
+    return np.exp(log_S)
+
+
+def asian_payoffs(paths, K, avg_type="arithmetic", option_type="call") -> np.ndarray:
+    """src/pricing_models/exotic_options.py:118-128 (average excludes column 0)."""
+    if avg_type == "arithmetic":
+        avg = np.mean(paths[:, 1:], axis=1)
+    else:
+        avg = np.exp(np.mean(np.log(paths[:, 1:]), axis=1))
+    if option_type == "call":
+        return np.maximum(avg - K, 0)
+    return np.maximum(K - avg, 0)
+
+
+def barrier_payoffs(paths, K, barrier, barrier_type="up-and-out", option_type="call") -> np.ndarray:
+    """src/pricing_models/exotic_options.py:198-222 (monitoring includes column 0, >= / <=)."""
+    if barrier <= 0:
+        raise ValueError("Barrier must be positive")
+    if barrier_type.startswith("up"):
+        crossed = np.any(paths >= barrier, axis=1)
+    else:
+        crossed = np.any(paths <= barrier, axis=1)
+    active = ~crossed if barrier_type.endswith("out") else crossed
+    S_T = paths[:, -1]
+    pay = np.maximum(S_T - K, 0) if option_type == "call" else np.maximum(K - S_T, 0)
+    return pay * active
+
+
+def lookback_payoffs(paths, K, lookback_type="floating", option_type="call") -> np.ndarray:
+    """src/pricing_models/exotic_options.py:380-399 (extrema include column 0)."""
+    S_T = paths[:, -1]
+    S_max = np.max(paths, axis=1)
+    S_min = np.min(paths, axis=1)
+    if lookback_type == "floating":
+        return S_T - S_min if option_type == "call" else S_max - S_T
+    if option_type == "call":
+        return np.maximum(S_max - K, 0)
+    return np.maximum(K - S_min, 0)
+
+
+def exotic_price(kind, S, K, T, r, sigma, q=0.0, *, seed, n_paths, n_steps, option_type="call",
+                 avg_type="arithmetic", barrier=0.0, barrier_type="up-and-out",
+                 lookback_type="floating", return_payoffs=False):
+    """``AsianOption/BarrierOption/LookbackOption(...).price(n_paths, n_steps, ...)``.
+
+    src/pricing_models/exotic_options.py:97-131, :174-224, :368-401.  Chunk-free:
+    materialises the full path array like the reference does.
+    """
+    if kind == "barrier" and barrier <= 0:
+        raise ValueError("Barrier must be positive")
+    Z = normals_legacy(seed, (n_paths, n_steps))
+    paths = exotic_paths_from_normals(S, T, r, sigma, q, Z)
+    if kind == "asian":
+        pay = asian_payoffs(paths, K, avg_type, option_type)
+    elif kind == "barrier":
+        pay = barrier_payoffs(paths, K, barrier, barrier_type, option_type)
+    elif kind == "lookback":
+        pay = lookback_payoffs(paths, K, lookback_type, option_type)
+    else:
+        raise ValueError(kind)
+    price = np.exp(-r * T) * np.mean(pay)
+    return (price, pay) if return_payoffs else price
+
+
+def asian_geometric_closed_form(S, K, T, r, sigma, q=0.0, option_type="call") -> float:
+    """Continuous-averaging closed form, src/pricing_models/exotic_options.py:143-160."""
+    from scipy.stats import norm
+
+    sigma_adj = sigma / np.sqrt(3)
+    r_adj = 0.5 * (r - q - sigma**2 / 6)
+    d1 = (np.log(S / K) + (r_adj + 0.5 * sigma_adj**2) * T) / (sigma_adj * np.sqrt(T))
+    d2 = d1 - sigma_adj * np.sqrt(T)
+    if option_type == "call":
+        return S * np.exp((r_adj - r) * T) * norm.cdf(d1) - K * np.exp(-r * T) * norm.cdf(d2)
+    return K * np.exp(-r * T) * norm.cdf(-d2) - S * np.exp((r_adj - r) * T) * norm.cdf(-d1)
+
+
+# --------------------------------------------------------------------------
+# Bump-and-revalue Greeks
+# --------------------------------------------------------------------------
+
+H_SIGMA = 0.01
+H_R = 1e-4
+H_T = 1 / 365.0
+
+
+def greek_bumps(S):
+    """src/greeks/unified_greeks.py:274-277."""
+    return max(1e-4, 0.01 * S), max(1e-4, 0.01), 1e-4, 1 / 365.0
+
+
+def greeks_bump_and_revalue(price_fn: Callable[..., float], S, K, T, r, sigma, q=0.0,
+                            include_second_order: bool = True) -> "OrderedDict[str, float]":
+    """Finite-difference Greeks over ``price_fn(S, K, T, r, sigma, q)``.
+
+    src/greeks/unified_greeks.py:274-362: memoised scenario prices; delta/gamma
+    central in S; vega central in sigma; theta one-sided over one day (n_steps
+    kept, so dt shrinks); rho central in r; vanna 4-point cross; charm from the
+    delta at T - 1/365; vomma second difference in sigma.
+    """
+    h_S, h_sigma, h_r, h_T = greek_bumps(S)
+    cache = {}
+
+    def P(S_=S, T_=T, r_=r, sigma_=sigma):
+        key = (S_, K, T_, r_, sigma_, q)
+        if key not in cache:
+            cache[key] = price_fn(S_, K, T_, r_, sigma_, q)
+        return cache[key]
+
+    p_mid = P()
+    p_S_up, p_S_down = P(S_=S + h_S), P(S_=S - h_S)
+    delta = (p_S_up - p_S_down) / (2 * h_S)
+    gamma = (p_S_up - 2 * p_mid + p_S_down) / (h_S**2)
+    p_v_up, p_v_down = P(sigma_=sigma + h_sigma), P(sigma_=sigma - h_sigma)
+    vega = (p_v_up - p_v_down) / (2 * h_sigma)
+    if T > h_T:
+        theta = (P(T_=T - h_T) - p_mid) / h_T
+    else:
+        theta = -p_mid / max(T, 1e-6)
+    rho = (P(r_=r + h_r) - P(r_=r - h_r)) / (2 * h_r)
+    out = OrderedDict(price=p_mid, delta=delta, gamma=gamma, vega=vega, theta=theta, rho=rho)
+    if include_second_order:
+        vanna = (P(S_=S + h_S, sigma_=sigma + h_sigma) - P(S_=S + h_S, sigma_=sigma - h_sigma)
+                 - P(S_=S - h_S, sigma_=sigma + h_sigma) + P(S_=S - h_S, sigma_=sigma - h_sigma)) / (
+            4 * h_S * h_sigma)
+        if T > h_T:
+            d_T = (P(S_=S + h_S, T_=T - h_T) - P(S_=S - h_S, T_=T - h_T)) / (2 * h_S)
+            charm = (d_T - delta) / h_T
+        else:
+            charm = 0.0
+        vomma = (p_v_up - 2 * p_mid + p_v_down) / (h_sigma**2)
+        out["vanna"], out["charm"], out["vomma"] = vanna, charm, vomma
+    return out
+
+
+# --------------------------------------------------------------------------
+# Black-Scholes closed form (analytic oracle for the 3-standard-error checks)
+# --------------------------------------------------------------------------
+
+
+def black_scholes(S, K, T, r, sigma, option_type="call", q=0.0) -> float:
+    """src/pricing_models/black_scholes.py:33-52."""
+    from scipy.stats import norm
+
+    if S <= 0 or K <= 0 or T < 0 or sigma < 0:
+        raise ValueError("Invalid input")
+    if T == 0:
+        return max(S - K, 0.0) if option_type == "call" else max(K - S, 0.0)
+    d1 = (np.log(S / K) + (r - q + 0.5 * sigma**2) * T) / (sigma * np.sqrt(T))
+    d2 = d1 - sigma * np.sqrt(T)
+    if option_type == "call":
+        return float(S * np.exp(-q * T) * norm.cdf(d1) - K * np.exp(-r * T) * norm.cdf(d2))
+    return float(K * np.exp(-r * T) * norm.cdf(-d2) - S * np.exp(-q * T) * norm.cdf(-d1))
+
+
+def black_scholes_greeks(S, K, T, r, sigma, option_type="call", q=0.0):
+    """Analytic delta/gamma/vega (textbook BSM; used only as a statistical anchor)."""
+    from scipy.stats import norm
+
+    d1 = (np.log(S / K) + (r - q + 0.5 * sigma**2) * T) / (sigma * np.sqrt(T))
+    pdf = norm.pdf(d1)
+    delta = np.exp(-q * T) * (norm.cdf(d1) if option_type == "call" else norm.cdf(d1) - 1.0)
+    gamma = np.exp(-q * T) * pdf / (S * sigma * np.sqrt(T))
+    vega = S * np.exp(-q * T) * pdf * np.sqrt(T)
+    return float(delta), float(gamma), float(vega)
+
+
+# --------------------------------------------------------------------------
+# Timed CPU baseline used by bench.py (bounded samples of the benchmark workload)
+# --------------------------------------------------------------------------
+
+
+def grid_workload(n_strikes=64, n_maturities=64):
+    """The C5 grid of SURVEY.md §8(d): 64 strikes x 64 maturities, S=100, r=5%, sigma=20%."""
+    K = np.linspace(60.0, 140.0, n_strikes)
+    T = np.linspace(1.0 / 12.0, 2.0, n_maturities)
+    KK, TT = np.meshgrid(K, T, indexing="ij")
+    n = KK.size
+    return dict(S=np.full(n, 100.0), K=KK.ravel().copy(), T=TT.ravel().copy(),
+                r=np.full(n, 0.05), sigma=np.full(n, 0.2), q=np.zeros(n))
+
+
+def cpu_grid_sample(option_indices, num_simulations, num_steps, seed, option_type="call"):
+    """Price a slice of the C5 grid the way the reference would on CPU.
+
+    One option at a time through the ``simulate_gbm_numpy`` arithmetic
+    (gbm_numpy.py:32-53 + monte_carlo.py:140-146); the reference's own batch
+    backend (monte_carlo_unified.py:329) would allocate ``n_opt*N*n`` doubles,
+    which does not fit, so the slice is priced option by option with option
+    ``i`` drawing from ``default_rng(seed + i)`` (the Numba backend's seeding,
+    monte_carlo_unified.py:190).
+    """
+    g = grid_workload()
+    out = np.empty(len(option_indices))
+    for j, i in enumerate(option_indices):
+        res = european_price(g["S"][i], g["K"][i], g["T"][i], g["r"][i], g["sigma"][i], option_type,
+                             g["q"][i], num_simulations=num_simulations, num_steps=num_steps,
+                             seed=seed + int(i))
+        out[j] = res.price
+    return out

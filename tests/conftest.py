@@ -1,0 +1,32 @@
+"""pytest configuration: markers and shared fixtures."""
+
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "slow: long-running statistical case")
+
+
+@pytest.fixture(scope="session")
+def goldens():
+    with open(os.path.join(ROOT, "tests", "golden", "reference_goldens.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def engine():
+    """One CUDA engine handle for the whole GPU test session."""
+    from optionslab_b200 import _ffi
+
+    eng = _ffi.Engine(device=0)
+    yield eng
+    eng.close()

@@ -1,0 +1,140 @@
+"""Generate tests/golden/reference_goldens.json by running the REAL reference.
+
+Run in the build container only (``/root/reference`` does not exist on the GPU
+box):  ``python tests/golden/make_goldens.py``.
+
+The reference imports ``streamlit`` from ``src/utils/decorators/caching.py:3``
+(reached through ``src/__init__.py:24-31``); a pass-through stub module is put
+on ``sys.modules`` so nothing under ``/root/reference`` is modified.  Normal
+draws depend on the NumPy build, so the NumPy version is recorded and the
+tests compare bit-for-bit only when it matches.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import scipy
+
+REFERENCE_ROOT = os.environ.get("OPTIONSLAB_REFERENCE", "/root/reference")
+
+
+def import_reference():
+    st = types.ModuleType("streamlit")
+
+    def _passthrough(*dargs, **dkwargs):
+        if len(dargs) == 1 and callable(dargs[0]) and not dkwargs:
+            return dargs[0]
+        return lambda fn: fn
+
+    st.cache_data = _passthrough
+    st.cache_resource = _passthrough
+    sys.modules.setdefault("streamlit", st)
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    from src.greeks.unified_greeks import ExoticAdapter, compute_greeks_unified
+    from src.pricing_models.black_scholes import black_scholes
+    from src.pricing_models.exotic_options import AsianOption, BarrierOption, LookbackOption
+    from src.pricing_models.monte_carlo import MonteCarloPricer
+    from src.pricing_models.monte_carlo_unified import MonteCarloPricerUni
+
+    return dict(MonteCarloPricer=MonteCarloPricer, MonteCarloPricerUni=MonteCarloPricerUni,
+                AsianOption=AsianOption, BarrierOption=BarrierOption, LookbackOption=LookbackOption,
+                compute_greeks_unified=compute_greeks_unified, ExoticAdapter=ExoticAdapter,
+                black_scholes=black_scholes)
+
+
+def main():
+    ref = import_reference()
+    MCP, Uni = ref["MonteCarloPricer"], ref["MonteCarloPricerUni"]
+    P = dict(S=100.0, K=100.0, T=1.0, r=0.05, sigma=0.2)
+    g = {"numpy": np.__version__, "scipy": scipy.__version__, "point": P, "seed": 42}
+
+    g["black_scholes"] = {"call": float(ref["black_scholes"](**P, option_type="call")),
+                          "put": float(ref["black_scholes"](**P, option_type="put")),
+                          "call_q2": float(ref["black_scholes"](**P, option_type="call", q=0.02))}
+
+    # --- MonteCarloPricer (monte_carlo.py:108-152) ---------------------------------
+    eu = {}
+    for n_sims, n_steps in [(10000, 50), (100000, 252), (100000, 1), (4096, 7)]:
+        for ot in ("call", "put"):
+            pr = MCP(n_sims, n_steps, seed=42)
+            res = pr.price(**P, option_type=ot, return_error=True)
+            term = pr._simulate(P["S"], P["T"], P["r"], P["sigma"], 0.0)
+            pay = np.maximum(term - P["K"], 0.0) if ot == "call" else np.maximum(P["K"] - term, 0.0)
+            eu[f"{n_sims}x{n_steps}_{ot}"] = {
+                "price": res.price, "std_error": res.std_error, "n_paths": res.n_paths,
+                "payoff_head": pay[:8].tolist(), "payoff_mirror_head": pay[n_sims:n_sims + 8].tolist(),
+                "payoff_sum": float(np.sum(pay)),
+            }
+    pr = MCP(20000, 64, seed=7)
+    eu["20000x64_call_q"] = {"price": pr.price(105.0, 95.0, 0.75, 0.03, 0.35, "call", q=0.02, return_error=True).price}
+    g["european"] = eu
+
+    # --- MonteCarloPricerUni NumPy backend (monte_carlo_unified.py:451-689) ---------
+    uni = Uni(10000, 50, seed=42, use_numba=False, use_gpu=False)
+    g["uni"] = {"price_call": uni.price(**P, option_type="call"), "price_put": uni.price(**P, option_type="put")}
+    S_v = np.array([100.0, 110.0, 90.0, 100.0, 100.0])
+    K_v = np.array([100.0, 100.0, 100.0, 95.0, 105.0])
+    T_v = np.array([1.0, 1.0, 1.0, 0.5, 0.5])
+    r_v = np.full(5, 0.05)
+    s_v = np.array([0.2, 0.2, 0.2, 0.3, 0.15])
+    q_v = np.array([0.0, 0.0, 0.0, 0.02, 0.01])
+    uni_b = Uni(2000, 20, seed=42, use_numba=False, use_gpu=False)
+    g["uni"]["batch_inputs"] = dict(S=S_v.tolist(), K=K_v.tolist(), T=T_v.tolist(), r=r_v.tolist(),
+                                    sigma=s_v.tolist(), q=q_v.tolist(), num_simulations=2000, num_steps=20)
+    g["uni"]["price_batch_call"] = uni_b.price_batch(S_v, K_v, T_v, r_v, s_v, "call", q_v).tolist()
+    g["uni"]["price_batch_put"] = uni_b.price_batch(S_v, K_v, T_v, r_v, s_v, "put", q_v).tolist()
+    d, gm = uni_b.delta_gamma_batch(S_v, K_v, T_v, r_v, s_v, "call", q_v, h=1.0)
+    g["uni"]["delta_gamma_batch_h1"] = {"delta": d.tolist(), "gamma": gm.tolist()}
+    d1, g1 = Uni(10000, 50, seed=42, use_numba=False).delta_gamma(**P, option_type="call", h=1.0, seed=42)
+    g["uni"]["delta_gamma_h1_seed42"] = [d1, g1]
+
+    # --- compute_greeks_unified (unified_greeks.py:235-367) -------------------------
+    gk = {}
+    for ot in ("call", "put"):
+        out = ref["compute_greeks_unified"](MCP(100000, 252, seed=42), **P, option_type=ot)
+        gk[f"100000x252_{ot}"] = {k: float(v) for k, v in out.items()}
+    out = ref["compute_greeks_unified"](MCP(20000, 16, seed=3), 105.0, 95.0, 0.75, 0.03, 0.35, "put", q=0.02)
+    gk["20000x16_put_q"] = {k: float(v) for k, v in out.items()}
+    out = ref["compute_greeks_unified"](MCP(20000, 16, seed=3), 100.0, 100.0, 0.002, 0.05, 0.2, "call")
+    gk["20000x16_call_shortT"] = {k: float(v) for k, v in out.items()}
+    g["greeks"] = gk
+
+    # --- Exotics (exotic_options.py:97-131,174-224,368-401) -------------------------
+    ex = {}
+    for n_paths, n_steps in [(100000, 252), (5000, 12)]:
+        a = ref["AsianOption"](**P, seed=42)
+        tag = f"{n_paths}x{n_steps}"
+        ex[f"asian_arith_call_{tag}"] = float(a.price(n_paths, n_steps, "arithmetic", "call"))
+        ex[f"asian_arith_put_{tag}"] = float(a.price(n_paths, n_steps, "arithmetic", "put"))
+        ex[f"asian_geom_call_{tag}"] = float(a.price(n_paths, n_steps, "geometric", "call"))
+        lb = ref["LookbackOption"](**P, seed=42)
+        for lt in ("floating", "fixed"):
+            for ot in ("call", "put"):
+                ex[f"lookback_{lt}_{ot}_{tag}"] = float(lb.price(n_paths, n_steps, lt, ot))
+    ex["asian_geom_closed_form_call"] = float(ref["AsianOption"](**P).price_geometric_closed_form("call"))
+    for n_paths, n_steps in [(100000, 365), (5000, 12)]:
+        tag = f"{n_paths}x{n_steps}"
+        for B, kinds in [(120.0, ("up-and-out", "up-and-in")), (85.0, ("down-and-out", "down-and-in"))]:
+            b = ref["BarrierOption"](**P, seed=42, barrier=B)
+            for bt in kinds:
+                for ot in ("call", "put"):
+                    ex[f"barrier_{bt}_{ot}_B{int(B)}_{tag}"] = float(b.price(n_paths, n_steps, bt, ot))
+    ad = ref["ExoticAdapter"](ref["AsianOption"](**P, seed=42), n_paths=20000, n_steps=32, avg_type="arithmetic")
+    out = ref["compute_greeks_unified"](ad, **P, option_type="call")
+    ex["asian_adapter_greeks_20000x32"] = {k: float(v) for k, v in out.items()}
+    g["exotics"] = ex
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_goldens.json")
+    with open(path, "w") as f:
+        json.dump(g, f, indent=1, sort_keys=True)
+    print("wrote", path)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,149 @@
+"""CPU: the NumPy oracle restatement must reproduce the real reference's outputs.
+
+The goldens were produced by ``tests/golden/make_goldens.py`` importing the
+unmodified reference.  Same NumPy build => draws are identical and the oracle
+must agree to the last bit (we allow 2 ulp-ish 1e-15 rel for BLAS/SIMD paths);
+another NumPy build => only the RNG-free anchors are compared.
+"""
+
+import numpy as np
+import pytest
+
+from oracle import reference_mc as orc
+
+P = dict(S=100.0, K=100.0, T=1.0, r=0.05, sigma=0.2)
+REL = 1e-14
+
+
+def _same_numpy(goldens):
+    return goldens["numpy"] == np.__version__
+
+
+def test_black_scholes_anchor(goldens):
+    assert orc.black_scholes(**P, option_type="call") == pytest.approx(goldens["black_scholes"]["call"], rel=1e-15)
+    assert orc.black_scholes(**P, option_type="put") == pytest.approx(goldens["black_scholes"]["put"], rel=1e-15)
+    assert orc.black_scholes(**P, option_type="call", q=0.02) == pytest.approx(goldens["black_scholes"]["call_q2"], rel=1e-15)
+    # reference tests/test_black_scholes.py:9,14
+    assert orc.black_scholes(**P, option_type="call") == pytest.approx(10.45, rel=1e-2)
+    assert orc.black_scholes(**P, option_type="put") == pytest.approx(5.57, rel=1e-2)
+
+
+@pytest.mark.parametrize("n_sims,n_steps", [(10000, 50), (100000, 1), (4096, 7), (100000, 252)])
+@pytest.mark.parametrize("ot", ["call", "put"])
+def test_european_matches_reference(goldens, n_sims, n_steps, ot):
+    if not _same_numpy(goldens):
+        pytest.skip("goldens recorded with another NumPy build")
+    g = goldens["european"][f"{n_sims}x{n_steps}_{ot}"]
+    res = orc.european_price(**P, option_type=ot, num_simulations=n_sims, num_steps=n_steps, seed=42)
+    assert res.price == pytest.approx(g["price"], rel=REL)
+    assert res.std_error == pytest.approx(g["std_error"], rel=1e-12)
+    assert res.n_paths == g["n_paths"]
+    np.testing.assert_allclose(res.payoffs[:8], g["payoff_head"], rtol=REL, atol=0)
+    np.testing.assert_allclose(res.payoffs[n_sims:n_sims + 8], g["payoff_mirror_head"], rtol=REL, atol=0)
+    assert float(np.sum(res.payoffs)) == pytest.approx(g["payoff_sum"], rel=REL)
+
+
+def test_european_with_dividend(goldens):
+    if not _same_numpy(goldens):
+        pytest.skip("goldens recorded with another NumPy build")
+    res = orc.european_price(105.0, 95.0, 0.75, 0.03, 0.35, "call", q=0.02, num_simulations=20000, num_steps=64, seed=7)
+    assert res.price == pytest.approx(goldens["european"]["20000x64_call_q"]["price"], rel=REL)
+
+
+def test_uni_matches_reference(goldens):
+    if not _same_numpy(goldens):
+        pytest.skip("goldens recorded with another NumPy build")
+    u = goldens["uni"]
+    assert orc.uni_price(**P, option_type="call", num_simulations=10000, num_steps=50, seed=42) == pytest.approx(u["price_call"], rel=REL)
+    assert orc.uni_price(**P, option_type="put", num_simulations=10000, num_steps=50, seed=42) == pytest.approx(u["price_put"], rel=REL)
+    b = u["batch_inputs"]
+    for ot in ("call", "put"):
+        got = orc.uni_price_batch(b["S"], b["K"], b["T"], b["r"], b["sigma"], ot, np.array(b["q"]),
+                                  num_simulations=b["num_simulations"], num_steps=b["num_steps"], seed=42)
+        np.testing.assert_allclose(got, u[f"price_batch_{ot}"], rtol=REL)
+    S = np.array(b["S"])
+    kw = dict(num_simulations=b["num_simulations"], num_steps=b["num_steps"], seed=42)
+    args = (b["K"], b["T"], b["r"], b["sigma"], "call", np.array(b["q"]))
+    d, g = orc.central_delta_gamma(orc.uni_price_batch(S + 1.0, *args, **kw), orc.uni_price_batch(S, *args, **kw),
+                                   orc.uni_price_batch(S - 1.0, *args, **kw), 1.0)
+    np.testing.assert_allclose(d, u["delta_gamma_batch_h1"]["delta"], rtol=1e-12)
+    np.testing.assert_allclose(g, u["delta_gamma_batch_h1"]["gamma"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("ot", ["call", "put"])
+def test_greeks_match_reference(goldens, ot):
+    if not _same_numpy(goldens):
+        pytest.skip("goldens recorded with another NumPy build")
+    g = goldens["greeks"][f"100000x252_{ot}"]
+
+    def price_fn(S, K, T, r, sigma, q):
+        return orc.european_price(S, K, T, r, sigma, ot, q, num_simulations=100000, num_steps=252, seed=42).price
+
+    out = orc.greeks_bump_and_revalue(price_fn, **P)
+    assert list(out.keys()) == ["price", "delta", "gamma", "vega", "theta", "rho", "vanna", "charm", "vomma"]
+    for k, v in g.items():
+        assert out[k] == pytest.approx(v, rel=1e-9, abs=1e-9), k
+
+
+def test_greeks_edge_cases(goldens):
+    if not _same_numpy(goldens):
+        pytest.skip("goldens recorded with another NumPy build")
+
+    def fn(ot):
+        return lambda S, K, T, r, sigma, q: orc.european_price(
+            S, K, T, r, sigma, ot, q, num_simulations=20000, num_steps=16, seed=3).price
+
+    out = orc.greeks_bump_and_revalue(fn("put"), 105.0, 95.0, 0.75, 0.03, 0.35, q=0.02)
+    for k, v in goldens["greeks"]["20000x16_put_q"].items():
+        assert out[k] == pytest.approx(v, rel=1e-9, abs=1e-9), k
+    out = orc.greeks_bump_and_revalue(fn("call"), 100.0, 100.0, 0.002, 0.05, 0.2)   # T < 1/365 branch
+    for k, v in goldens["greeks"]["20000x16_call_shortT"].items():
+        assert out[k] == pytest.approx(v, rel=1e-9, abs=1e-9), k
+
+
+@pytest.mark.parametrize("tag,n_paths,n_steps", [("5000x12", 5000, 12), ("100000x252", 100000, 252)])
+def test_asian_lookback_match_reference(goldens, tag, n_paths, n_steps):
+    if not _same_numpy(goldens):
+        pytest.skip("goldens recorded with another NumPy build")
+    ex = goldens["exotics"]
+    kw = dict(seed=42, n_paths=n_paths, n_steps=n_steps)
+    assert orc.exotic_price("asian", **P, **kw, avg_type="arithmetic", option_type="call") == pytest.approx(ex[f"asian_arith_call_{tag}"], rel=REL)
+    assert orc.exotic_price("asian", **P, **kw, avg_type="arithmetic", option_type="put") == pytest.approx(ex[f"asian_arith_put_{tag}"], rel=REL)
+    assert orc.exotic_price("asian", **P, **kw, avg_type="geometric", option_type="call") == pytest.approx(ex[f"asian_geom_call_{tag}"], rel=REL)
+    for lt in ("floating", "fixed"):
+        for ot in ("call", "put"):
+            got = orc.exotic_price("lookback", **P, **kw, lookback_type=lt, option_type=ot)
+            assert got == pytest.approx(ex[f"lookback_{lt}_{ot}_{tag}"], rel=REL)
+
+
+@pytest.mark.parametrize("tag,n_paths,n_steps", [("5000x12", 5000, 12), ("100000x365", 100000, 365)])
+def test_barrier_matches_reference(goldens, tag, n_paths, n_steps):
+    if not _same_numpy(goldens):
+        pytest.skip("goldens recorded with another NumPy build")
+    ex = goldens["exotics"]
+    for B, kinds in [(120.0, ("up-and-out", "up-and-in")), (85.0, ("down-and-out", "down-and-in"))]:
+        for bt in kinds:
+            for ot in ("call", "put"):
+                got = orc.exotic_price("barrier", **P, seed=42, n_paths=n_paths, n_steps=n_steps,
+                                       barrier=B, barrier_type=bt, option_type=ot)
+                assert got == pytest.approx(ex[f"barrier_{bt}_{ot}_B{int(B)}_{tag}"], rel=REL, abs=1e-15)
+
+
+def test_asian_closed_form_and_adapter_greeks(goldens):
+    ex = goldens["exotics"]
+    assert orc.asian_geometric_closed_form(**P) == pytest.approx(ex["asian_geom_closed_form_call"], rel=1e-14)
+    if not _same_numpy(goldens):
+        pytest.skip("goldens recorded with another NumPy build")
+
+    def fn(S, K, T, r, sigma, q):
+        return orc.exotic_price("asian", S, K, T, r, sigma, q, seed=42, n_paths=20000, n_steps=32)
+
+    out = orc.greeks_bump_and_revalue(fn, **P)
+    for k, v in ex["asian_adapter_greeks_20000x32"].items():
+        assert out[k] == pytest.approx(v, rel=1e-9, abs=1e-9), k
+
+
+def test_barrier_rejects_nonpositive_barrier():
+    # reference tests/test_exotic_options.py:187-193
+    with pytest.raises(ValueError, match="positive"):
+        orc.exotic_price("barrier", **P, seed=1, n_paths=10, n_steps=2, barrier=0.0)
