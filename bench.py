@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the Monte Carlo hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+Workload (BASELINE.json configs[4], SURVEY.md §8d "C5"): a grid of 4096 European calls
+(64 strikes x 64 maturities, S=100, r=5%, sigma=20%), each simulated INDEPENDENTLY with
+1,000,000 antithetic path pairs x 252 log-Euler steps from its own Philox stream.
+One "step" = one pass over the whole grid = 4096 x 1e6 x 252 = 1.032e12 GBM path-steps.
+Metric: GBM path-steps / second (independent normal streams x steps; antithetic mirrors and
+CRN scenarios are NOT counted), whole job over all N GPUs.  N > 1: paths are partitioned across
+ranks (strong scaling: total work fixed) and the (sum, sum^2, n) moments are combined with ONE
+NCCL all-reduce per step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA engine
+  python bench.py --impl reference [...]                        # the reference's NumPy algorithm on host cores
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC, UNIT = "gbm_path_steps_per_sec", "path-steps/s"
+N_STRIKES, N_MATURITIES = 64, 64
+N_OPT, N_PATHS, N_STEPS, SEED = N_STRIKES * N_MATURITIES, 1_000_000, 252, 42
+WORKLOAD = (f"C5: {N_OPT}-option European call grid ({N_STRIKES} strikes 60..140 x {N_MATURITIES} maturities 1/12..2y, "
+            f"S=100 r=0.05 sigma=0.2) x {N_PATHS} paths x {N_STEPS} steps, each option simulated independently "
+            f"(antithetic, own Philox stream)")
+# Instruction budget of the dominant kernel (european_kernel<1,true,2> inner loop, counted from the shipped
+# SASS with cuobjdump — profiles/r01_sass_european.txt): per path-step 14.75 issued instructions, of which 2 MUFU.
+INSTR_PER_STEP, MUFU_PER_STEP, IMAD_PER_STEP, LOP_PER_STEP = 14.75, 2.0, 4.0, 4.5
+
+
+def grid_params():
+    K = np.linspace(60.0, 140.0, N_STRIKES)
+    T = np.linspace(1.0 / 12.0, 2.0, N_MATURITIES)
+    KK, TT = np.meshgrid(K, T, indexing="ij")
+    n = KK.size
+    return dict(S=np.full(n, 100.0), K=KK.ravel().copy(), T=TT.ravel().copy(), r=np.full(n, 0.05),
+                sigma=np.full(n, 0.2), q=np.zeros(n))
+
+
+# ------------------------------------------------------------------------------------------------
+# nvidia-smi clock sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device_index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, power, reasons = [], [], [], set()
+        for t, line in self.lines:
+            if not (t0 <= t <= t1 + 0.2):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2])), power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in timed region"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(power), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle port) on host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_price_option(args):
+    from oracle import reference_mc as orc
+
+    i, n_paths = args
+    return orc.cpu_grid_sample([i], n_paths, N_STEPS, SEED)[0]
+
+
+def cpu_sample(option_indices, n_paths, processes):
+    """Price a slice of the grid with the NumPy restatement of the reference; returns (seconds, prices)."""
+    t0 = time.perf_counter()
+    if processes <= 1:
+        prices = [_cpu_price_option((i, n_paths)) for i in option_indices]
+    else:
+        import multiprocessing as mp
+
+        with mp.get_context("fork").Pool(processes) as pool:
+            prices = pool.map(_cpu_price_option, [(i, n_paths) for i in option_indices])
+    return time.perf_counter() - t0, np.array(prices)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    n_paths = 100_000
+    per_step = procs * 2  # options per timed step: two per worker
+    idx = list(np.linspace(0, N_OPT - 1, per_step).astype(int))
+    for _ in range(args.warmup):
+        cpu_sample(idx[:procs], 2_000, procs)
+    total_t = 0.0
+    for _ in range(args.steps):
+        t, _ = cpu_sample(idx, n_paths, procs)
+        total_t += t
+    work = per_step * n_paths * N_STEPS * args.steps
+    value = work / total_t
+    sample = (f"{per_step} grid options x {n_paths} paths x {N_STEPS} steps per step, NumPy restatement of "
+              f"simulate_gbm_numpy+payoff (oracle/reference_mc.py), one process per core over options")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_engine_arm(args):
+    import torch
+
+    from optionslab_b200 import MonteCarloPricerUni, _ffi, distributed
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run --nproc-per-node N")
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    import torch.distributed as dist
+
+    ctx = distributed.init(backend="nccl") if world > 1 else None
+    eng = _ffi.get_engine(local)
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream(dev)
+
+    g = grid_params()
+    params_np = _ffi.make_params(g["S"], g["K"], g["T"], g["r"], g["sigma"], g["q"]).reshape(N_OPT, 1)
+    params_dev = torch.from_numpy(params_np.view(np.float64).reshape(N_OPT, 8).copy()).to(dev)
+    out_dev = torch.zeros((N_OPT, 3), dtype=torch.float64, device=dev)
+    spec = _ffi.make_spec(_ffi.EUROPEAN, N_STEPS, antithetic=True)
+    begin, count = distributed.partition_paths(N_PATHS, rank, world)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def device_step():
+        flush.zero_()
+        eng.simulate_device(spec, params_dev.data_ptr(), N_OPT, 1, SEED, count, out_dev.data_ptr(), stream.cuda_stream,
+                            path_begin=begin)
+        if world > 1:
+            dist.all_reduce(out_dev)
+
+    peaks = eng.measure_peaks() if rank == 0 else None
+
+    # ---- value: inputs resident in HBM, device-timed ------------------------------------------------
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    eng.set_kernel_timing(True)
+    launches0 = eng.kernel_launches()
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        device_step()
+    ev1.record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    elapsed = torch.tensor([ev0.elapsed_time(ev1) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    elapsed_s = float(elapsed.item())
+    launches = eng.kernel_launches() - launches0 + args.steps  # + the L2-flush memset kernel per step
+    ktime = eng.kernel_timing()
+    eng.set_kernel_timing(False)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    moments = out_dev.cpu().numpy()
+    work_per_step = float(N_OPT) * N_PATHS * N_STEPS
+    value = work_per_step * args.steps / elapsed_s
+
+    # ---- e2e: the public API, host buffers in, host prices out ---------------------------------------
+    pricer = MonteCarloPricerUni(num_simulations=N_PATHS, num_steps=N_STEPS, seed=SEED)
+    e2e_steps = max(1, min(args.steps, 3))
+    prices = pricer.price_batch(g["S"], g["K"], g["T"], g["r"], g["sigma"], "call", g["q"])  # warm-up (pinned buffers)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        prices = pricer.price_batch(g["S"], g["K"], g["T"], g["r"], g["sigma"], "call", g["q"])
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = work_per_step * e2e_steps / float(e2e_t.item())
+
+    if rank == 0:
+        # sanity: the timed run produced prices (checked against Black-Scholes within 4 standard errors)
+        from optionslab_b200 import runtime
+
+        m = moments.view(_ffi.MOMENTS_DTYPE).reshape(N_OPT)
+        dev_prices = runtime.discounted_price(m, g["r"], g["T"])
+        se = runtime.discounted_std_error(m, g["r"], g["T"])
+        from oracle import reference_mc as orc  # checker only
+
+        bs = np.array([orc.black_scholes(g["S"][i], g["K"][i], g["T"][i], g["r"][i], g["sigma"][i], "call") for i in range(N_OPT)])
+        z = (dev_prices - bs) / se
+        ok = bool(np.all(np.abs(z) < 5.0) and np.allclose(prices, dev_prices, rtol=1e-9))
+
+        kernel_s = ktime["mean_ms"] * 1e-3
+        per_gpu_steps = work_per_step / world
+        kernel_rate = per_gpu_steps / kernel_s  # path-steps/s of ONE GPU inside the kernel
+        mufu_frac = kernel_rate * MUFU_PER_STEP / peaks["mufu_per_s"]
+        issue_frac = kernel_rate * INSTR_PER_STEP / peaks["issue_per_s"]
+        hbm_bytes = N_OPT * (64 + 24)  # algorithmic HBM traffic per launch: parameter block in, moments out
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            hbm_src = "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        bound = "xu" if mufu_frac >= issue_frac else "issue"
+        roofline = {
+            "bound": bound,
+            "kernel": "european_kernel<NS=1,ANTI,ILP=2>",
+            "kernel_ms": ktime["mean_ms"], "kernel_ms_min": ktime["min_ms"], "kernels_timed": ktime["count"],
+            "achieved": kernel_rate * (MUFU_PER_STEP if bound == "xu" else INSTR_PER_STEP),
+            "peak": peaks["mufu_per_s"] if bound == "xu" else peaks["issue_per_s"],
+            "unit": "MUFU op/s" if bound == "xu" else "thread-instr/s",
+            "frac": max(mufu_frac, issue_frac),
+            "peak_source": "measured live by b200mc_measure_peaks on this GPU (pipe microbenchmarks)",
+            "per_path_step": {"instructions": INSTR_PER_STEP, "mufu": MUFU_PER_STEP, "imad_wide": IMAD_PER_STEP, "lop3": LOP_PER_STEP},
+            "xu_frac": mufu_frac, "issue_frac": issue_frac,
+            "imad_frac": kernel_rate * IMAD_PER_STEP / peaks["imad_wide_per_s"],
+            "alu_frac": kernel_rate * (LOP_PER_STEP + 1.0) / peaks["lop3_per_s"],
+            "vs_rng_only_probe": kernel_rate / peaks["normals_per_s"],
+            "traffic": None,
+            "hbm": {"achieved_gbs": hbm_bytes / kernel_s / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
+                    "frac": hbm_bytes / kernel_s / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": hbm_bytes},
+            "pipe_peaks": peaks,
+        }
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            idx = list(np.linspace(0, N_OPT - 1, 8).astype(int))
+            cpu_sample(idx[:1], 2_000, 1)
+            t_cpu, cpu_prices = cpu_sample(idx, 100_000, 1)
+            cpu = {"value": len(idx) * 100_000 * N_STEPS / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"{len(idx)} grid options x 100000 paths x {N_STEPS} steps, NumPy restatement of the reference "
+                             f"(oracle/reference_mc.py; NumPy's generator is single-threaded), host has {cores} cores",
+                   "seconds": t_cpu,
+                   "max_abs_price_diff_vs_gpu": float(np.max(np.abs(cpu_prices - dev_prices[idx])))}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * elapsed_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_options": N_OPT, "paths_per_option": N_PATHS, "steps_per_path": N_STEPS,
+                       "parallelism": f"paths partitioned over {world} rank(s), one all-reduce of {N_OPT}x3 doubles per step",
+                       "l2": "256 MiB memset between steps (inside the timed region); the kernel's HBM input is 262 KB"},
+            "options_per_sec": N_OPT * args.steps / elapsed_s,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(params_np.nbytes),
+                    "d2h_bytes_per_step": int(N_OPT * 24), "steps": e2e_steps, "api": "MonteCarloPricerUni.price_batch (numpy in/out)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "prices_ok": ok, "max_abs_z_vs_black_scholes": float(np.max(np.abs(z))),
+        }
+        print(json.dumps(line))
+    if ctx is not None:
+        distributed.shutdown()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["engine", "reference"], default="engine")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_engine_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

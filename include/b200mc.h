@@ -1,0 +1,168 @@
+/* b200mc — C ABI of the B200-native Monte Carlo pricing engine (libb200mc.so).
+ *
+ * This is the drop-in boundary for OptionsLab's Monte Carlo hot path.  The reference is pure
+ * Python and has no FFI of its own; its boundary is the duck-typed pricer interface
+ *   PricerProtocol.price(S, K, T, r, sigma, option_type, q=0.0, **kw)   src/greeks/unified_greeks.py:45-66
+ * plus the concrete classes behind it.  The Python classes in optionslab_b200/ mirror those classes
+ * and call ONLY the functions declared here (ctypes; see INTEGRATION.md for the binding stub a
+ * reference maintainer would add).  Each entry point names the reference computation it replaces.
+ *
+ * Conventions: plain pointers and sizes, no C++ / torch types.  Every function returns 0 on
+ * success or a negative b200mc_status; the message is available from b200mc_last_error().  The
+ * library owns all device scratch memory; the caller owns every buffer it passes in.  "host"
+ * entry points block until results are in the caller's host buffers; "_device" entry points take
+ * device pointers plus a cudaStream_t (as void*) and are asynchronous on that stream.
+ */
+#ifndef B200MC_H_
+#define B200MC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MC_ABI_VERSION 1
+#define B200MC_MAX_SCENARIOS 16
+
+typedef struct b200mc_engine b200mc_engine_t;
+
+typedef enum {
+  B200MC_OK = 0,
+  B200MC_ERR_INVALID = -1, /* bad argument (null pointer, zero size, unknown kind, ...) */
+  B200MC_ERR_CUDA = -2,    /* CUDA runtime failure; message has the cudaError string */
+  B200MC_ERR_NOMEM = -4    /* device or pinned-host allocation failed */
+} b200mc_status;
+
+/* Payoff families on the hot path. */
+typedef enum {
+  B200MC_EUROPEAN = 0,    /* terminal payoff;  src/pricing_models/monte_carlo.py:140-143 */
+  B200MC_ASIAN_ARITH = 1, /* mean of S_t, t=1..n;  src/pricing_models/exotic_options.py:119-120 */
+  B200MC_ASIAN_GEOM = 2,  /* exp(mean(log S_t));   src/pricing_models/exotic_options.py:121-122 */
+  B200MC_BARRIER = 3,     /* any(S_t >= B) / any(S_t <= B), t=0..n;  exotic_options.py:201-212 */
+  B200MC_LOOKBACK = 4     /* running max / min, t=0..n;  exotic_options.py:382-399 */
+} b200mc_kind;
+
+typedef struct {
+  int32_t kind;           /* b200mc_kind */
+  int32_t is_put;         /* 0 call, 1 put */
+  int32_t antithetic;     /* 1: each draw also prices the mirrored path (-Z), as gbm_numpy.py:48-51.
+                             Only B200MC_EUROPEAN supports it (the reference's exotics do not mirror). */
+  int32_t barrier_down;   /* BARRIER: 0 = up (S_t >= B), 1 = down (S_t <= B) */
+  int32_t barrier_in;     /* BARRIER: 0 = knock-out, 1 = knock-in */
+  int32_t lookback_fixed; /* LOOKBACK: 0 = floating strike, 1 = fixed strike */
+  uint32_t n_steps;       /* time steps per path (>= 1) */
+  uint32_t reserved;
+} b200mc_spec_t;
+
+/* One (option, scenario) parameter set, FP64.  Scenarios of an option share its normal draws
+ * (common random numbers) — the bumped re-pricings of src/greeks/unified_greeks.py:295-358. */
+typedef struct {
+  double S, K, T, r, sigma, q;
+  double barrier; /* BARRIER only */
+  double reserved;
+} b200mc_params_t;
+
+/* Raw FP64 payoff moments of one (option, scenario): sum over samples of the UNDISCOUNTED payoff,
+ * of its square, and the sample count (2x paths when antithetic).  The host applies exp(-rT), the
+ * mean, the standard error (monte_carlo.py:145-150) and the finite-difference formulas. */
+typedef struct {
+  double sum, sum_sq, n;
+} b200mc_moments_t;
+
+typedef struct {
+  int32_t device;
+  int32_t sm_count;
+  int32_t cc_major, cc_minor;
+  int32_t sm_clock_khz;  /* cudaDevAttrClockRate */
+  int32_t mem_clock_khz;
+  int64_t total_mem_bytes;
+  int32_t l2_bytes;
+  int32_t reserved;
+  char name[64];
+} b200mc_info_t;
+
+/* Pipe-rate microbenchmarks, measured on the device the engine owns (thread-level ops / second).
+ * These are the roofline denominators for the issue/XU-bound simulation kernels. */
+typedef struct {
+  double ffma_per_s;      /* FP32 FMA, 3-register form */
+  double imad_wide_per_s; /* 32x32->64 integer multiply (the Philox multiply) */
+  double lop3_per_s;      /* 3-input logic op */
+  double mufu_per_s;      /* MUFU mix used by the generator (lg2, sqrt, sin, cos) */
+  double mufu_ex2_per_s;
+  double issue_per_s;     /* mixed independent FFMA+LOP3 stream: warp-instruction issue ceiling x 32 */
+  double philox_per_s;    /* Philox4x32-10 calls / s, counter mode, nothing else */
+  double normals_per_s;   /* Philox + Box-Muller normals / s, summed in registers, nothing else */
+  double sm_clock_mhz_seen; /* clock64()-derived average SM clock while the probes ran */
+  double reserved[3];
+} b200mc_peaks_t;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int b200mc_abi_version(void);
+int b200mc_create(b200mc_engine_t** out, int device);
+void b200mc_destroy(b200mc_engine_t* eng);
+/* Message of the last failed call on this engine (eng == NULL: last failed b200mc_create). */
+const char* b200mc_last_error(const b200mc_engine_t* eng);
+int b200mc_device_info(b200mc_engine_t* eng, b200mc_info_t* out);
+
+/* ---- the hot path: fused Philox -> GBM -> payoff -> (sum, sum^2) ----------------------------- *
+ * Replaces, per option i and scenario k:  simulate_gbm_numpy + payoff + mean/std
+ * (src/simulation/gbm_numpy.py:32-53, src/pricing_models/monte_carlo.py:140-150), the batched
+ * variant (src/pricing_models/monte_carlo_unified.py:321-343,622-631) and the exotic path
+ * generator + payoff (src/pricing_models/exotic_options.py:54-67,116-131,198-224,380-401).
+ *
+ * params  : [n_opt][n_scen] (row-major), 1 <= n_scen <= B200MC_MAX_SCENARIOS
+ * seed    : Philox key.  Option i draws from stream (stream_base + i); all its scenarios share it.
+ * paths   : global path indices [path_begin, path_begin + n_paths) — disjoint ranges on different
+ *           ranks give disjoint Philox subsequences; results depend only on the index range.
+ * out     : [n_opt][n_scen] moments.
+ */
+int b200mc_simulate(b200mc_engine_t* eng, const b200mc_spec_t* spec, const b200mc_params_t* params_host,
+                    uint32_t n_opt, uint32_t n_scen, uint64_t seed, uint32_t stream_base,
+                    uint64_t path_begin, uint64_t n_paths, b200mc_moments_t* out_host);
+
+int b200mc_simulate_device(b200mc_engine_t* eng, const b200mc_spec_t* spec, const b200mc_params_t* params_dev,
+                           uint32_t n_opt, uint32_t n_scen, uint64_t seed, uint32_t stream_base,
+                           uint64_t path_begin, uint64_t n_paths, b200mc_moments_t* out_dev,
+                           void* cuda_stream);
+
+/* ---- FP64 parity mode: price from caller-supplied normal draws ------------------------------- *
+ * Z is row-major [n_paths][spec->n_steps] FP64 — exactly the array the reference draws at
+ * gbm_numpy.py:43 / monte_carlo_unified.py:329 (one option) / exotic_options.py:59.
+ * accumulate = 0: log S_T = ln S + drift*n + vol*sum(Z)            (gbm_numpy.py:46-50)
+ * accumulate = 1: log S_t = ln S + running sum of (drift + vol*Z)   (monte_carlo_unified.py:333-337,
+ *                 exotic_options.py:62-65); forced for path-dependent kinds.
+ * payoffs : per-path undiscounted payoffs; [0,N) from +Z and, when spec->antithetic, [N,2N) from -Z
+ *           (the reference's concatenate layout, gbm_numpy.py:51).  May be NULL.
+ * out     : moments over all samples (fixed-order FP64 tree; deterministic).
+ */
+int b200mc_payoffs_from_normals(b200mc_engine_t* eng, const b200mc_spec_t* spec, const b200mc_params_t* p,
+                                int accumulate, const double* Z_host, uint64_t n_paths,
+                                double* payoffs_host, b200mc_moments_t* out_host);
+
+int b200mc_payoffs_from_normals_device(b200mc_engine_t* eng, const b200mc_spec_t* spec, const b200mc_params_t* p,
+                                       int accumulate, const double* Z_dev, uint64_t n_paths,
+                                       double* payoffs_dev, b200mc_moments_t* out_dev, void* cuda_stream);
+
+/* ---- inspection of the random stream (tests / diagnostics) ----------------------------------- */
+/* out_host[(p - path_begin) * n_steps + s] = the FP32 standard normal the simulation kernels use
+ * for step s of global path p of (seed, stream). */
+int b200mc_generate_normals(b200mc_engine_t* eng, uint64_t seed, uint32_t stream, uint64_t path_begin,
+                            uint64_t n_paths, uint32_t n_steps, float* out_host);
+/* Raw Philox4x32-10: in = n x {c0,c1,c2,c3,k0,k1}, out = n x 4 words (known-answer tests). */
+int b200mc_philox_raw(b200mc_engine_t* eng, const uint32_t* ctr_key_host, uint32_t n, uint32_t* out_host);
+
+/* ---- measurement ------------------------------------------------------------------------------ */
+int b200mc_measure_peaks(b200mc_engine_t* eng, b200mc_peaks_t* out);
+/* Kernels launched by this engine since creation (the caller's gpu_launches evidence). */
+uint64_t b200mc_kernel_launches(const b200mc_engine_t* eng);
+/* When enabled, every simulation / from-normals kernel is bracketed by a CUDA event pair on the
+ * stream it is launched on (a ring of 64 pairs; enabling resets it).  b200mc_kernel_timing waits for
+ * the recorded kernels and returns their mean and minimum duration and how many were timed. */
+int b200mc_set_kernel_timing(b200mc_engine_t* eng, int enabled);
+int b200mc_kernel_timing(b200mc_engine_t* eng, float* mean_ms, float* min_ms, int32_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MC_H_ */

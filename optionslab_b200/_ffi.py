@@ -1,0 +1,245 @@
+"""ctypes binding of libb200mc.so (include/b200mc.h) — the only gateway to the GPU.
+
+There is deliberately no fallback: if the shared library is missing, cannot be loaded, or no
+sm_100 device is present, ``AccelerationError`` is raised.  Nothing here imports ``oracle``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional
+
+import numpy as np
+
+from .exceptions import AccelerationError, MonteCarloError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200mc.so")
+ABI_VERSION = 1
+MAX_SCENARIOS = 16
+
+EUROPEAN, ASIAN_ARITH, ASIAN_GEOM, BARRIER, LOOKBACK = range(5)
+
+
+class Spec(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("is_put", C.c_int32), ("antithetic", C.c_int32),
+                ("barrier_down", C.c_int32), ("barrier_in", C.c_int32), ("lookback_fixed", C.c_int32),
+                ("n_steps", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class Info(C.Structure):
+    _fields_ = [("device", C.c_int32), ("sm_count", C.c_int32), ("cc_major", C.c_int32), ("cc_minor", C.c_int32),
+                ("sm_clock_khz", C.c_int32), ("mem_clock_khz", C.c_int32), ("total_mem_bytes", C.c_int64),
+                ("l2_bytes", C.c_int32), ("reserved", C.c_int32), ("name", C.c_char * 64)]
+
+
+class Peaks(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("ffma_per_s", "imad_wide_per_s", "lop3_per_s", "mufu_per_s", "mufu_ex2_per_s",
+                                          "issue_per_s", "philox_per_s", "normals_per_s", "sm_clock_mhz_seen")] + \
+               [("reserved", C.c_double * 3)]
+
+
+PARAMS_DTYPE = np.dtype([("S", "f8"), ("K", "f8"), ("T", "f8"), ("r", "f8"), ("sigma", "f8"), ("q", "f8"),
+                         ("barrier", "f8"), ("reserved", "f8")])
+MOMENTS_DTYPE = np.dtype([("sum", "f8"), ("sum_sq", "f8"), ("n", "f8")])
+
+# name -> (restype, argtypes); also the list the CPU tests check the .so exports against the header.
+_P = C.c_void_p
+SIGNATURES = {
+    "b200mc_abi_version": (C.c_int, []),
+    "b200mc_create": (C.c_int, [C.POINTER(_P), C.c_int]),
+    "b200mc_destroy": (None, [_P]),
+    "b200mc_last_error": (C.c_char_p, [_P]),
+    "b200mc_device_info": (C.c_int, [_P, C.POINTER(Info)]),
+    "b200mc_simulate": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
+                                  C.c_uint64, C.c_uint64, _P]),
+    "b200mc_simulate_device": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
+                                         C.c_uint64, C.c_uint64, _P, _P]),
+    "b200mc_payoffs_from_normals": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_int, _P, C.c_uint64, _P, _P]),
+    "b200mc_payoffs_from_normals_device": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_int, _P, C.c_uint64, _P, _P, _P]),
+    "b200mc_generate_normals": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, _P]),
+    "b200mc_philox_raw": (C.c_int, [_P, _P, C.c_uint32, _P]),
+    "b200mc_measure_peaks": (C.c_int, [_P, C.POINTER(Peaks)]),
+    "b200mc_kernel_launches": (C.c_uint64, [_P]),
+    "b200mc_set_kernel_timing": (C.c_int, [_P, C.c_int]),
+    "b200mc_kernel_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen libb200mc.so and type its entry points.  Raises AccelerationError if it is absent."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise AccelerationError(
+                f"{LIB_PATH} is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)", backend="cuda")
+        try:
+            lib = C.CDLL(LIB_PATH)
+        except OSError as exc:
+            raise AccelerationError(f"cannot load {LIB_PATH}: {exc}", backend="cuda") from exc
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if lib.b200mc_abi_version() != ABI_VERSION:
+            raise AccelerationError(f"libb200mc ABI {lib.b200mc_abi_version()} != expected {ABI_VERSION}", backend="cuda")
+        _lib = lib
+        return lib
+
+
+def make_spec(kind: int, n_steps: int, *, is_put=False, antithetic=False, barrier_down=False, barrier_in=False,
+              lookback_fixed=False) -> Spec:
+    return Spec(int(kind), int(bool(is_put)), int(bool(antithetic)), int(bool(barrier_down)), int(bool(barrier_in)),
+                int(bool(lookback_fixed)), int(n_steps), 0)
+
+
+def make_params(S, K, T, r, sigma, q=0.0, barrier=0.0) -> np.ndarray:
+    """Broadcast the arguments into a PARAMS_DTYPE array (any common shape)."""
+    arrs = np.broadcast_arrays(*(np.asarray(x, dtype=np.float64) for x in (S, K, T, r, sigma, q, barrier)))
+    out = np.zeros(arrs[0].shape, dtype=PARAMS_DTYPE)
+    for name, a in zip(("S", "K", "T", "r", "sigma", "q", "barrier"), arrs):
+        out[name] = a
+    return out
+
+
+class Engine:
+    """One device-side engine handle.  Thread-safe (the C side serialises calls per handle)."""
+
+    def __init__(self, device: Optional[int] = None):
+        self._lib = load_library()
+        if device is None:
+            device = int(os.environ.get("B200MC_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        self.device = int(device)
+        h = _P()
+        rc = self._lib.b200mc_create(C.byref(h), self.device)
+        if rc != 0:
+            msg = self._lib.b200mc_last_error(None).decode()
+            raise AccelerationError(f"b200mc_create({self.device}) failed: {msg}", backend="cuda")
+        self._h = h
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200mc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self._lib.b200mc_last_error(self._h).decode()
+            if rc == -1:
+                raise MonteCarloError(f"{what}: {msg}")
+            raise AccelerationError(f"{what}: {msg}", backend="cuda")
+
+    # -- queries ----------------------------------------------------------------------------
+    def info(self) -> dict:
+        out = Info()
+        self._check(self._lib.b200mc_device_info(self._h, C.byref(out)), "b200mc_device_info")
+        d = {f: getattr(out, f) for f, _ in Info._fields_ if f not in ("reserved", "name")}
+        d["name"] = out.name.decode()
+        return d
+
+    def kernel_launches(self) -> int:
+        return int(self._lib.b200mc_kernel_launches(self._h))
+
+    def set_kernel_timing(self, enabled: bool):
+        self._check(self._lib.b200mc_set_kernel_timing(self._h, int(enabled)), "b200mc_set_kernel_timing")
+
+    def kernel_timing(self) -> dict:
+        """Mean / min duration (ms) and count of the simulation kernels timed since set_kernel_timing(True)."""
+        mean, best, n = C.c_float(), C.c_float(), C.c_int32()
+        self._check(self._lib.b200mc_kernel_timing(self._h, C.byref(mean), C.byref(best), C.byref(n)), "b200mc_kernel_timing")
+        return {"mean_ms": float(mean.value), "min_ms": float(best.value), "count": int(n.value)}
+
+    def measure_peaks(self) -> dict:
+        out = Peaks()
+        self._check(self._lib.b200mc_measure_peaks(self._h, C.byref(out)), "b200mc_measure_peaks")
+        return {f: getattr(out, f) for f, _ in Peaks._fields_ if f != "reserved"}
+
+    # -- hot path ---------------------------------------------------------------------------
+    def simulate(self, spec: Spec, params: np.ndarray, seed: int, n_paths: int, *, stream_base: int = 0,
+                 path_begin: int = 0) -> np.ndarray:
+        """params: PARAMS_DTYPE array [n_opt, n_scen] -> MOMENTS_DTYPE array [n_opt, n_scen] (host buffers)."""
+        params = np.ascontiguousarray(params, dtype=PARAMS_DTYPE)
+        if params.ndim != 2:
+            raise MonteCarloError("params must have shape [n_opt, n_scen]")
+        out = np.empty(params.shape, dtype=MOMENTS_DTYPE)
+        rc = self._lib.b200mc_simulate(self._h, C.byref(spec), params.ctypes.data, params.shape[0], params.shape[1],
+                                       int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF,
+                                       int(path_begin), int(n_paths), out.ctypes.data)
+        self._check(rc, "b200mc_simulate")
+        return out
+
+    def simulate_device(self, spec: Spec, params_ptr: int, n_opt: int, n_scen: int, seed: int, n_paths: int, out_ptr: int,
+                        cuda_stream: int, *, stream_base: int = 0, path_begin: int = 0):
+        """Asynchronous variant on raw device pointers (params / moments already in HBM)."""
+        rc = self._lib.b200mc_simulate_device(self._h, C.byref(spec), params_ptr, n_opt, n_scen,
+                                              int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF,
+                                              int(path_begin), int(n_paths), out_ptr, cuda_stream)
+        self._check(rc, "b200mc_simulate_device")
+
+    # -- FP64 parity mode -------------------------------------------------------------------
+    def payoffs_from_normals(self, spec: Spec, params: np.ndarray, Z: np.ndarray, *, accumulate: bool = False,
+                             want_payoffs: bool = True):
+        Z = np.ascontiguousarray(Z, dtype=np.float64)
+        if Z.ndim != 2 or Z.shape[1] != spec.n_steps:
+            raise MonteCarloError("Z must have shape [n_paths, n_steps]")
+        p = np.ascontiguousarray(params, dtype=PARAMS_DTYPE).reshape(-1)
+        if p.size != 1:
+            raise MonteCarloError("parity mode prices one parameter set per call")
+        n_paths = Z.shape[0]
+        pay = np.empty(n_paths * (2 if spec.antithetic else 1), dtype=np.float64) if want_payoffs else None
+        mom = np.empty(1, dtype=MOMENTS_DTYPE)
+        rc = self._lib.b200mc_payoffs_from_normals(self._h, C.byref(spec), p.ctypes.data, int(accumulate), Z.ctypes.data,
+                                                   n_paths, pay.ctypes.data if want_payoffs else None, mom.ctypes.data)
+        self._check(rc, "b200mc_payoffs_from_normals")
+        return pay, mom[0]
+
+    def payoffs_from_normals_device(self, spec: Spec, params: np.ndarray, Z_ptr: int, n_paths: int, payoffs_ptr: int,
+                                    out_ptr: int, cuda_stream: int, *, accumulate: bool = False):
+        p = np.ascontiguousarray(params, dtype=PARAMS_DTYPE).reshape(-1)
+        rc = self._lib.b200mc_payoffs_from_normals_device(self._h, C.byref(spec), p.ctypes.data, int(accumulate), Z_ptr,
+                                                          n_paths, payoffs_ptr, out_ptr, cuda_stream)
+        self._check(rc, "b200mc_payoffs_from_normals_device")
+
+    # -- stream inspection ------------------------------------------------------------------
+    def generate_normals(self, seed: int, n_paths: int, n_steps: int, *, stream: int = 0, path_begin: int = 0) -> np.ndarray:
+        out = np.empty((n_paths, n_steps), dtype=np.float32)
+        rc = self._lib.b200mc_generate_normals(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, stream, path_begin, n_paths, n_steps,
+                                               out.ctypes.data)
+        self._check(rc, "b200mc_generate_normals")
+        return out
+
+    def philox_raw(self, ctr_key: np.ndarray) -> np.ndarray:
+        ck = np.ascontiguousarray(ctr_key, dtype=np.uint32).reshape(-1, 6)
+        out = np.empty((ck.shape[0], 4), dtype=np.uint32)
+        self._check(self._lib.b200mc_philox_raw(self._h, ck.ctypes.data, ck.shape[0], out.ctypes.data), "b200mc_philox_raw")
+        return out
+
+
+_engines = {}
+_engines_lock = threading.Lock()
+
+
+def get_engine(device: Optional[int] = None) -> Engine:
+    """Process-wide engine per device (created on first use)."""
+    if device is None:
+        device = int(os.environ.get("B200MC_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _engines_lock:
+        eng = _engines.get(device)
+        if eng is None or eng._h is None:
+            eng = _engines[device] = Engine(device)
+        return eng

@@ -1,0 +1,531 @@
+// libb200mc.so — C ABI (include/b200mc.h) over the sm_100a simulation kernels.
+//
+// One engine = one device + one stream + scratch (tile partials, staged parameters, pinned host
+// mirrors).  No exceptions cross the boundary; every failure becomes a status code plus a message.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b200mc.h"
+#include "f64_kernels.cuh"
+#include "mc_kernels.cuh"
+#include "peaks.cuh"
+
+using namespace b200mc;
+
+namespace {
+
+std::mutex g_create_mutex;
+std::string g_create_error;
+
+struct DeviceBuffer {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct b200mc_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaDeviceProp prop{};
+  std::string error;
+  std::mutex mutex;  // one call at a time per engine (the reference's pricer objects are single-threaded too)
+  DeviceBuffer partials, params_dev, moments_dev, scratch_a, scratch_b;
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  uint64_t launches = 0;
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // scratch pair for the probes
+  static constexpr int kRing = 64;
+  cudaEvent_t ring0[kRing] = {}, ring1[kRing] = {};
+  uint64_t timed = 0;  // kernels timed since timing was enabled
+};
+
+namespace {
+
+int fail(b200mc_engine* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) e->error = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+#define CU_TRY(e, call)                                                                              \
+  do {                                                                                               \
+    cudaError_t err__ = (call);                                                                      \
+    if (err__ != cudaSuccess)                                                                        \
+      return fail(e, err__ == cudaErrorMemoryAllocation ? B200MC_ERR_NOMEM : B200MC_ERR_CUDA,         \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__);    \
+  } while (0)
+
+int reserve(b200mc_engine* e, DeviceBuffer& b, size_t bytes) {
+  if (b.bytes >= bytes) return 0;
+  if (b.ptr) {
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    CU_TRY(e, cudaFree(b.ptr));
+    b.ptr = nullptr, b.bytes = 0;
+  }
+  const size_t want = std::max(bytes, (size_t)1 << 16);
+  CU_TRY(e, cudaMalloc(&b.ptr, want));
+  b.bytes = want;
+  return 0;
+}
+
+int reserve_pinned(b200mc_engine* e, size_t bytes) {
+  if (e->pinned_bytes >= bytes) return 0;
+  if (e->pinned) {
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    CU_TRY(e, cudaFreeHost(e->pinned));
+    e->pinned = nullptr, e->pinned_bytes = 0;
+  }
+  const size_t want = std::max(bytes, (size_t)1 << 16);
+  CU_TRY(e, cudaMallocHost(&e->pinned, want));
+  e->pinned_bytes = want;
+  return 0;
+}
+
+int check_spec(b200mc_engine* e, const b200mc_spec_t* s) {
+  if (!s) return fail(e, B200MC_ERR_INVALID, "spec is null");
+  if (s->kind < B200MC_EUROPEAN || s->kind > B200MC_LOOKBACK) return fail(e, B200MC_ERR_INVALID, "unknown payoff kind %d", s->kind);
+  if (s->n_steps == 0) return fail(e, B200MC_ERR_INVALID, "n_steps must be >= 1");
+  if (s->antithetic && s->kind != B200MC_EUROPEAN)
+    return fail(e, B200MC_ERR_INVALID, "antithetic mirroring is only defined for the European payoff");
+  return 0;
+}
+
+uint32_t pad_scenarios(uint32_t n) {
+  uint32_t p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+// Tile shape: enough CTAs to fill 148 SMs x 8 resident CTAs for ~4 waves when the problem allows,
+// at most kMaxPathsPerThread paths per thread, evenly spread so the last tile is not ragged-heavy.
+void plan_tiles(const b200mc_engine* e, uint32_t n_opt, uint64_t n_paths, uint32_t& tiles, uint32_t& ppt) {
+  const uint64_t want_ctas = (uint64_t)e->prop.multiProcessorCount * 8 * 4;
+  const uint64_t want_tiles = std::max<uint64_t>(1, (want_ctas + n_opt - 1) / n_opt);
+  uint64_t p = n_paths / ((uint64_t)kBlock * want_tiles);
+  p = std::min<uint64_t>(std::max<uint64_t>(p, 1), kMaxPathsPerThread);
+  const uint64_t t = (n_paths + (uint64_t)kBlock * p - 1) / ((uint64_t)kBlock * p);
+  p = (n_paths + (uint64_t)kBlock * t - 1) / ((uint64_t)kBlock * t);
+  tiles = (uint32_t)t;
+  ppt = (uint32_t)p;
+}
+
+template <int NS>
+cudaError_t launch_european(const SimArgs& a, bool anti, dim3 grid, cudaStream_t s) {
+  if (anti) european_kernel<NS, true, 2><<<grid, kBlock, 0, s>>>(a);
+  else european_kernel<NS, false, 2><<<grid, kBlock, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <int KIND>
+cudaError_t launch_pathdep(const SimArgs& a, uint32_t ns, dim3 grid, cudaStream_t s) {
+  switch (ns) {
+    case 1: pathdep_kernel<KIND, 1><<<grid, kBlock, 0, s>>>(a); break;
+    case 2: pathdep_kernel<KIND, 2><<<grid, kBlock, 0, s>>>(a); break;
+    case 4: pathdep_kernel<KIND, 4><<<grid, kBlock, 0, s>>>(a); break;
+    case 8: pathdep_kernel<KIND, 8><<<grid, kBlock, 0, s>>>(a); break;
+    default: pathdep_kernel<KIND, 16><<<grid, kBlock, 0, s>>>(a); break;
+  }
+  return cudaGetLastError();
+}
+
+// Enqueue simulation + fold on `stream`; params/out are device pointers.
+int enqueue_simulation(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc_params_t* params_dev, uint32_t n_opt,
+                       uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
+                       b200mc_moments_t* out_dev, cudaStream_t stream, bool time_it) {
+  if (int rc = check_spec(e, spec)) return rc;
+  if (!params_dev || !out_dev) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
+  if (n_opt == 0 || n_paths == 0) return fail(e, B200MC_ERR_INVALID, "n_opt and n_paths must be >= 1");
+  if (n_scen == 0 || n_scen > B200MC_MAX_SCENARIOS)
+    return fail(e, B200MC_ERR_INVALID, "n_scen must be in [1, %d]", B200MC_MAX_SCENARIOS);
+
+  const uint32_t ns = pad_scenarios(n_scen);
+  uint32_t tiles, ppt;
+  plan_tiles(e, n_opt, n_paths, tiles, ppt);
+  const uint64_t ctas = (uint64_t)tiles * n_opt;
+  if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
+  if (int rc = reserve(e, e->partials, ctas * 2 * ns * sizeof(double))) return rc;
+
+  SimArgs a{};
+  a.params = params_dev;
+  a.partials = (double*)e->partials.ptr;
+  a.path_begin = path_begin;
+  a.n_paths = n_paths;
+  a.n_opt = n_opt;
+  a.n_scen = n_scen;
+  a.tiles = tiles;
+  a.paths_per_thread = ppt;
+  a.n_steps = spec->n_steps;
+  a.seed_lo = (uint32_t)seed;
+  a.seed_hi = (uint32_t)(seed >> 32);
+  a.stream_base = stream_base;
+  a.is_put = spec->is_put;
+  a.barrier_in = spec->barrier_in;
+  a.lookback_fixed = spec->lookback_fixed;
+  // which extremum the path-dependent kernels track (they follow sgn * log2(S_t/S_0) and keep its max)
+  a.sgn_negative = 0;
+  if (spec->kind == B200MC_BARRIER) a.sgn_negative = spec->barrier_down ? 1 : 0;
+  if (spec->kind == B200MC_LOOKBACK) a.sgn_negative = (spec->lookback_fixed ? spec->is_put : !spec->is_put) ? 1 : 0;
+
+  const dim3 grid((unsigned)ctas);
+  const int slot = (int)(e->timed % b200mc_engine::kRing);
+  if (time_it) CU_TRY(e, cudaEventRecord(e->ring0[slot], stream));
+  cudaError_t err = cudaSuccess;
+  switch (spec->kind) {
+    case B200MC_EUROPEAN:
+      switch (ns) {
+        case 1: err = launch_european<1>(a, spec->antithetic, grid, stream); break;
+        case 2: err = launch_european<2>(a, spec->antithetic, grid, stream); break;
+        case 4: err = launch_european<4>(a, spec->antithetic, grid, stream); break;
+        case 8: err = launch_european<8>(a, spec->antithetic, grid, stream); break;
+        default: err = launch_european<16>(a, spec->antithetic, grid, stream); break;
+      }
+      break;
+    case B200MC_ASIAN_ARITH: err = launch_pathdep<B200MC_ASIAN_ARITH>(a, ns, grid, stream); break;
+    case B200MC_ASIAN_GEOM: err = launch_pathdep<B200MC_ASIAN_GEOM>(a, ns, grid, stream); break;
+    case B200MC_BARRIER: err = launch_pathdep<B200MC_BARRIER>(a, ns, grid, stream); break;
+    case B200MC_LOOKBACK: err = launch_pathdep<B200MC_LOOKBACK>(a, ns, grid, stream); break;
+  }
+  if (err != cudaSuccess) return fail(e, B200MC_ERR_CUDA, "simulation kernel launch failed: %s", cudaGetErrorString(err));
+  if (time_it) {
+    CU_TRY(e, cudaEventRecord(e->ring1[slot], stream));
+    e->timed += 1;
+  }
+  const double samples = (double)n_paths * (spec->antithetic ? 2.0 : 1.0);
+  fold_kernel<<<n_opt * n_scen, 32, 0, stream>>>((const double*)e->partials.ptr, params_dev, out_dev, n_scen, ns, tiles, samples);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 2;
+  return 0;
+}
+
+int enqueue_from_normals(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc_params_t* p, int accumulate,
+                         const double* Z_dev, uint64_t n_paths, double* payoffs_dev, b200mc_moments_t* out_dev,
+                         cudaStream_t stream, bool time_it) {
+  if (int rc = check_spec(e, spec)) return rc;
+  if (!p || !Z_dev || !out_dev) return fail(e, B200MC_ERR_INVALID, "null pointer argument");
+  if (n_paths == 0) return fail(e, B200MC_ERR_INVALID, "n_paths must be >= 1");
+  const uint64_t ctas = (n_paths + kF64Block - 1) / kF64Block;
+  if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "too many paths for one launch");
+  if (int rc = reserve(e, e->partials, ctas * 2 * sizeof(double))) return rc;
+  F64Args a{};
+  a.Z = Z_dev;
+  a.payoffs = payoffs_dev;
+  a.partials = (double*)e->partials.ptr;
+  a.n_paths = n_paths;
+  a.n_steps = spec->n_steps;
+  a.accumulate = (accumulate || spec->kind != B200MC_EUROPEAN) ? 1 : 0;
+  a.antithetic = spec->antithetic;
+  a.is_put = spec->is_put;
+  a.barrier_down = spec->barrier_down;
+  a.barrier_in = spec->barrier_in;
+  a.lookback_fixed = spec->lookback_fixed;
+  a.S = p->S, a.K = p->K, a.T = p->T, a.r = p->r, a.sigma = p->sigma, a.q = p->q, a.barrier = p->barrier;
+  const dim3 grid((unsigned)ctas);
+  const int slot = (int)(e->timed % b200mc_engine::kRing);
+  if (time_it) CU_TRY(e, cudaEventRecord(e->ring0[slot], stream));
+  switch (spec->kind) {
+    case B200MC_EUROPEAN: from_normals_kernel<B200MC_EUROPEAN><<<grid, kF64Block, 0, stream>>>(a); break;
+    case B200MC_ASIAN_ARITH: from_normals_kernel<B200MC_ASIAN_ARITH><<<grid, kF64Block, 0, stream>>>(a); break;
+    case B200MC_ASIAN_GEOM: from_normals_kernel<B200MC_ASIAN_GEOM><<<grid, kF64Block, 0, stream>>>(a); break;
+    case B200MC_BARRIER: from_normals_kernel<B200MC_BARRIER><<<grid, kF64Block, 0, stream>>>(a); break;
+    case B200MC_LOOKBACK: from_normals_kernel<B200MC_LOOKBACK><<<grid, kF64Block, 0, stream>>>(a); break;
+  }
+  CU_TRY(e, cudaGetLastError());
+  if (time_it) {
+    CU_TRY(e, cudaEventRecord(e->ring1[slot], stream));
+    e->timed += 1;
+  }
+  const double samples = (double)n_paths * (spec->antithetic ? 2.0 : 1.0);
+  fold_kernel<<<1, 32, 0, stream>>>((const double*)e->partials.ptr, nullptr, out_dev, 1, 1, (uint32_t)ctas, samples);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 2;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200mc_abi_version(void) { return B200MC_ABI_VERSION; }
+
+int b200mc_create(b200mc_engine_t** out, int device) {
+  std::lock_guard<std::mutex> g(g_create_mutex);
+  if (!out) return fail(nullptr, B200MC_ERR_INVALID, "out pointer is null");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0)
+    return fail(nullptr, B200MC_ERR_CUDA, "no CUDA device available: %s", err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0");
+  if (device < 0 || device >= count) return fail(nullptr, B200MC_ERR_INVALID, "device %d out of range [0, %d)", device, count);
+  b200mc_engine* e = new (std::nothrow) b200mc_engine();
+  if (!e) return fail(nullptr, B200MC_ERR_NOMEM, "host allocation failed");
+  e->device = device;
+  auto bail = [&](cudaError_t er, const char* what) {
+    fail(nullptr, B200MC_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(er));
+    delete e;
+    return (int)B200MC_ERR_CUDA;
+  };
+  if ((err = cudaSetDevice(device)) != cudaSuccess) return bail(err, "cudaSetDevice");
+  if ((err = cudaGetDeviceProperties(&e->prop, device)) != cudaSuccess) return bail(err, "cudaGetDeviceProperties");
+  if (e->prop.major < 10) {
+    fail(nullptr, B200MC_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", device, e->prop.major, e->prop.minor);
+    delete e;
+    return B200MC_ERR_CUDA;
+  }
+  if ((err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(err, "cudaStreamCreate");
+  if ((err = cudaEventCreate(&e->ev0)) != cudaSuccess) return bail(err, "cudaEventCreate");
+  if ((err = cudaEventCreate(&e->ev1)) != cudaSuccess) return bail(err, "cudaEventCreate");
+  for (int i = 0; i < b200mc_engine::kRing; ++i) {
+    if ((err = cudaEventCreate(&e->ring0[i])) != cudaSuccess) return bail(err, "cudaEventCreate");
+    if ((err = cudaEventCreate(&e->ring1[i])) != cudaSuccess) return bail(err, "cudaEventCreate");
+  }
+  *out = e;
+  return 0;
+}
+
+void b200mc_destroy(b200mc_engine_t* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (DeviceBuffer* b : {&e->partials, &e->params_dev, &e->moments_dev, &e->scratch_a, &e->scratch_b})
+    if (b->ptr) cudaFree(b->ptr);
+  if (e->pinned) cudaFreeHost(e->pinned);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  for (int i = 0; i < b200mc_engine::kRing; ++i) {
+    if (e->ring0[i]) cudaEventDestroy(e->ring0[i]);
+    if (e->ring1[i]) cudaEventDestroy(e->ring1[i]);
+  }
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+const char* b200mc_last_error(const b200mc_engine_t* e) { return e ? e->error.c_str() : g_create_error.c_str(); }
+
+int b200mc_device_info(b200mc_engine_t* e, b200mc_info_t* out) {
+  if (!e || !out) return fail(e, B200MC_ERR_INVALID, "null argument");
+  memset(out, 0, sizeof *out);
+  out->device = e->device;
+  out->sm_count = e->prop.multiProcessorCount;
+  out->cc_major = e->prop.major;
+  out->cc_minor = e->prop.minor;
+  int v = 0;
+  cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, e->device);
+  out->sm_clock_khz = v;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMemoryClockRate, e->device);
+  out->mem_clock_khz = v;
+  out->total_mem_bytes = (int64_t)e->prop.totalGlobalMem;
+  out->l2_bytes = e->prop.l2CacheSize;
+  strncpy(out->name, e->prop.name, sizeof(out->name) - 1);
+  return 0;
+}
+
+int b200mc_simulate_device(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_dev, uint32_t n_opt,
+                           uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
+                           b200mc_moments_t* out_dev, void* cuda_stream) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  CU_TRY(e, cudaSetDevice(e->device));
+  return enqueue_simulation(e, spec, params_dev, n_opt, n_scen, seed, stream_base, path_begin, n_paths, out_dev,
+                            (cudaStream_t)cuda_stream, e->timing);
+}
+
+int b200mc_simulate(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_host, uint32_t n_opt,
+                    uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
+                    b200mc_moments_t* out_host) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  if (!params_host || !out_host) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
+  if (n_opt == 0 || n_scen == 0 || n_scen > B200MC_MAX_SCENARIOS) return fail(e, B200MC_ERR_INVALID, "bad n_opt / n_scen");
+  CU_TRY(e, cudaSetDevice(e->device));
+  const size_t n = (size_t)n_opt * n_scen;
+  const size_t in_bytes = n * sizeof(b200mc_params_t), out_bytes = n * sizeof(b200mc_moments_t);
+  if (int rc = reserve(e, e->params_dev, in_bytes)) return rc;
+  if (int rc = reserve(e, e->moments_dev, out_bytes)) return rc;
+  if (int rc = reserve_pinned(e, in_bytes + out_bytes)) return rc;
+  char* pin_in = (char*)e->pinned;
+  char* pin_out = pin_in + in_bytes;
+  memcpy(pin_in, params_host, in_bytes);
+  CU_TRY(e, cudaMemcpyAsync(e->params_dev.ptr, pin_in, in_bytes, cudaMemcpyHostToDevice, e->stream));
+  if (int rc = enqueue_simulation(e, spec, (const b200mc_params_t*)e->params_dev.ptr, n_opt, n_scen, seed, stream_base,
+                                  path_begin, n_paths, (b200mc_moments_t*)e->moments_dev.ptr, e->stream, e->timing))
+    return rc;
+  CU_TRY(e, cudaMemcpyAsync(pin_out, e->moments_dev.ptr, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  memcpy(out_host, pin_out, out_bytes);
+  return 0;
+}
+
+int b200mc_payoffs_from_normals_device(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* p, int accumulate,
+                                       const double* Z_dev, uint64_t n_paths, double* payoffs_dev, b200mc_moments_t* out_dev,
+                                       void* cuda_stream) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  CU_TRY(e, cudaSetDevice(e->device));
+  return enqueue_from_normals(e, spec, p, accumulate, Z_dev, n_paths, payoffs_dev, out_dev, (cudaStream_t)cuda_stream, e->timing);
+}
+
+int b200mc_payoffs_from_normals(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* p, int accumulate,
+                                const double* Z_host, uint64_t n_paths, double* payoffs_host, b200mc_moments_t* out_host) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  if (int rc = check_spec(e, spec)) return rc;
+  if (!p || !Z_host || !out_host) return fail(e, B200MC_ERR_INVALID, "null pointer argument");
+  if (n_paths == 0) return fail(e, B200MC_ERR_INVALID, "n_paths must be >= 1");
+  CU_TRY(e, cudaSetDevice(e->device));
+  const size_t z_bytes = (size_t)n_paths * spec->n_steps * sizeof(double);
+  const size_t n_out = (size_t)n_paths * (spec->antithetic ? 2 : 1);
+  if (int rc = reserve(e, e->scratch_a, z_bytes)) return rc;
+  if (int rc = reserve(e, e->scratch_b, n_out * sizeof(double))) return rc;
+  if (int rc = reserve(e, e->moments_dev, sizeof(b200mc_moments_t))) return rc;
+  CU_TRY(e, cudaMemcpyAsync(e->scratch_a.ptr, Z_host, z_bytes, cudaMemcpyHostToDevice, e->stream));
+  if (int rc = enqueue_from_normals(e, spec, p, accumulate, (const double*)e->scratch_a.ptr, n_paths,
+                                    payoffs_host ? (double*)e->scratch_b.ptr : nullptr, (b200mc_moments_t*)e->moments_dev.ptr,
+                                    e->stream, e->timing))
+    return rc;
+  if (payoffs_host)
+    CU_TRY(e, cudaMemcpyAsync(payoffs_host, e->scratch_b.ptr, n_out * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaMemcpyAsync(out_host, e->moments_dev.ptr, sizeof(b200mc_moments_t), cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int b200mc_generate_normals(b200mc_engine_t* e, uint64_t seed, uint32_t stream, uint64_t path_begin, uint64_t n_paths,
+                            uint32_t n_steps, float* out_host) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  if (!out_host || n_paths == 0 || n_steps == 0) return fail(e, B200MC_ERR_INVALID, "bad argument");
+  CU_TRY(e, cudaSetDevice(e->device));
+  const size_t bytes = (size_t)n_paths * n_steps * sizeof(float);
+  if (int rc = reserve(e, e->scratch_a, bytes)) return rc;
+  const uint64_t work = n_paths * ((n_steps + 3) / 4);
+  const unsigned grid = (unsigned)std::min<uint64_t>((work + 255) / 256, (uint64_t)e->prop.multiProcessorCount * 32);
+  normals_kernel<<<grid, 256, 0, e->stream>>>((uint32_t)seed, (uint32_t)(seed >> 32), stream, path_begin, n_paths, n_steps,
+                                              (float*)e->scratch_a.ptr);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 1;
+  CU_TRY(e, cudaMemcpyAsync(out_host, e->scratch_a.ptr, bytes, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int b200mc_philox_raw(b200mc_engine_t* e, const uint32_t* in_host, uint32_t n, uint32_t* out_host) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  if (!in_host || !out_host || n == 0) return fail(e, B200MC_ERR_INVALID, "bad argument");
+  CU_TRY(e, cudaSetDevice(e->device));
+  if (int rc = reserve(e, e->scratch_a, (size_t)n * 6 * sizeof(uint32_t))) return rc;
+  if (int rc = reserve(e, e->scratch_b, (size_t)n * 4 * sizeof(uint32_t))) return rc;
+  CU_TRY(e, cudaMemcpyAsync(e->scratch_a.ptr, in_host, (size_t)n * 6 * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+  philox_raw_kernel<<<(n + 127) / 128, 128, 0, e->stream>>>((const uint32_t*)e->scratch_a.ptr, n, (uint32_t*)e->scratch_b.ptr);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 1;
+  CU_TRY(e, cudaMemcpyAsync(out_host, e->scratch_b.ptr, (size_t)n * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+uint64_t b200mc_kernel_launches(const b200mc_engine_t* e) { return e ? e->launches : 0; }
+
+int b200mc_set_kernel_timing(b200mc_engine_t* e, int enabled) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  e->timing = enabled != 0;
+  e->timed = 0;
+  return 0;
+}
+
+int b200mc_kernel_timing(b200mc_engine_t* e, float* mean_ms, float* min_ms, int32_t* count) {
+  if (!e || !mean_ms || !min_ms || !count) return fail(e, B200MC_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(e->mutex);
+  if (e->timed == 0) return fail(e, B200MC_ERR_INVALID, "no timed kernel (enable with b200mc_set_kernel_timing)");
+  CU_TRY(e, cudaSetDevice(e->device));
+  const int n = (int)std::min<uint64_t>(e->timed, b200mc_engine::kRing);
+  double sum = 0.0;
+  float best = 1e30f;
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    CU_TRY(e, cudaEventSynchronize(e->ring1[i]));
+    CU_TRY(e, cudaEventElapsedTime(&ms, e->ring0[i], e->ring1[i]));
+    sum += ms;
+    best = std::min(best, ms);
+  }
+  *mean_ms = (float)(sum / n);
+  *min_ms = best;
+  *count = n;
+  return 0;
+}
+
+// ---- pipe-rate probes ---------------------------------------------------------------------------
+int b200mc_measure_peaks(b200mc_engine_t* e, b200mc_peaks_t* out) {
+  if (!e || !out) return fail(e, B200MC_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(e->mutex);
+  CU_TRY(e, cudaSetDevice(e->device));
+  memset(out, 0, sizeof *out);
+  const unsigned grid = (unsigned)e->prop.multiProcessorCount * 8, block = 256;
+  const double threads = (double)grid * block;
+  if (int rc = reserve(e, e->scratch_a, (size_t)grid * block * sizeof(uint64_t))) return rc;
+  if (int rc = reserve(e, e->scratch_b, (size_t)grid * 2 * sizeof(long long))) return rc;
+  void* buf = e->scratch_a.ptr;
+  cudaStream_t s = e->stream;
+  float ms = 0.f;
+  auto timed = [&](auto&& launch) -> int {
+    launch();  // warm-up (also pages the code in)
+    CU_TRY(e, cudaGetLastError());
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+      CU_TRY(e, cudaEventRecord(e->ev0, s));
+      launch();
+      CU_TRY(e, cudaEventRecord(e->ev1, s));
+      CU_TRY(e, cudaEventSynchronize(e->ev1));
+      CU_TRY(e, cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+      best = std::min(best, ms);
+      e->launches += 1;
+    }
+    ms = best;
+    return 0;
+  };
+  const uint32_t it = 4096;
+  if (int rc = timed([&] { probe::ffma<<<grid, block, 0, s>>>(it, 1.0000001f, 1e-9f, (float*)buf); })) return rc;
+  out->ffma_per_s = threads * it * 4.0 * probe::kChains / (ms * 1e-3);
+  if (int rc = timed([&] { probe::imad_wide<<<grid, block, 0, s>>>(it, 0xD2511F53u, (uint64_t*)buf); })) return rc;
+  out->imad_wide_per_s = threads * it * 4.0 * probe::kChains / (ms * 1e-3);
+  if (int rc = timed([&] { probe::lop3<<<grid, block, 0, s>>>(it, 0x9E3779B9u, 0xBB67AE85u, (uint32_t*)buf); })) return rc;
+  out->lop3_per_s = threads * it * 4.0 * probe::kChains / (ms * 1e-3);
+  if (int rc = timed([&] { probe::mufu_mix<<<grid, block, 0, s>>>(it / 4, (float*)buf); })) return rc;
+  out->mufu_per_s = threads * (it / 4) * 4.0 * probe::kChains / (ms * 1e-3);
+  if (int rc = timed([&] { probe::mufu_ex2<<<grid, block, 0, s>>>(it / 4, (float*)buf); })) return rc;
+  out->mufu_ex2_per_s = threads * (it / 4) * 4.0 * probe::kChains / (ms * 1e-3);
+  if (int rc = timed([&] { probe::issue_mix<<<grid, block, 0, s>>>(it, 1.0000001f, 1e-9f, 0x9E3779B9u, (float*)buf); })) return rc;
+  out->issue_per_s = threads * it * 4.0 * (probe::kChains / 2) * 3.0 / (ms * 1e-3);
+  if (int rc = timed([&] { probe::philox_only<<<grid, block, 0, s>>>(it, 42u, 0u, (uint32_t*)buf); })) return rc;
+  out->philox_per_s = threads * it / (ms * 1e-3);
+  if (int rc = timed([&] { probe::normals_only<<<grid, block, 0, s>>>(it, 42u, 0u, (float*)buf, (long long*)e->scratch_b.ptr); })) return rc;
+  out->normals_per_s = threads * it * 4.0 / (ms * 1e-3);
+  std::vector<long long> clk((size_t)grid * 2);
+  CU_TRY(e, cudaMemcpy(clk.data(), e->scratch_b.ptr, clk.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+  std::vector<double> mhz;
+  for (unsigned i = 0; i < grid; ++i)
+    if (clk[2 * i + 1] > 0) mhz.push_back((double)clk[2 * i] / (double)clk[2 * i + 1] * 1e3);
+  if (!mhz.empty()) {
+    std::nth_element(mhz.begin(), mhz.begin() + mhz.size() / 2, mhz.end());
+    out->sm_clock_mhz_seen = mhz[mhz.size() / 2];
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -27,6 +27,4 @@ def engine():
     """One CUDA engine handle for the whole GPU test session."""
     from optionslab_b200 import _ffi
 
-    eng = _ffi.Engine(device=0)
-    yield eng
-    eng.close()
+    yield _ffi.get_engine(0)  # the same process-wide engine the pricer classes use

@@ -1,0 +1,76 @@
+"""CPU: libb200mc.so loads without a GPU and exports exactly what include/b200mc.h declares."""
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from optionslab_b200 import _ffi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "b200mc.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200mc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert _header_functions() == sorted(_ffi.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _ffi.load_library()
+    for name in _header_functions():
+        assert hasattr(lib, name), name
+    assert lib.b200mc_abi_version() == _ffi.ABI_VERSION
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_ffi.Spec) == 32
+    assert _ffi.PARAMS_DTYPE.itemsize == 64 and _ffi.MOMENTS_DTYPE.itemsize == 24
+    assert C.sizeof(_ffi.Info) == 4 * 6 + 8 + 4 * 2 + 64
+    assert C.sizeof(_ffi.Peaks) == 12 * 8
+    p = _ffi.make_params(100.0, [90.0, 110.0], 1.0, 0.05, 0.2, 0.0, 120.0)
+    assert p.shape == (2,) and p["K"].tolist() == [90.0, 110.0] and p["barrier"].tolist() == [120.0, 120.0]
+
+
+def test_null_engine_calls_are_rejected_not_crashing():
+    lib = _ffi.load_library()
+    assert lib.b200mc_kernel_launches(None) == 0
+    assert lib.b200mc_set_kernel_timing(None, 1) == -1
+    assert lib.b200mc_simulate(None, None, None, 1, 1, 0, 0, 0, 1, None) == -1
+    lib.b200mc_destroy(None)
+
+
+def test_no_cpu_fallback_without_a_device():
+    """On a box with no GPU the product path must fail loudly, never compute on the CPU."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    from optionslab_b200 import AccelerationError, AsianOption, MonteCarloPricer, MonteCarloPricerUni
+    _ffi._engines.clear()
+    with pytest.raises(AccelerationError):
+        MonteCarloPricer(1000, 4, seed=1).price(100, 100, 1.0, 0.05, 0.2, "call")
+    with pytest.raises(AccelerationError):
+        AsianOption(100, 100, 1.0, 0.05, 0.2, seed=1).price(1000, 4)
+    from optionslab_b200 import MonteCarloError
+    with pytest.raises(MonteCarloError):  # Uni wraps engine failures like monte_carlo_unified.py:510-511
+        MonteCarloPricerUni(1000, 4, seed=1).price(100, 100, 1.0, 0.05, 0.2, "call")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "optionslab_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "oracle/" not in text or f.endswith((".cuh", ".cu")), f

@@ -1,0 +1,187 @@
+"""GPU, correctness test 2 of BASELINE.json: with the on-device Philox stream, prices and Greeks
+fall within 3 standard errors of the reference and of the Black-Scholes closed form — plus the
+exact properties the fused FP32 path must have (determinism, shard additivity, fused == separate).
+
+The FP32 path is also compared, draw for draw, against the FP64 oracle evaluation of the SAME
+Philox stream (oracle/philox_oracle.c normals through oracle/reference_mc.py): that isolates
+arithmetic error (tolerance 2e-4 relative on a price, i.e. far below one standard error) from
+Monte Carlo noise.
+"""
+
+import numpy as np
+import pytest
+
+import optionslab_b200 as ob
+from optionslab_b200 import _ffi, runtime
+from oracle import philox_oracle as po
+from oracle import reference_mc as orc
+
+pytestmark = pytest.mark.gpu
+P = dict(S=100.0, K=100.0, T=1.0, r=0.05, sigma=0.2)
+BS_CALL, BS_PUT = 10.450583572185565, 5.573526022256971
+# reference values at 1M paths (recorded from the real reference, NumPy 2.3.5)
+REF_1M = dict(call=(10.457915429444164, 0.010426610119053227), delta=0.6370571458618244, gamma=0.019004492473989387,
+              vega=37.564849270217415, asian=5.768271672258132, up_and_out=1.2995964895711083, up_and_in=9.13740139898588)
+
+
+def _price_se(m, r=P["r"], T=P["T"]):
+    return float(runtime.discounted_price(m, r, T)), float(runtime.discounted_std_error(m, r, T))
+
+
+# ---------------- arithmetic accuracy against the FP64 oracle on the same draws -------------------
+
+@pytest.mark.parametrize("n_steps", [1, 3, 16, 50, 253])
+def test_european_fp32_path_vs_fp64_oracle_same_stream(engine, n_steps):
+    n, seed = 20_000, 31
+    Z = po.normals(seed, n, n_steps)
+    for ot, q in (("call", 0.0), ("put", 0.02)):
+        pay = orc.vanilla_payoffs(orc.gbm_terminal_from_normals(P["S"], P["T"], P["r"], P["sigma"], q, Z), P["K"], ot)
+        spec = _ffi.make_spec(_ffi.EUROPEAN, n_steps, is_put=(ot == "put"), antithetic=True)
+        m = engine.simulate(spec, _ffi.make_params(**P, q=q).reshape(1, 1), seed, n)[0, 0]
+        assert m["n"] == 2 * n
+        assert m["sum"] == pytest.approx(pay.sum(), rel=2e-4)
+        assert m["sum_sq"] == pytest.approx((pay**2).sum(), rel=4e-4)
+
+
+def test_exotics_fp32_path_vs_fp64_oracle_same_stream(engine):
+    n, n_steps, seed = 20_000, 37, 5  # 37 = 9 Philox blocks + 1 leftover draw
+    Z = po.normals(seed, n, n_steps)
+    paths = orc.exotic_paths_from_normals(P["S"], P["T"], P["r"], P["sigma"], 0.0, Z)
+    cases = []
+    for ot in ("call", "put"):
+        cases += [(_ffi.make_spec(_ffi.ASIAN_ARITH, n_steps, is_put=ot == "put"), 0.0, orc.asian_payoffs(paths, P["K"], "arithmetic", ot)),
+                  (_ffi.make_spec(_ffi.ASIAN_GEOM, n_steps, is_put=ot == "put"), 0.0, orc.asian_payoffs(paths, P["K"], "geometric", ot))]
+        for B, bts in ((115.0, ("up-and-out", "up-and-in")), (90.0, ("down-and-out", "down-and-in"))):
+            for bt in bts:
+                cases.append((_ffi.make_spec(_ffi.BARRIER, n_steps, is_put=ot == "put", barrier_down=bt.startswith("down"),
+                                             barrier_in=bt.endswith("in")), B, orc.barrier_payoffs(paths, P["K"], B, bt, ot)))
+        for lt in ("floating", "fixed"):
+            cases.append((_ffi.make_spec(_ffi.LOOKBACK, n_steps, is_put=ot == "put", lookback_fixed=lt == "fixed"), 0.0,
+                          orc.lookback_payoffs(paths, P["K"], lt, ot)))
+    for spec, B, pay in cases:
+        m = engine.simulate(spec, _ffi.make_params(**P, barrier=B).reshape(1, 1), seed, n)[0, 0]
+        assert m["n"] == n
+        # barrier: a path within FP32 rounding of B may flip; allow a few payoffs' worth of slack
+        assert m["sum"] == pytest.approx(pay.sum(), rel=5e-4, abs=60.0 if spec.kind == _ffi.BARRIER else 0.0), (spec.kind, spec.is_put)
+
+
+# ---------------- statistical agreement with the reference and Black-Scholes ----------------------
+
+def test_config1_european_100k_x_252_vs_reference_and_black_scholes():
+    res = ob.MonteCarloPricer(100_000, 252, seed=42).price(**P, option_type="call", return_error=True)
+    assert res.n_paths == 200_000 and 0 < res.std_error < res.price
+    ref_price, ref_se = 10.46001409391075, 0.03303353316736617  # real reference, same config (goldens)
+    assert res.std_error == pytest.approx(ref_se, rel=0.02)
+    assert abs(res.price - BS_CALL) <= 3 * res.std_error
+    assert abs(res.price - ref_price) <= 3 * np.hypot(res.std_error, ref_se)
+    put = ob.MonteCarloPricer(100_000, 252, seed=42).price(**P, option_type="put", return_error=True)
+    assert abs(put.price - BS_PUT) <= 3 * put.std_error
+
+
+def test_single_step_default_matches_black_scholes():
+    res = ob.MonteCarloPricer(1_000_000, seed=1).price(**P, option_type="call", return_error=True)
+    assert abs(res.price - BS_CALL) <= 3 * res.std_error
+    fast = ob.MonteCarloPricer(1_000_000, 50, seed=1, method=ob.MCMethod.FAST).price(**P, option_type="call")
+    assert fast == res.price  # FAST forces one step (monte_carlo.py:86-92)
+
+
+def test_config2_greeks_1m_x_252_crn_single_launch(engine):
+    pr = ob.MonteCarloPricer(1_000_000, 252, seed=42)
+    before = engine.kernel_launches()
+    g = pr.greeks(**P, option_type="call")
+    assert engine.kernel_launches() - before == 2  # one fused simulation + one fold for all 14 scenarios
+    d_bs, g_bs, v_bs = orc.black_scholes_greeks(**P)
+    assert g["price"] == pytest.approx(BS_CALL, abs=3 * 0.0105)
+    assert g["delta"] == pytest.approx(d_bs, abs=1.5e-3) and g["delta"] == pytest.approx(REF_1M["delta"], abs=2e-3)
+    assert g["gamma"] == pytest.approx(g_bs, abs=1e-3) and g["gamma"] == pytest.approx(REF_1M["gamma"], abs=1e-3)
+    assert g["vega"] == pytest.approx(v_bs, abs=0.3) and g["vega"] == pytest.approx(REF_1M["vega"], abs=0.4)
+    assert g["theta"] == pytest.approx(-6.414, abs=0.15) and g["rho"] == pytest.approx(53.232, abs=0.5)
+    assert list(g) == ["price", "delta", "gamma", "vega", "theta", "rho", "vanna", "charm", "vomma"]
+    p = pr.greeks(**P, option_type="put")
+    assert p["delta"] == pytest.approx(d_bs - 1.0, abs=1.5e-3) and p["gamma"] == pytest.approx(g["gamma"], rel=1e-4)
+    assert pr.delta(**P) == g["delta"] and pr.vega(**P) == g["vega"]
+
+
+def test_fused_greeks_equal_separate_repricings_bitwise():
+    """One launch with 14 scenarios == 14 launches of 1 scenario (same draws, same reduction order)."""
+    pr = ob.MonteCarloPricer(50_000, 32, seed=9)
+
+    class CallByCall:  # hides price_scenarios: forces the reference's route
+        def price(self, *a, **k):
+            return pr.price(*a, **k)
+
+    fused = ob.compute_greeks_unified(pr, **P, option_type="put", q=0.01)
+    separate = ob.compute_greeks_unified(CallByCall(), **P, option_type="put", q=0.01)
+    assert dict(fused) == dict(separate)
+
+
+def test_config3_asian_4m_x_252():
+    res = ob.AsianOption(**P, seed=42).price(n_paths=4_000_000, n_steps=252, return_error=True)
+    ref_se_1m = 8.0 / np.sqrt(1e6)  # payoff std ~ 8 => reference's own 1M-path noise
+    assert abs(res.price - REF_1M["asian"]) <= 3 * np.hypot(res.std_error, ref_se_1m)
+    assert res.n_paths == 4_000_000 and res.price < BS_CALL
+    geo = ob.AsianOption(**P, seed=42).price(n_paths=1_000_000, n_steps=252, avg_type="geometric", return_error=True)
+    assert abs(geo.price - 5.552463811592335) <= 3 * np.hypot(geo.std_error, 0.008)
+    assert geo.price == pytest.approx(ob.AsianOption(**P).price_geometric_closed_form(), rel=0.05)
+    assert geo.price < res.price  # AM-GM
+
+
+def test_config4_barrier_16m_x_365_and_in_out_parity(engine):
+    opt = ob.BarrierOption(**P, seed=42, barrier=120.0)
+    out = opt.price(16_000_000, 365, "up-and-out", "call", return_error=True)
+    assert abs(out.price - REF_1M["up_and_out"]) <= 3 * np.hypot(out.std_error, 0.0035)
+    inn = opt.price(16_000_000, 365, "up-and-in", "call", return_error=True)
+    assert abs(inn.price - REF_1M["up_and_in"]) <= 3 * np.hypot(inn.std_error, 0.016)
+    # same draws: knock-in + knock-out is the vanilla payoff path by path
+    never = ob.BarrierOption(**P, seed=42, barrier=1e9).price(16_000_000, 365, "up-and-out", "call", return_error=True)
+    assert out.price + inn.price == pytest.approx(never.price, rel=1e-5)
+    assert abs(never.price - BS_CALL) <= 3 * never.std_error
+
+
+def test_same_seed_is_bit_identical_and_seeds_differ():
+    a = ob.MonteCarloPricer(100_000, 50, seed=42).price(**P, option_type="call")
+    b = ob.MonteCarloPricer(100_000, 50, seed=42).price(**P, option_type="call")
+    c = ob.MonteCarloPricer(100_000, 50, seed=43).price(**P, option_type="call")
+    assert a == b and a != c
+    pr = ob.MonteCarloPricer(100_000, 50, seed=1)
+    assert pr.price(**P, option_type="call", seed=42) == a  # per-call override, monte_carlo.py:84
+    assert ob.MonteCarloPricer(100_000, 50, seed=0).price(**P, option_type="call") != a  # seed=0 honoured
+    x = ob.AsianOption(**P, seed=7).price(50_000, 64)
+    assert x == ob.AsianOption(**P, seed=7).price(50_000, 64)
+    assert ob.AsianOption(**P).price(50_000, 64) != ob.AsianOption(**P).price(50_000, 64)  # unseeded
+
+
+def test_path_ranges_are_additive_the_multi_gpu_contract(engine):
+    """moments([0,N)) == sum of moments over any partition of [0,N) (up to FP64 summation order)."""
+    spec = _ffi.make_spec(_ffi.EUROPEAN, 20, antithetic=True)
+    params = np.stack([_ffi.make_params(100.0, K, 1.0, 0.05, 0.2) for K in (90.0, 100.0, 110.0)]).reshape(3, 1)
+    N = 300_001
+    whole = engine.simulate(spec, params, 5, N)
+    for world in (2, 3, 8):
+        acc = np.zeros((3, 1, 3))
+        for rank in range(world):
+            b, c = ob.distributed.partition_paths(N, rank, world)
+            part = engine.simulate(spec, params, 5, c, path_begin=b)
+            acc += np.stack([part["sum"], part["sum_sq"], part["n"]], axis=-1)
+        np.testing.assert_allclose(acc[..., 0], whole["sum"], rtol=1e-6)  # per-thread FP32 partial sums regroup
+        np.testing.assert_allclose(acc[..., 1], whole["sum_sq"], rtol=1e-6)
+        np.testing.assert_array_equal(acc[..., 2], whole["n"])
+
+
+def test_scaling_homogeneity_is_exact(engine):
+    """price(aS, aK) = a * price(S, K): the kernels work on S_t/S_0, so this holds to FP64 rounding."""
+    spec = _ffi.make_spec(_ffi.ASIAN_ARITH, 16)
+    base = engine.simulate(spec, _ffi.make_params(100.0, 95.0, 1.0, 0.05, 0.3).reshape(1, 1), 3, 100_000)[0, 0]
+    scaled = engine.simulate(spec, _ffi.make_params(400.0, 380.0, 1.0, 0.05, 0.3).reshape(1, 1), 3, 100_000)[0, 0]
+    assert scaled["sum"] == pytest.approx(4 * base["sum"], rel=1e-14)
+
+
+def test_ragged_and_tiny_sizes(engine):
+    for n_paths in (1, 2, 31, 255, 257, 1025):
+        for n_steps in (1, 2, 3, 4, 5):
+            spec = _ffi.make_spec(_ffi.EUROPEAN, n_steps, antithetic=True)
+            m = engine.simulate(spec, _ffi.make_params(**P).reshape(1, 1), 1, n_paths)[0, 0]
+            Z = po.normals(1, n_paths, n_steps)
+            pay = orc.vanilla_payoffs(orc.gbm_terminal_from_normals(P["S"], P["T"], P["r"], P["sigma"], 0.0, Z), P["K"], "call")
+            assert m["n"] == 2 * n_paths
+            assert m["sum"] == pytest.approx(pay.sum(), rel=3e-4, abs=1e-3)

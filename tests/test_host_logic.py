@@ -1,0 +1,139 @@
+"""CPU: host-side mirror of the reference interface (no kernel is launched)."""
+
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+import optionslab_b200 as ob
+from optionslab_b200 import distributed, greeks, runtime
+from oracle import reference_mc as orc
+
+P = dict(S=100.0, K=100.0, T=1.0, r=0.05, sigma=0.2)
+
+
+class BSPricer:
+    """A PricerProtocol object with no price_scenarios: exercises the call-by-call route."""
+
+    def __init__(self):
+        self.calls = 0
+
+    def price(self, S, K, T, r, sigma, option_type, q=0.0, **kw):
+        self.calls += 1
+        return orc.black_scholes(S, K, T, r, sigma, option_type, q)
+
+
+class FusedBS(BSPricer):
+    def price_scenarios(self, scenarios, option_type, **kw):
+        self.fused_sizes = getattr(self, "fused_sizes", []) + [len(scenarios)]
+        return [orc.black_scholes(s[0], s[1], s[2], s[3], s[4], option_type, s[5]) for s in scenarios]
+
+
+def test_constructor_contracts():
+    # tests/test_monte_carlo.py:95-112 and :375-390 of the reference
+    p = ob.MonteCarloPricer(num_simulations=5000, num_steps=100, seed=123)
+    assert (p.num_simulations, p.num_steps, p.seed) == (5000, 100, 123)
+    for bad in (0, -100):
+        with pytest.raises(ValueError):
+            ob.MonteCarloPricer(num_simulations=bad)
+    assert ob.MonteCarloPricer().num_steps == 1 and ob.MonteCarloPricerUni().num_steps == 100
+    assert isinstance(ob.MonteCarloPricer().seed, int) and 0 <= ob.MonteCarloPricer().seed < 2**31
+    ob.MonteCarloPricer(10, 1, seed=0, method=ob.MCMethod.NUMBA, use_numba=True)  # stale kwarg accepted
+    u = ob.MonteCarloPricerUni(num_simulations=5000, num_steps=50, seed=1, use_numba=False, use_gpu=False)
+    assert (u.num_simulations, u.num_steps, u.seed) == (5000, 50, 1)
+    with pytest.raises(ob.InputValidationError):
+        ob.MonteCarloPricerUni(num_simulations=0)
+    with pytest.raises(ob.InputValidationError):
+        ob.MonteCarloPricerUni(num_steps=-1)
+    assert issubclass(ob.InputValidationError, ob.MonteCarloError)
+
+
+def test_validation_happens_before_any_launch():
+    u = ob.MonteCarloPricerUni(100, 5, seed=1)
+    for args in [(0, 100, 1.0, 0.05, 0.2, "call"), (100, 100, 1.0, 0.05, -0.2, "call"),
+                 (100, 100, 1.0, 0.05, 0.2, "invalid"), (100, 0, 1.0, 0.05, 0.2, "put"), (100, 100, 0.0, 0.05, 0.2, "put")]:
+        with pytest.raises(ob.InputValidationError):
+            u.price(*args)
+    with pytest.raises(ValueError, match="positive"):
+        ob.BarrierOption(**P, barrier=0.0).price(10, 2)
+    with pytest.raises(ValueError, match="positive"):
+        ob.BarrierOption(**P, barrier=-5.0).price(10, 2)
+
+
+def test_expired_option_is_intrinsic_without_gpu():
+    p = ob.MonteCarloPricer(10, 1, seed=1)
+    assert p.price(110, 100, 0.0, 0.05, 0.2, "call") == 10
+    assert p.price(90, 100, -1.0, 0.05, 0.2, "put") == 10
+    r = p.price(110, 100, 0.0, 0.05, 0.2, "put", return_error=True)
+    assert (r.price, r.std_error, r.n_paths) == (0, 0.0, 0)
+
+
+def test_greek_scenarios_and_formulas_match_reference_restatement():
+    for (S, K, T, r, sigma, q) in [(100, 100, 1.0, 0.05, 0.2, 0.0), (105, 95, 0.75, 0.03, 0.35, 0.02), (100, 100, 0.002, 0.05, 0.2, 0.0)]:
+        for ot in ("call", "put"):
+            want = orc.greeks_bump_and_revalue(lambda S_, K_, T_, r_, s_, q_: orc.black_scholes(S_, K_, T_, r_, s_, ot, q_), S, K, T, r, sigma, q)
+            plain, fused = BSPricer(), FusedBS()
+            got_plain = ob.compute_greeks_unified(plain, S, K, T, r, sigma, ot, q)
+            got_fused = ob.compute_greeks_unified(fused, S, K, T, r, sigma, ot, q)
+            assert isinstance(got_plain, OrderedDict)
+            assert list(got_plain) == list(want) == ["price", "delta", "gamma", "vega", "theta", "rho", "vanna", "charm", "vomma"]
+            for k in want:
+                assert got_plain[k] == want[k] and got_fused[k] == want[k], k
+            n_expected = 14 if T > 1 / 365 else 11
+            assert plain.calls == n_expected and fused.fused_sizes == [n_expected] and fused.calls == 0
+    first = ob.compute_greeks_unified(BSPricer(), **P, include_second_order=False)
+    assert list(first) == ["price", "delta", "gamma", "vega", "theta", "rho"]
+    assert len(greeks.greek_scenarios(**P, include_second_order=False)) == 8
+
+
+def test_greeks_error_wrapping():
+    class Broken:
+        def price(self, *a, **k):
+            raise RuntimeError("boom")
+
+    with pytest.raises(ob.GreeksError, match="Failed to compute unified Greeks: boom"):
+        ob.compute_greeks_unified(Broken(), **P)
+
+
+def test_exotic_adapter_mutates_and_forwards():
+    class Fake:
+        S = K = T = r = sigma = q = None
+
+        def price(self, n_paths, n_steps, **kw):
+            self.seen = (n_paths, n_steps, kw)
+            return self.S + self.sigma
+
+    ex = Fake()
+    ad = ob.ExoticAdapter(ex, n_paths=123, n_steps=7, avg_type="geometric")
+    assert ad.price(101.0, 99.0, 0.5, 0.01, 0.3, "put", q=0.02) == 101.3
+    assert (ex.S, ex.K, ex.T, ex.r, ex.sigma, ex.q) == (101.0, 99.0, 0.5, 0.01, 0.3, 0.02)
+    assert ex.seen == (123, 7, {"avg_type": "geometric", "option_type": "put"})
+    assert isinstance(ad, ob.PricerProtocol) and isinstance(ob.MonteCarloPricer(10), ob.PricerProtocol)
+    assert ad.price_scenarios([(100, 100, 1, 0.05, 0.2, 0.0), (101, 100, 1, 0.05, 0.2, 0.0)], "call") == [100.2, 101.2]
+
+
+def test_moment_arithmetic_matches_reference_formulas():
+    rng = np.random.default_rng(0)
+    pay = np.maximum(rng.normal(5, 10, 20000), 0)
+    m = np.zeros((), dtype=ob._ffi.MOMENTS_DTYPE)
+    m["sum"], m["sum_sq"], m["n"] = pay.sum(), (pay**2).sum(), len(pay)
+    assert float(runtime.discounted_price(m, 0.05, 1.0)) == pytest.approx(orc.discounted_mean(pay, 0.05, 1.0), rel=1e-14)
+    assert float(runtime.discounted_std_error(m, 0.05, 1.0)) == pytest.approx(orc.discounted_std_error(pay, 0.05, 1.0), rel=1e-10)
+
+
+def test_partition_paths_is_an_exact_cover():
+    for n in (1, 7, 1000, 16_000_000, 2**40 + 5):
+        for w in (1, 2, 3, 4, 8):
+            spans = [distributed.partition_paths(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+            for (b0, c0), (b1, _) in zip(spans, spans[1:]):
+                assert b0 + c0 == b1
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+    with pytest.raises(ValueError):
+        distributed.partition_paths(10, 2, 2)
+
+
+def test_closed_form_geometric_asian_matches_reference():
+    assert ob.AsianOption(**P).price_geometric_closed_form("call") == pytest.approx(orc.asian_geometric_closed_form(**P), rel=1e-12)
+    assert ob.AsianOption(**P, q=0.01).price_geometric_closed_form("put") == pytest.approx(
+        orc.asian_geometric_closed_form(**P, q=0.01, option_type="put"), rel=1e-12)

@@ -1,0 +1,69 @@
+"""CPU: pin the Philox restatements (C oracle and the host build of the device header) to the
+Random123 known answers, and sanity-check the documented uniform->normal mapping."""
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import philox_oracle as po
+from tests import kat
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def host_header_lib(tmp_path_factory):
+    out = tmp_path_factory.mktemp("hostphilox") / "libhost_philox.so"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(out), os.path.join(ROOT, "tests", "host_philox.cpp")], check=True)
+    lib = C.CDLL(str(out))
+    lib.host_philox4x32_10.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    return lib
+
+
+def test_c_oracle_known_answers():
+    for ctr, key, want in kat.PHILOX4X32_10_KAT:
+        assert tuple(int(x) for x in po.philox4x32_10(ctr, key)) == want
+
+
+def test_device_header_known_answers_and_matches_oracle(host_header_lib):
+    ck = kat.kat_inputs()
+    out = np.empty((len(ck), 4), dtype=np.uint32)
+    host_header_lib.host_philox4x32_10(ck.ctypes.data, len(ck), out.ctypes.data)
+    np.testing.assert_array_equal(out, kat.kat_outputs())
+    rng = np.random.default_rng(0)
+    ck = rng.integers(0, 2**32, size=(2000, 6), dtype=np.uint64).astype(np.uint32)
+    out = np.empty((len(ck), 4), dtype=np.uint32)
+    host_header_lib.host_philox4x32_10(ck.ctypes.data, len(ck), out.ctypes.data)
+    for i in range(0, len(ck), 97):
+        np.testing.assert_array_equal(out[i], po.philox4x32_10(ck[i, :4], ck[i, 4:]))
+
+
+def test_stream_layout_is_counter_based():
+    """Path p / step s depends only on (seed, stream, p, s): sub-ranges and prefixes agree."""
+    full = po.normals(11, 64, 10, stream=3)
+    np.testing.assert_array_equal(po.normals(11, 16, 10, stream=3, path_begin=40), full[40:56])
+    np.testing.assert_array_equal(po.normals(11, 64, 7, stream=3), full[:, :7])
+    assert not np.array_equal(po.normals(11, 64, 10, stream=4), full)
+    assert not np.array_equal(po.normals(12, 64, 10, stream=3), full)
+    big = po.normals(5, 2, 4, path_begin=(1 << 32) - 1)  # crosses the 32-bit path-word boundary
+    assert np.all(np.isfinite(big)) and not np.array_equal(big[0], big[1])
+
+
+def test_normal_mapping_moments():
+    z = po.normals(2024, 250_000, 8).ravel()  # 2e6 draws
+    n = z.size
+    assert abs(z.mean()) < 4 / np.sqrt(n)
+    assert abs(z.var() - 1) < 4 * np.sqrt(2 / n)
+    assert abs((z**3).mean()) < 4 * np.sqrt(15 / n)
+    assert abs((z**4).mean() - 3) < 4 * np.sqrt(96 / n)
+    assert np.abs(z).max() < 5.7  # radius is capped at sqrt(2*23*ln2) = 5.647 by the 23-bit uniform
+    # Kolmogorov-Smirnov against the normal CDF
+    from scipy import stats
+    assert stats.kstest(z[:200_000], "norm").pvalue > 1e-3
+    # successive draws of a path and neighbouring paths are uncorrelated
+    zz = z.reshape(-1, 8)
+    assert abs(np.corrcoef(zz[:, 0], zz[:, 1])[0, 1]) < 4 / np.sqrt(len(zz))
+    assert abs(np.corrcoef(zz[:-1, 0], zz[1:, 0])[0, 1]) < 4 / np.sqrt(len(zz))
