@@ -37,9 +37,10 @@ N_OPT, N_PATHS, N_STEPS, SEED = N_STRIKES * N_MATURITIES, 1_000_000, 252, 42
 WORKLOAD = (f"C5: {N_OPT}-option European call grid ({N_STRIKES} strikes 60..140 x {N_MATURITIES} maturities 1/12..2y, "
             f"S=100 r=0.05 sigma=0.2) x {N_PATHS} paths x {N_STEPS} steps, each option simulated independently "
             f"(antithetic, own Philox stream)")
-# Instruction budget of the dominant kernel (european_kernel<1,true,2> inner loop, counted from the shipped
-# SASS with cuobjdump — profiles/r01_sass_european.txt): per path-step 14.75 issued instructions, of which 2 MUFU.
-INSTR_PER_STEP, MUFU_PER_STEP, IMAD_PER_STEP, LOP_PER_STEP = 14.75, 2.0, 4.0, 4.5
+# Instruction budget of the dominant kernel (european_kernel<1,true> inner loop, counted from the shipped SASS
+# with cuobjdump — profiles/r01_sass_european.txt): 202 issued instructions per 16 path-steps, of which 32 MUFU,
+# 48 IMAD.WIDE (fmaheavy pipe), 62 LOP3 + 12 LEA (ALU pipe).
+INSTR_PER_STEP, MUFU_PER_STEP, IMAD_PER_STEP, LOP_PER_STEP = 202 / 16, 2.0, 3.0, 74 / 16
 
 
 def grid_params():
@@ -256,8 +257,9 @@ def run_engine_arm(args):
         from oracle import reference_mc as orc  # checker only
 
         bs = np.array([orc.black_scholes(g["S"][i], g["K"][i], g["T"][i], g["r"][i], g["sigma"][i], "call") for i in range(N_OPT)])
-        z = (dev_prices - bs) / se
-        ok = bool(np.all(np.abs(z) < 5.0) and np.allclose(prices, dev_prices, rtol=1e-9))
+        z = np.abs(dev_prices - bs) / np.maximum(se, 1e-300)
+        z = np.where(se > 0, z, 0.0)  # deep out-of-the-money short maturities: every payoff is 0 and Black-Scholes is < 1e-5
+        ok = bool(np.all(np.abs(dev_prices - bs) <= 5.0 * se + 1e-5) and np.allclose(prices, dev_prices, rtol=1e-9))
 
         kernel_s = ktime["mean_ms"] * 1e-3
         per_gpu_steps = work_per_step / world
@@ -273,17 +275,17 @@ def run_engine_arm(args):
         bound = "xu" if mufu_frac >= issue_frac else "issue"
         roofline = {
             "bound": bound,
-            "kernel": "european_kernel<NS=1,ANTI,ILP=2>",
+            "kernel": "european_kernel<NS=1,ANTI>",
             "kernel_ms": ktime["mean_ms"], "kernel_ms_min": ktime["min_ms"], "kernels_timed": ktime["count"],
             "achieved": kernel_rate * (MUFU_PER_STEP if bound == "xu" else INSTR_PER_STEP),
             "peak": peaks["mufu_per_s"] if bound == "xu" else peaks["issue_per_s"],
             "unit": "MUFU op/s" if bound == "xu" else "thread-instr/s",
             "frac": max(mufu_frac, issue_frac),
             "peak_source": "measured live by b200mc_measure_peaks on this GPU (pipe microbenchmarks)",
-            "per_path_step": {"instructions": INSTR_PER_STEP, "mufu": MUFU_PER_STEP, "imad_wide": IMAD_PER_STEP, "lop3": LOP_PER_STEP},
+            "per_path_step": {"instructions": INSTR_PER_STEP, "mufu": MUFU_PER_STEP, "imad_wide": IMAD_PER_STEP, "alu": LOP_PER_STEP},
             "xu_frac": mufu_frac, "issue_frac": issue_frac,
             "imad_frac": kernel_rate * IMAD_PER_STEP / peaks["imad_wide_per_s"],
-            "alu_frac": kernel_rate * (LOP_PER_STEP + 1.0) / peaks["lop3_per_s"],
+            "alu_frac": kernel_rate * LOP_PER_STEP / peaks["lop3_per_s"],
             "vs_rng_only_probe": kernel_rate / peaks["normals_per_s"],
             "traffic": None,
             "hbm": {"achieved_gbs": hbm_bytes / kernel_s / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,

@@ -124,21 +124,29 @@ void plan_tiles(const b200mc_engine* e, uint32_t n_opt, uint64_t n_paths, uint32
   ppt = (uint32_t)p;
 }
 
+// __launch_bounds__ minBlocksPerSM per kernel family, picked from measurements on B200
+// (profiles/r01_variants.txt): the schedulers want the three Philox chains of a superblock
+// interleaved, which needs ~60-75 registers; squeezing below 48 costs 5-10%.
+constexpr int kMinBlocksSmall = 4;    // European, 1-2 scenarios (61 registers)
+constexpr int kMinBlocksPathdep = 3;  // Asian / barrier / lookback, 1-2 scenarios (<= 78 registers)
+constexpr int kMinBlocksWide = 2;     // 4-16 scenarios (<= 128 registers)
+
 template <int NS>
 cudaError_t launch_european(const SimArgs& a, bool anti, dim3 grid, cudaStream_t s) {
-  if (anti) european_kernel<NS, true, 2><<<grid, kBlock, 0, s>>>(a);
-  else european_kernel<NS, false, 2><<<grid, kBlock, 0, s>>>(a);
+  constexpr int kMinBlocks = NS <= 2 ? kMinBlocksSmall : kMinBlocksWide;
+  if (anti) european_kernel<NS, true, kMinBlocks><<<grid, kBlock, 0, s>>>(a);
+  else european_kernel<NS, false, kMinBlocks><<<grid, kBlock, 0, s>>>(a);
   return cudaGetLastError();
 }
 
 template <int KIND>
 cudaError_t launch_pathdep(const SimArgs& a, uint32_t ns, dim3 grid, cudaStream_t s) {
   switch (ns) {
-    case 1: pathdep_kernel<KIND, 1><<<grid, kBlock, 0, s>>>(a); break;
-    case 2: pathdep_kernel<KIND, 2><<<grid, kBlock, 0, s>>>(a); break;
-    case 4: pathdep_kernel<KIND, 4><<<grid, kBlock, 0, s>>>(a); break;
-    case 8: pathdep_kernel<KIND, 8><<<grid, kBlock, 0, s>>>(a); break;
-    default: pathdep_kernel<KIND, 16><<<grid, kBlock, 0, s>>>(a); break;
+    case 1: pathdep_kernel<KIND, 1, kMinBlocksPathdep><<<grid, kBlock, 0, s>>>(a); break;
+    case 2: pathdep_kernel<KIND, 2, kMinBlocksPathdep><<<grid, kBlock, 0, s>>>(a); break;
+    case 4: pathdep_kernel<KIND, 4, kMinBlocksWide><<<grid, kBlock, 0, s>>>(a); break;
+    case 8: pathdep_kernel<KIND, 8, kMinBlocksWide><<<grid, kBlock, 0, s>>>(a); break;
+    default: pathdep_kernel<KIND, 16, kMinBlocksWide><<<grid, kBlock, 0, s>>>(a); break;
   }
   return cudaGetLastError();
 }
@@ -412,8 +420,7 @@ int b200mc_generate_normals(b200mc_engine_t* e, uint64_t seed, uint32_t stream, 
   CU_TRY(e, cudaSetDevice(e->device));
   const size_t bytes = (size_t)n_paths * n_steps * sizeof(float);
   if (int rc = reserve(e, e->scratch_a, bytes)) return rc;
-  const uint64_t work = n_paths * ((n_steps + 3) / 4);
-  const unsigned grid = (unsigned)std::min<uint64_t>((work + 255) / 256, (uint64_t)e->prop.multiProcessorCount * 32);
+  const unsigned grid = (unsigned)std::min<uint64_t>((n_paths + 255) / 256, (uint64_t)e->prop.multiProcessorCount * 32);
   normals_kernel<<<grid, 256, 0, e->stream>>>((uint32_t)seed, (uint32_t)(seed >> 32), stream, path_begin, n_paths, n_steps,
                                               (float*)e->scratch_a.ptr);
   CU_TRY(e, cudaGetLastError());
@@ -515,7 +522,7 @@ int b200mc_measure_peaks(b200mc_engine_t* e, b200mc_peaks_t* out) {
   if (int rc = timed([&] { probe::philox_only<<<grid, block, 0, s>>>(it, 42u, 0u, (uint32_t*)buf); })) return rc;
   out->philox_per_s = threads * it / (ms * 1e-3);
   if (int rc = timed([&] { probe::normals_only<<<grid, block, 0, s>>>(it, 42u, 0u, (float*)buf, (long long*)e->scratch_b.ptr); })) return rc;
-  out->normals_per_s = threads * it * 4.0 / (ms * 1e-3);
+  out->normals_per_s = threads * (double)((it / 3) * 16) / (ms * 1e-3);
   std::vector<long long> clk((size_t)grid * 2);
   CU_TRY(e, cudaMemcpy(clk.data(), e->scratch_b.ptr, clk.size() * sizeof(long long), cudaMemcpyDeviceToHost));
   std::vector<double> mhz;

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "mc_kernels.cuh"
 #include "normal.cuh"
 #include "philox.cuh"
 
@@ -155,17 +156,12 @@ __global__ void normals_only(uint32_t iters, uint32_t k0, uint32_t k1, float* ou
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long n0 = global_ns();
   const long long t0 = clock64();
+  // iters Philox calls -> iters * 16/3 normals, through the production word layout (mc_kernels.cuh)
   float W = 0.f;
-  for (uint32_t it = 0; it < iters; ++it) {
-    const u32x4 x = philox4x32<10>(gid, it, 0u, 7u, k0, k1);
-    float r0, c0, s0, r1, c1, s1;
-    box_muller_pair(x.x, x.y, r0, c0, s0);
-    box_muller_pair(x.z, x.w, r1, c1, s1);
-    W = fmaf(r0, c0, W);
-    W = fmaf(r0, s0, W);
-    W = fmaf(r1, c1, W);
-    W = fmaf(r1, s1, W);
-  }
+  for_each_pair((uint64_t)gid, (iters / 3) * 16, 7u, k0, k1, [&](const NormalPair& p, int n_use) {
+    W = fmaf(p.rad, p.cs, W);
+    if (n_use > 1) W = fmaf(p.rad, p.sn, W);
+  });
   out[gid] = W;
   if (threadIdx.x == 0) {
     clocks[2 * blockIdx.x] = clock64() - t0;

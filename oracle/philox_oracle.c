@@ -7,12 +7,13 @@
  *     Random123 v1.14 include/Random123/philox.h).  The reference (OptionsLab) uses NumPy PCG64 /
  *     MT19937 and pins nothing about Philox, so this is pinned by the Random123 known-answer
  *     vectors only (tests/test_philox_oracle.py): "parity unpinned" w.r.t. the reference.
- * (2) b200mc_oracle_normals(): this repo's documented uniform->normal mapping (DESIGN.md "RNG stream
- *     contract"), evaluated in double precision with libm, as the ground truth the device's
+ * (2) b200mc_oracle_normals(): this repo's documented word->normal mapping (normal.cuh / DESIGN.md
+ *     "RNG stream contract"), evaluated in double precision with libm, as the ground truth the device's
  *     MUFU-approximated normals are compared to (abs tol ~1e-5).
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
@@ -40,29 +41,40 @@ static double word_to_unit(uint32_t x) { /* float in [1,2) built from the top 23
   return (double)f;
 }
 
-/* One Box-Muller pair from two words: radius from xa, angle from xb. */
-static void pair_to_normals(uint32_t xa, uint32_t xb, double* z_cos, double* z_sin) {
-  double u = 2.0 - word_to_unit(xa);       /* (0, 1], grid 2^-23 */
-  double turn = word_to_unit(xb) - 1.5;    /* [-0.5, 0.5) revolutions */
+/* One Box-Muller pair: radius from a full word, angle from a 16-bit integer h.
+ * theta = (2^23 + h) * step + bias with the device's FP32 constants (normal.cuh kAngleStep /
+ * kAngleBias), evaluated here in double: 65536 equally spaced angles covering [-pi, pi). */
+static void pair_to_normals(uint32_t radius_word, uint32_t h, double* z_cos, double* z_sin) {
+  const float step_f = 9.58737992428525768573e-5f;
+  const float bias_f = -807.38931197248091f;
+  double u = 2.0 - word_to_unit(radius_word);       /* (0, 1], grid 2^-23 */
+  double theta = (8388608.0 + (double)h) * (double)step_f + (double)bias_f;
   double radius = sqrt(-2.0 * log(u));
-  *z_cos = radius * cos(6.283185307179586476925 * turn);
-  *z_sin = radius * sin(6.283185307179586476925 * turn);
+  *z_cos = radius * cos(theta);
+  *z_sin = radius * sin(theta);
 }
 
-/* out[(p - path_begin) * n_steps + s] = normal for step s of global path p. */
+/* out[(p - path_begin) * n_steps + s] = normal for step s of global path p.
+ * Word stream of a path: Philox outputs of counters (path_lo, j, path_hi, stream), j = 0,1,2,...
+ * Triple t = words 3t, 3t+1, 3t+2 -> steps 4t..4t+3 (see optionslab_b200/csrc/normal.cuh). */
 void b200mc_oracle_normals(uint64_t seed, uint32_t stream, uint64_t path_begin, uint64_t n_paths,
                            uint32_t n_steps, double* out) {
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t n_triples = (n_steps + 3u) / 4u;
+  uint32_t n_calls = (3u * n_triples + 3u) / 4u;
+  uint32_t* w = (uint32_t*)malloc(sizeof(uint32_t) * 4u * (n_calls ? n_calls : 1u));
   for (uint64_t i = 0; i < n_paths; ++i) {
     uint64_t p = path_begin + i;
-    for (uint32_t blk = 0; blk * 4u < n_steps; ++blk) {
-      uint32_t ctr[4] = {(uint32_t)p, (uint32_t)(p >> 32), blk, stream};
-      uint32_t x[4];
+    for (uint32_t j = 0; j < n_calls; ++j) {
+      uint32_t ctr[4] = {(uint32_t)p, j, (uint32_t)(p >> 32), stream};
+      philox4x32_10(ctr, key, w + 4u * j);
+    }
+    for (uint32_t t = 0; t < n_triples; ++t) {
       double z[4];
-      philox4x32_10(ctr, key, x);
-      pair_to_normals(x[0], x[1], &z[0], &z[1]);
-      pair_to_normals(x[2], x[3], &z[2], &z[3]);
-      for (uint32_t j = 0; j < 4 && blk * 4u + j < n_steps; ++j) out[i * n_steps + blk * 4u + j] = z[j];
+      pair_to_normals(w[3u * t], w[3u * t + 2u] & 0xffffu, &z[0], &z[1]);
+      pair_to_normals(w[3u * t + 1u], w[3u * t + 2u] >> 16, &z[2], &z[3]);
+      for (uint32_t j = 0; j < 4u && 4u * t + j < n_steps; ++j) out[i * n_steps + 4u * t + j] = z[j];
     }
   }
+  free(w);
 }

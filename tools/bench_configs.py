@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""Per-config measurements for BASELINE.json configs C1-C4 (C5 is bench.py): kernel time (CUDA events
+inside the engine), end-to-end API time, achieved fraction of the measured XU/issue peaks, and the
+NumPy oracle timed on a bounded sample next to it.  Writes one JSON line per config."""
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import optionslab_b200 as ob  # noqa: E402
+from optionslab_b200 import _ffi  # noqa: E402
+from oracle import reference_mc as orc  # noqa: E402  (CPU baseline / checker only)
+
+P = dict(S=100.0, K=100.0, T=1.0, r=0.05, sigma=0.2)
+# per path-step (instructions, MUFU) of each kernel family, from the shipped SASS (profiles/r01_sass_*.txt)
+BUDGET = {"european": (202 / 16, 2.0), "asian": (266 / 16, 3.0), "barrier": (250 / 16, 2.0)}
+
+
+def timed(fn, reps=5):
+    fn()
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = fn()
+        best = min(best, time.perf_counter() - t0)
+    return best, out
+
+
+def main():
+    eng = _ffi.get_engine(0)
+    peaks = eng.measure_peaks()
+    rows = []
+
+    def record(name, family, path_steps, traj_steps, api_fn, cpu_fn, cpu_steps, note=""):
+        eng.set_kernel_timing(True)
+        api_s, result = timed(api_fn)
+        kt = eng.kernel_timing()
+        eng.set_kernel_timing(False)
+        t0 = time.perf_counter()
+        cpu_result = cpu_fn()
+        cpu_s = time.perf_counter() - t0
+        instr, mufu = BUDGET[family]
+        rate = traj_steps / (kt["min_ms"] * 1e-3)
+        rows.append({"config": name, "kernel_ms": kt["min_ms"], "api_ms": api_s * 1e3,
+                     "path_steps_per_s_kernel": path_steps / (kt["min_ms"] * 1e-3), "path_steps_per_s_api": path_steps / api_s,
+                     "trajectory_steps_per_s_kernel": rate,
+                     "xu_frac": rate * mufu / peaks["mufu_per_s"], "issue_frac": rate * instr / peaks["issue_per_s"],
+                     "result": result, "cpu_oracle": {"seconds": cpu_s, "path_steps_per_s": cpu_steps / cpu_s, "result": cpu_result,
+                                                      "cores": 1, "kind": "port"}, "note": note})
+        print(json.dumps(rows[-1]), flush=True)
+
+    # C1: European call, 100k paths x 252 steps
+    pr = ob.MonteCarloPricer(100_000, 252, seed=42)
+    record("C1 European call 100k x 252", "european", 100_000 * 252, 100_000 * 252,
+           lambda: pr.price(**P, option_type="call"),
+           lambda: orc.european_price(**P, option_type="call", num_simulations=100_000, num_steps=252, seed=42).price, 100_000 * 252)
+    # C2: Greeks, 1M x 252, 14 CRN scenarios in one launch (reference: 14 separate simulations)
+    pr2 = ob.MonteCarloPricer(1_000_000, 252, seed=42)
+    cpu_pr = lambda S, K, T, r, s, q: orc.european_price(S, K, T, r, s, "call", q, num_simulations=100_000, num_steps=252, seed=42).price
+    record("C2 Greeks (14 CRN scenarios) 1M x 252", "european", 1_000_000 * 252, 1_000_000 * 252,
+           lambda: dict(pr2.greeks(**P, option_type="call")),
+           lambda: dict(orc.greeks_bump_and_revalue(cpu_pr, **P)), 14 * 100_000 * 252,
+           note="CPU oracle at 100k paths, 14 re-simulations; path-steps counted once per re-simulation on the CPU side")
+    # C3: arithmetic Asian call, 4M x 252
+    asian = ob.AsianOption(**P, seed=42)
+    record("C3 Asian arithmetic call 4M x 252", "asian", 4_000_000 * 252, 4_000_000 * 252,
+           lambda: float(asian.price(4_000_000, 252)),
+           lambda: float(orc.exotic_price("asian", **P, seed=42, n_paths=100_000, n_steps=252)), 100_000 * 252,
+           note="CPU oracle at 100k paths (the full path array of 4M x 253 doubles is 8 GB per temporary)")
+    # C4: up-and-out barrier call, 16M x 365
+    bar = ob.BarrierOption(**P, seed=42, barrier=120.0)
+    record("C4 up-and-out barrier call 16M x 365", "barrier", 16_000_000 * 365, 16_000_000 * 365,
+           lambda: float(bar.price(16_000_000, 365, "up-and-out")),
+           lambda: float(orc.exotic_price("barrier", **P, seed=42, n_paths=100_000, n_steps=365, barrier=120.0)), 100_000 * 365,
+           note="CPU oracle at 100k paths (16M x 366 doubles = 46.8 GB per array does not fit)")
+    out = {"peaks": peaks, "device": eng.info(), "rows": rows}
+    path = os.path.join(ROOT, "gpurun_out", "configs_r01.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
