@@ -175,6 +175,7 @@ def run_engine_arm(args):
     torch.cuda.set_device(local)
     import torch.distributed as dist
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     ctx = distributed.init(backend="nccl") if world > 1 else None
     eng = _ffi.get_engine(local)
     dev = torch.device("cuda", local)
