@@ -70,6 +70,12 @@ typedef struct {
   double sum, sum_sq, n;
 } b200mc_moments_t;
 
+/* Moments for the terminal-spot control variate (src/pricing_models/monte_carlo.py:154-186):
+ * sums over samples of payoff, payoff^2, S_T, S_T^2 and payoff*S_T (all undiscounted), and n. */
+typedef struct {
+  double sum_payoff, sum_payoff_sq, sum_terminal, sum_terminal_sq, sum_payoff_terminal, n;
+} b200mc_cv_moments_t;
+
 typedef struct {
   int32_t device;
   int32_t sm_count;
@@ -125,6 +131,13 @@ int b200mc_simulate_device(b200mc_engine_t* eng, const b200mc_spec_t* spec, cons
                            uint32_t n_opt, uint32_t n_scen, uint64_t seed, uint32_t stream_base,
                            uint64_t path_begin, uint64_t n_paths, b200mc_moments_t* out_dev,
                            void* cuda_stream);
+
+/* European payoff + the sums np.cov(discounted, terminal) needs, same launch shape as b200mc_simulate
+ * (spec->kind must be B200MC_EUROPEAN).  Replaces price_with_control_variate's simulation and
+ * reductions (src/pricing_models/monte_carlo.py:166-186); beta and the adjustment stay on the host. */
+int b200mc_simulate_control_variate(b200mc_engine_t* eng, const b200mc_spec_t* spec, const b200mc_params_t* params_host,
+                                    uint32_t n_opt, uint32_t n_scen, uint64_t seed, uint32_t stream_base,
+                                    uint64_t path_begin, uint64_t n_paths, b200mc_cv_moments_t* out_host);
 
 /* ---- FP64 parity mode: price from caller-supplied normal draws ------------------------------- *
  * Z is row-major [n_paths][spec->n_steps] FP64 — exactly the array the reference draws at

@@ -44,6 +44,8 @@ class Peaks(C.Structure):
 PARAMS_DTYPE = np.dtype([("S", "f8"), ("K", "f8"), ("T", "f8"), ("r", "f8"), ("sigma", "f8"), ("q", "f8"),
                          ("barrier", "f8"), ("reserved", "f8")])
 MOMENTS_DTYPE = np.dtype([("sum", "f8"), ("sum_sq", "f8"), ("n", "f8")])
+CV_MOMENTS_DTYPE = np.dtype([("sum_payoff", "f8"), ("sum_payoff_sq", "f8"), ("sum_terminal", "f8"), ("sum_terminal_sq", "f8"),
+                             ("sum_payoff_terminal", "f8"), ("n", "f8")])
 
 # name -> (restype, argtypes); also the list the CPU tests check the .so exports against the header.
 _P = C.c_void_p
@@ -57,6 +59,8 @@ SIGNATURES = {
                                   C.c_uint64, C.c_uint64, _P]),
     "b200mc_simulate_device": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
                                          C.c_uint64, C.c_uint64, _P, _P]),
+    "b200mc_simulate_control_variate": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
+                                                  C.c_uint64, C.c_uint64, _P]),
     "b200mc_payoffs_from_normals": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_int, _P, C.c_uint64, _P, _P]),
     "b200mc_payoffs_from_normals_device": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_int, _P, C.c_uint64, _P, _P, _P]),
     "b200mc_generate_normals": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, _P]),
@@ -171,16 +175,16 @@ class Engine:
 
     # -- hot path ---------------------------------------------------------------------------
     def simulate(self, spec: Spec, params: np.ndarray, seed: int, n_paths: int, *, stream_base: int = 0,
-                 path_begin: int = 0) -> np.ndarray:
-        """params: PARAMS_DTYPE array [n_opt, n_scen] -> MOMENTS_DTYPE array [n_opt, n_scen] (host buffers)."""
+                 path_begin: int = 0, control_variate: bool = False) -> np.ndarray:
+        """params: PARAMS_DTYPE array [n_opt, n_scen] -> MOMENTS_DTYPE (or CV_MOMENTS_DTYPE) array [n_opt, n_scen]."""
         params = np.ascontiguousarray(params, dtype=PARAMS_DTYPE)
         if params.ndim != 2:
             raise MonteCarloError("params must have shape [n_opt, n_scen]")
-        out = np.empty(params.shape, dtype=MOMENTS_DTYPE)
-        rc = self._lib.b200mc_simulate(self._h, C.byref(spec), params.ctypes.data, params.shape[0], params.shape[1],
-                                       int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF,
-                                       int(path_begin), int(n_paths), out.ctypes.data)
-        self._check(rc, "b200mc_simulate")
+        out = np.empty(params.shape, dtype=CV_MOMENTS_DTYPE if control_variate else MOMENTS_DTYPE)
+        fn = self._lib.b200mc_simulate_control_variate if control_variate else self._lib.b200mc_simulate
+        rc = fn(self._h, C.byref(spec), params.ctypes.data, params.shape[0], params.shape[1],
+                int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF, int(path_begin), int(n_paths), out.ctypes.data)
+        self._check(rc, "b200mc_simulate_control_variate" if control_variate else "b200mc_simulate")
         return out
 
     def simulate_device(self, spec: Spec, params_ptr: int, n_opt: int, n_scen: int, seed: int, n_paths: int, out_ptr: int,

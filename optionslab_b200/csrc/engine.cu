@@ -132,10 +132,15 @@ constexpr int kMinBlocksPathdep = 3;  // Asian / barrier / lookback, 1-2 scenari
 constexpr int kMinBlocksWide = 2;     // 4-16 scenarios (<= 128 registers)
 
 template <int NS>
-cudaError_t launch_european(const SimArgs& a, bool anti, dim3 grid, cudaStream_t s) {
+cudaError_t launch_european(const SimArgs& a, bool anti, bool cv, dim3 grid, cudaStream_t s) {
   constexpr int kMinBlocks = NS <= 2 ? kMinBlocksSmall : kMinBlocksWide;
-  if (anti) european_kernel<NS, true, kMinBlocks><<<grid, kBlock, 0, s>>>(a);
-  else european_kernel<NS, false, kMinBlocks><<<grid, kBlock, 0, s>>>(a);
+  if (cv) {
+    if (anti) european_kernel<NS, true, kMinBlocksWide, true><<<grid, kBlock, 0, s>>>(a);
+    else european_kernel<NS, false, kMinBlocksWide, true><<<grid, kBlock, 0, s>>>(a);
+  } else {
+    if (anti) european_kernel<NS, true, kMinBlocks><<<grid, kBlock, 0, s>>>(a);
+    else european_kernel<NS, false, kMinBlocks><<<grid, kBlock, 0, s>>>(a);
+  }
   return cudaGetLastError();
 }
 
@@ -154,19 +159,20 @@ cudaError_t launch_pathdep(const SimArgs& a, uint32_t ns, dim3 grid, cudaStream_
 // Enqueue simulation + fold on `stream`; params/out are device pointers.
 int enqueue_simulation(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc_params_t* params_dev, uint32_t n_opt,
                        uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
-                       b200mc_moments_t* out_dev, cudaStream_t stream, bool time_it) {
+                       void* out_dev, cudaStream_t stream, bool time_it, bool cv = false) {
   if (int rc = check_spec(e, spec)) return rc;
   if (!params_dev || !out_dev) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
   if (n_opt == 0 || n_paths == 0) return fail(e, B200MC_ERR_INVALID, "n_opt and n_paths must be >= 1");
   if (n_scen == 0 || n_scen > B200MC_MAX_SCENARIOS)
     return fail(e, B200MC_ERR_INVALID, "n_scen must be in [1, %d]", B200MC_MAX_SCENARIOS);
 
+  if (cv && spec->kind != B200MC_EUROPEAN) return fail(e, B200MC_ERR_INVALID, "the control variate is defined for the European payoff only");
   const uint32_t ns = pad_scenarios(n_scen);
   uint32_t tiles, ppt;
   plan_tiles(e, n_opt, n_paths, tiles, ppt);
   const uint64_t ctas = (uint64_t)tiles * n_opt;
   if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
-  if (int rc = reserve(e, e->partials, ctas * 2 * ns * sizeof(double))) return rc;
+  if (int rc = reserve(e, e->partials, ctas * (cv ? 5 : 2) * ns * sizeof(double))) return rc;
 
   SimArgs a{};
   a.params = params_dev;
@@ -196,11 +202,11 @@ int enqueue_simulation(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc
   switch (spec->kind) {
     case B200MC_EUROPEAN:
       switch (ns) {
-        case 1: err = launch_european<1>(a, spec->antithetic, grid, stream); break;
-        case 2: err = launch_european<2>(a, spec->antithetic, grid, stream); break;
-        case 4: err = launch_european<4>(a, spec->antithetic, grid, stream); break;
-        case 8: err = launch_european<8>(a, spec->antithetic, grid, stream); break;
-        default: err = launch_european<16>(a, spec->antithetic, grid, stream); break;
+        case 1: err = launch_european<1>(a, spec->antithetic, cv, grid, stream); break;
+        case 2: err = launch_european<2>(a, spec->antithetic, cv, grid, stream); break;
+        case 4: err = launch_european<4>(a, spec->antithetic, cv, grid, stream); break;
+        case 8: err = launch_european<8>(a, spec->antithetic, cv, grid, stream); break;
+        default: err = launch_european<16>(a, spec->antithetic, cv, grid, stream); break;
       }
       break;
     case B200MC_ASIAN_ARITH: err = launch_pathdep<B200MC_ASIAN_ARITH>(a, ns, grid, stream); break;
@@ -214,7 +220,10 @@ int enqueue_simulation(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc
     e->timed += 1;
   }
   const double samples = (double)n_paths * (spec->antithetic ? 2.0 : 1.0);
-  fold_kernel<<<n_opt * n_scen, 32, 0, stream>>>((const double*)e->partials.ptr, params_dev, out_dev, n_scen, ns, tiles, samples);
+  if (cv)
+    fold_cv_kernel<<<n_opt * n_scen, 32, 0, stream>>>((const double*)e->partials.ptr, params_dev, (b200mc_cv_moments_t*)out_dev, n_scen, ns, tiles, samples);
+  else
+    fold_kernel<<<n_opt * n_scen, 32, 0, stream>>>((const double*)e->partials.ptr, params_dev, (b200mc_moments_t*)out_dev, n_scen, ns, tiles, samples);
   CU_TRY(e, cudaGetLastError());
   e->launches += 2;
   return 0;
@@ -352,16 +361,16 @@ int b200mc_simulate_device(b200mc_engine_t* e, const b200mc_spec_t* spec, const 
                             (cudaStream_t)cuda_stream, e->timing);
 }
 
-int b200mc_simulate(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_host, uint32_t n_opt,
-                    uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
-                    b200mc_moments_t* out_host) {
+static int simulate_host(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_host, uint32_t n_opt,
+                         uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
+                         void* out_host, bool cv) {
   if (!e) return B200MC_ERR_INVALID;
   std::lock_guard<std::mutex> g(e->mutex);
   if (!params_host || !out_host) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
   if (n_opt == 0 || n_scen == 0 || n_scen > B200MC_MAX_SCENARIOS) return fail(e, B200MC_ERR_INVALID, "bad n_opt / n_scen");
   CU_TRY(e, cudaSetDevice(e->device));
   const size_t n = (size_t)n_opt * n_scen;
-  const size_t in_bytes = n * sizeof(b200mc_params_t), out_bytes = n * sizeof(b200mc_moments_t);
+  const size_t in_bytes = n * sizeof(b200mc_params_t), out_bytes = n * (cv ? sizeof(b200mc_cv_moments_t) : sizeof(b200mc_moments_t));
   if (int rc = reserve(e, e->params_dev, in_bytes)) return rc;
   if (int rc = reserve(e, e->moments_dev, out_bytes)) return rc;
   if (int rc = reserve_pinned(e, in_bytes + out_bytes)) return rc;
@@ -370,12 +379,24 @@ int b200mc_simulate(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_
   memcpy(pin_in, params_host, in_bytes);
   CU_TRY(e, cudaMemcpyAsync(e->params_dev.ptr, pin_in, in_bytes, cudaMemcpyHostToDevice, e->stream));
   if (int rc = enqueue_simulation(e, spec, (const b200mc_params_t*)e->params_dev.ptr, n_opt, n_scen, seed, stream_base,
-                                  path_begin, n_paths, (b200mc_moments_t*)e->moments_dev.ptr, e->stream, e->timing))
+                                  path_begin, n_paths, e->moments_dev.ptr, e->stream, e->timing, cv))
     return rc;
   CU_TRY(e, cudaMemcpyAsync(pin_out, e->moments_dev.ptr, out_bytes, cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
   memcpy(out_host, pin_out, out_bytes);
   return 0;
+}
+
+int b200mc_simulate(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_host, uint32_t n_opt,
+                    uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
+                    b200mc_moments_t* out_host) {
+  return simulate_host(e, spec, params_host, n_opt, n_scen, seed, stream_base, path_begin, n_paths, out_host, false);
+}
+
+int b200mc_simulate_control_variate(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_host,
+                                    uint32_t n_opt, uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin,
+                                    uint64_t n_paths, b200mc_cv_moments_t* out_host) {
+  return simulate_host(e, spec, params_host, n_opt, n_scen, seed, stream_base, path_begin, n_paths, out_host, true);
 }
 
 int b200mc_payoffs_from_normals_device(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* p, int accumulate,

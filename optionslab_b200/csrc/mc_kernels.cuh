@@ -151,8 +151,11 @@ __device__ __forceinline__ float terminal_sum(uint64_t path, uint32_t n_steps, u
   return W;
 }
 
-template <int NS, bool ANTI, int MINB>
+// CV = true additionally accumulates sum S_T, sum S_T^2 and sum payoff*S_T per scenario (the
+// terminal-spot control variate of monte_carlo.py:154-186): 5 sums instead of 2.
+template <int NS, bool ANTI, int MINB, bool CV = false>
 __global__ void __launch_bounds__(kBlock, MINB) european_kernel(const SimArgs a) {
+  constexpr int NM = CV ? 5 : 2;
   __shared__ Coef coef[NS];
   const uint32_t opt = blockIdx.x / a.tiles;
   const uint32_t tile = blockIdx.x - opt * a.tiles;
@@ -162,9 +165,9 @@ __global__ void __launch_bounds__(kBlock, MINB) european_kernel(const SimArgs a)
   }
   __syncthreads();
 
-  float acc[2 * NS];
+  float acc[NM * NS];
 #pragma unroll
-  for (int i = 0; i < 2 * NS; ++i) acc[i] = 0.0f;
+  for (int i = 0; i < NM * NS; ++i) acc[i] = 0.0f;
 
   const uint32_t stream = a.stream_base + opt;
   const bool is_put = a.is_put != 0;
@@ -176,17 +179,21 @@ __global__ void __launch_bounds__(kBlock, MINB) european_kernel(const SimArgs a)
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
       const Coef q = coef[k];
-      float p = vanilla(mufu_ex2(fmaf(q.c, W, q.a)), q.kappa, is_put);
-      acc[2 * k] += p;
-      acc[2 * k + 1] = fmaf(p, p, acc[2 * k + 1]);
-      if (ANTI) {
-        p = vanilla(mufu_ex2(fmaf(-q.c, W, q.a)), q.kappa, is_put);
-        acc[2 * k] += p;
-        acc[2 * k + 1] = fmaf(p, p, acc[2 * k + 1]);
+#pragma unroll
+      for (int mirror = 0; mirror < (ANTI ? 2 : 1); ++mirror) {
+        const float e = mufu_ex2(fmaf(mirror ? -q.c : q.c, W, q.a));  // S_T / S_0
+        const float p = vanilla(e, q.kappa, is_put);
+        acc[NM * k] += p;
+        acc[NM * k + 1] = fmaf(p, p, acc[NM * k + 1]);
+        if (CV) {
+          acc[NM * k + 2] += e;
+          acc[NM * k + 3] = fmaf(e, e, acc[NM * k + 3]);
+          acc[NM * k + 4] = fmaf(p, e, acc[NM * k + 4]);
+        }
       }
     }
   }
-  block_reduce_store<2 * NS>(acc, a.partials + (size_t)blockIdx.x * (2 * NS));
+  block_reduce_store<NM * NS>(acc, a.partials + (size_t)blockIdx.x * (NM * NS));
 }
 
 // ============================ path-dependent kinds (register state) =============================
@@ -293,6 +300,34 @@ __global__ void __launch_bounds__(32) fold_kernel(const double* __restrict__ par
     out[blockIdx.x].sum = s1 * S;
     out[blockIdx.x].sum_sq = s2 * S * S;
     out[blockIdx.x].n = samples;
+  }
+}
+
+// Control-variate flavour: 5 sums per (option, scenario), all quadratic ones scale with S^2.
+__global__ void __launch_bounds__(32) fold_cv_kernel(const double* __restrict__ partials, const b200mc_params_t* __restrict__ params,
+                                                     b200mc_cv_moments_t* __restrict__ out, uint32_t n_scen, uint32_t ns_pad,
+                                                     uint32_t tiles, double samples) {
+  const uint32_t opt = blockIdx.x / n_scen, k = blockIdx.x - opt * n_scen;
+  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (uint32_t t = threadIdx.x; t < tiles; t += 32) {
+    const double* p = partials + ((size_t)opt * tiles + t) * (5 * ns_pad) + 5 * k;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) s[i] += p[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], off);
+  if (threadIdx.x == 0) {
+    const double S = params[(size_t)opt * n_scen + k].S;
+    b200mc_cv_moments_t m;
+    m.sum_payoff = s[0] * S;
+    m.sum_payoff_sq = s[1] * S * S;
+    m.sum_terminal = s[2] * S;
+    m.sum_terminal_sq = s[3] * S * S;
+    m.sum_payoff_terminal = s[4] * S * S;
+    m.n = samples;
+    out[blockIdx.x] = m;
   }
 }
 

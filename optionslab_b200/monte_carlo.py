@@ -80,6 +80,16 @@ class MonteCarloPricer:
             return MCResult(price, float(runtime.discounted_std_error(m[0], r, T)), int(m[0]["n"]))
         return price
 
+    def price_with_control_variate(self, S: float, K: float, T: float, r: float, sigma: float,
+                                   option_type: Literal["call", "put"], q: float = 0.0, seed: Optional[int] = None) -> float:
+        """Terminal spot as control variate, E[S_T] = S*exp((r-q)T) (monte_carlo.py:154-186).  The five
+        sums np.cov needs come out of the same fused launch as the payoff."""
+        actual_seed = seed if seed is not None else self.seed
+        spec = _ffi.make_spec(_ffi.EUROPEAN, self._steps(), is_put=runtime.validate_option_type(option_type), antithetic=True)
+        m = runtime.simulate(spec, _ffi.make_params(S, K, T, r, sigma, q).reshape(1, 1), actual_seed, self.num_simulations,
+                             control_variate=True)[0, 0]
+        return runtime.control_variate_price(m, S, T, r, q)
+
     # -- fused common-random-number surface ---------------------------------------------------
     def price_scenarios(self, scenarios: Sequence, option_type: str, seed: Optional[int] = None, **_ignored):
         """Prices of up to 16 (S,K,T,r,sigma,q) scenarios sharing one set of draws, ONE launch."""

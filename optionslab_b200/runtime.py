@@ -24,21 +24,41 @@ def entropy_seed() -> int:
     return int.from_bytes(os.urandom(8), "little")
 
 
-def simulate(spec: _ffi.Spec, params: np.ndarray, seed: int, n_paths: int, *, stream_base: int = 0) -> np.ndarray:
+def simulate(spec: _ffi.Spec, params: np.ndarray, seed: int, n_paths: int, *, stream_base: int = 0,
+             control_variate: bool = False) -> np.ndarray:
     """Moments [n_opt, n_scen] over ALL ``n_paths`` global paths (sharded + all-reduced when a
-    distributed context is active)."""
+    distributed context is active).  Every field of the moment records is a plain sum, so the
+    combination across ranks is one element-wise all-reduce."""
     if n_paths < 1:
         raise MonteCarloError("n_paths must be >= 1")
     eng = _ffi.get_engine()
     ctx = distributed.current()
     if ctx is None or ctx.world_size == 1:
-        return eng.simulate(spec, params, seed, n_paths, stream_base=stream_base)
+        return eng.simulate(spec, params, seed, n_paths, stream_base=stream_base, control_variate=control_variate)
     begin, count = distributed.partition_paths(n_paths, ctx.rank, ctx.world_size)
     if count > 0:
-        local = eng.simulate(spec, params, seed, count, stream_base=stream_base, path_begin=begin)
+        local = eng.simulate(spec, params, seed, count, stream_base=stream_base, path_begin=begin,
+                             control_variate=control_variate)
     else:
-        local = np.zeros(np.shape(params), dtype=_ffi.MOMENTS_DTYPE)
+        local = np.zeros(np.shape(params), dtype=_ffi.CV_MOMENTS_DTYPE if control_variate else _ffi.MOMENTS_DTYPE)
     return distributed.allreduce_moments(local, ctx)
+
+
+def control_variate_price(m, S, T, r, q) -> float:
+    """Terminal-spot control variate from the 5 sums (src/pricing_models/monte_carlo.py:176-186):
+    discounted = exp(-rT)*payoff, beta = cov(discounted, S_T)/var(S_T) with ddof = 1 (np.cov),
+    beta = 0 when var(S_T) <= 1e-10, result = mean(discounted) - beta*(mean(S_T) - S*exp((r-q)T))."""
+    n = float(m["n"])
+    disc = math.exp(-r * T)
+    mean_d = disc * float(m["sum_payoff"]) / n
+    mean_s = float(m["sum_terminal"]) / n
+    forward = S * math.exp((r - q) * T)
+    if n < 2:
+        return mean_d
+    cov_ds = disc * (float(m["sum_payoff_terminal"]) - float(m["sum_payoff"]) * float(m["sum_terminal"]) / n) / (n - 1)
+    var_s = (float(m["sum_terminal_sq"]) - float(m["sum_terminal"]) ** 2 / n) / (n - 1)
+    beta = cov_ds / var_s if var_s > 1e-10 else 0.0
+    return float(mean_d - beta * (mean_s - forward))
 
 
 def discounted_price(moments, r, T):

@@ -127,6 +127,30 @@ def european_price(S, K, T, r, sigma, option_type, q=0.0, *, num_simulations, nu
     return OracleResult(discounted_mean(pay, r, T), discounted_std_error(pay, r, T), len(pay), pay)
 
 
+def control_variate_from_terminal(terminal: np.ndarray, S, K, T, r, q, option_type: str) -> float:
+    """``price_with_control_variate`` given the simulated terminals.
+
+    src/pricing_models/monte_carlo.py:168-186: discounted payoffs, ``np.cov`` (ddof=1) against the
+    terminal spot, beta zeroed when var(S_T) <= 1e-10, adjustment by mean(S_T) - S*exp((r-q)T).
+    """
+    pay = vanilla_payoffs(terminal, K, option_type)
+    discounted = np.exp(-r * T) * pay
+    control_mean = np.mean(terminal)
+    forward = S * np.exp((r - q) * T)
+    cov = np.cov(discounted, terminal)
+    beta = cov[0, 1] / cov[1, 1] if cov[1, 1] > 1e-10 else 0.0
+    return float(np.mean(discounted) - beta * (control_mean - forward))
+
+
+def european_price_control_variate(S, K, T, r, sigma, option_type, q=0.0, *, num_simulations, num_steps, seed) -> float:
+    """``MonteCarloPricer(...).price_with_control_variate`` (monte_carlo.py:154-186)."""
+    if num_steps == 1:
+        terminal = gbm_terminal_single_step(S, T, r, sigma, q, normals_generator(seed, num_simulations))
+    else:
+        terminal = gbm_terminal_from_normals(S, T, r, sigma, q, normals_generator(seed, (num_simulations, num_steps)))
+    return control_variate_from_terminal(terminal, S, K, T, r, q, option_type)
+
+
 # --------------------------------------------------------------------------
 # MonteCarloPricerUni: batched terminals (NumPy backend)
 # --------------------------------------------------------------------------

@@ -74,6 +74,12 @@ def main():
     pr = MCP(20000, 64, seed=7)
     eu["20000x64_call_q"] = {"price": pr.price(105.0, 95.0, 0.75, 0.03, 0.35, "call", q=0.02, return_error=True).price}
     g["european"] = eu
+    g["control_variate"] = {
+        "10000x50_call": MCP(10000, 50, seed=42).price_with_control_variate(**P, option_type="call"),
+        "10000x50_put": MCP(10000, 50, seed=42).price_with_control_variate(**P, option_type="put"),
+        "100000x1_call": MCP(100000, 1, seed=42).price_with_control_variate(**P, option_type="call"),
+        "20000x64_call_q": MCP(20000, 64, seed=7).price_with_control_variate(105.0, 95.0, 0.75, 0.03, 0.35, "call", q=0.02),
+    }
 
     # --- MonteCarloPricerUni NumPy backend (monte_carlo_unified.py:451-689) ---------
     uni = Uni(10000, 50, seed=42, use_numba=False, use_gpu=False)

@@ -1,0 +1,65 @@
+"""GPU: the sharded host path end to end with the real kernels — two ranks (gloo for the moment
+all-reduce, both on cuda:0 because the test box has one GPU) must reproduce the one-process price.
+The NCCL flavour of the same code is exercised by bench.py under torchrun (profiles/r01_bench_n2.json)."""
+
+import json
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+P = dict(S=100.0, K=100.0, T=1.0, r=0.05, sigma=0.2)
+
+
+def _prices():
+    import optionslab_b200 as ob
+
+    out = {}
+    res = ob.MonteCarloPricer(300_001, 24, seed=11).price(**P, option_type="call", return_error=True)
+    out["euro"] = [res.price, res.std_error, res.n_paths]
+    out["asian"] = float(ob.AsianOption(**P, seed=5).price(200_003, 20))
+    out["barrier"] = float(ob.BarrierOption(**P, seed=5, barrier=115.0).price(200_003, 20, "up-and-in", "put"))
+    uni = ob.MonteCarloPricerUni(100_001, 16, seed=3)
+    out["batch"] = uni.price_batch([100.0, 90.0, 110.0], [100.0, 95.0, 105.0], [1.0, 0.5, 2.0], [0.05] * 3, [0.2, 0.3, 0.1], "put").tolist()
+    out["greeks"] = dict(ob.MonteCarloPricer(100_001, 12, seed=2).greeks(**P, option_type="call"))
+    return out
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK="0", B200MC_DEVICE="0",
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from optionslab_b200 import distributed
+
+    distributed.init(backend="gloo")
+    res = _prices()
+    with open(os.path.join(out_dir, f"rank{rank}.json"), "w") as f:
+        json.dump(res, f)
+    distributed.shutdown()
+
+
+def test_two_ranks_reproduce_single_process_prices(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    from optionslab_b200 import distributed
+
+    distributed.shutdown()
+    whole = _prices()
+    for rank in range(2):
+        got = json.load(open(os.path.join(tmp_path, f"rank{rank}.json")))
+        assert got["euro"][2] == whole["euro"][2] == 600_002
+        # per-thread FP32 partial sums regroup when the path range is split: agreement is ~1e-7, far below 1 SE
+        assert got["euro"][0] == pytest.approx(whole["euro"][0], rel=1e-6)
+        assert got["euro"][1] == pytest.approx(whole["euro"][1], rel=1e-5)
+        assert got["asian"] == pytest.approx(whole["asian"], rel=1e-6)
+        assert got["barrier"] == pytest.approx(whole["barrier"], rel=1e-6)
+        np.testing.assert_allclose(got["batch"], whole["batch"], rtol=1e-6)
+        for k, v in whole["greeks"].items():
+            assert got["greeks"][k] == pytest.approx(v, rel=2e-3, abs=2e-3), k
+    a = json.load(open(os.path.join(tmp_path, "rank0.json")))
+    b = json.load(open(os.path.join(tmp_path, "rank1.json")))
+    assert a == b  # every rank holds the identical all-reduced result

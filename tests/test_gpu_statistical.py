@@ -102,6 +102,29 @@ def test_config2_greeks_1m_x_252_crn_single_launch(engine):
     assert pr.delta(**P) == g["delta"] and pr.vega(**P) == g["vega"]
 
 
+def test_control_variate_next_row(engine):
+    """price_with_control_variate (monte_carlo.py:154-186): same draws => FP32 path vs FP64 oracle on the engine's
+    own stream; statistically => closer to Black-Scholes than the plain estimator's noise."""
+    n, steps, seed = 50_000, 20, 13
+    pr = ob.MonteCarloPricer(n, steps, seed=seed)
+    for ot, bs in (("call", BS_CALL), ("put", BS_PUT)):
+        got = pr.price_with_control_variate(**P, option_type=ot)
+        terminal = orc.gbm_terminal_from_normals(P["S"], P["T"], P["r"], P["sigma"], 0.0, po.normals(seed, n, steps))
+        want = orc.control_variate_from_terminal(terminal, P["S"], P["K"], P["T"], P["r"], 0.0, ot)
+        assert got == pytest.approx(want, rel=3e-4)
+        plain = pr.price(**P, option_type=ot, return_error=True)
+        assert abs(got - bs) < 4 * plain.std_error
+    big = ob.MonteCarloPricer(2_000_000, 50, seed=1)
+    cv = big.price_with_control_variate(**P, option_type="call")
+    assert abs(cv - BS_CALL) < 0.015  # plain SE at this size is 0.0074; the control removes most of it
+    m = engine.simulate(_ffi.make_spec(_ffi.EUROPEAN, 8, antithetic=True), _ffi.make_params(**P).reshape(1, 1), 3, 10_000, control_variate=True)[0, 0]
+    m2 = engine.simulate(_ffi.make_spec(_ffi.EUROPEAN, 8, antithetic=True), _ffi.make_params(**P).reshape(1, 1), 3, 10_000)[0, 0]
+    assert m["n"] == 20_000 and m["sum_payoff"] == m2["sum"] and m["sum_payoff_sq"] == m2["sum_sq"]
+    assert m["sum_terminal"] / m["n"] == pytest.approx(100 * np.exp(0.05), rel=5e-3)
+    with pytest.raises(ob.MonteCarloError, match="European"):
+        engine.simulate(_ffi.make_spec(_ffi.ASIAN_ARITH, 8), _ffi.make_params(**P).reshape(1, 1), 3, 100, control_variate=True)
+
+
 def test_fused_greeks_equal_separate_repricings_bitwise():
     """One launch with 14 scenarios == 14 launches of 1 scenario (same draws, same reduction order)."""
     pr = ob.MonteCarloPricer(50_000, 32, seed=9)

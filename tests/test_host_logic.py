@@ -121,6 +121,22 @@ def test_moment_arithmetic_matches_reference_formulas():
     assert float(runtime.discounted_std_error(m, 0.05, 1.0)) == pytest.approx(orc.discounted_std_error(pay, 0.05, 1.0), rel=1e-10)
 
 
+def test_control_variate_formula_matches_reference_restatement():
+    """runtime.control_variate_price over the five sums == np.cov-based reference formula."""
+    rng = np.random.default_rng(5)
+    S, K, T, r, q = 100.0, 105.0, 0.75, 0.03, 0.01
+    terminal = S * np.exp(rng.normal(-0.02, 0.2, 50_000))
+    for ot in ("call", "put"):
+        pay = orc.vanilla_payoffs(terminal, K, ot)
+        m = np.zeros((), dtype=ob._ffi.CV_MOMENTS_DTYPE)
+        m["sum_payoff"], m["sum_payoff_sq"], m["sum_terminal"] = pay.sum(), (pay**2).sum(), terminal.sum()
+        m["sum_terminal_sq"], m["sum_payoff_terminal"], m["n"] = (terminal**2).sum(), (pay * terminal).sum(), len(pay)
+        assert runtime.control_variate_price(m, S, T, r, q) == pytest.approx(
+            orc.control_variate_from_terminal(terminal, S, K, T, r, q, ot), rel=1e-9)
+    m["sum_terminal"], m["sum_terminal_sq"] = 100.0 * 50_000, 100.0**2 * 50_000  # degenerate control: beta = 0
+    assert runtime.control_variate_price(m, S, T, r, q) == pytest.approx(np.exp(-r * T) * m["sum_payoff"] / m["n"], rel=1e-12)
+
+
 def test_partition_paths_is_an_exact_cover():
     for n in (1, 7, 1000, 16_000_000, 2**40 + 5):
         for w in (1, 2, 3, 4, 8):

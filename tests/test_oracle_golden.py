@@ -50,6 +50,17 @@ def test_european_with_dividend(goldens):
     assert res.price == pytest.approx(goldens["european"]["20000x64_call_q"]["price"], rel=REL)
 
 
+def test_control_variate_matches_reference(goldens):
+    if not _same_numpy(goldens):
+        pytest.skip("goldens recorded with another NumPy build")
+    g = goldens["control_variate"]
+    kw = dict(num_simulations=10000, num_steps=50, seed=42)
+    assert orc.european_price_control_variate(**P, option_type="call", **kw) == pytest.approx(g["10000x50_call"], rel=REL)
+    assert orc.european_price_control_variate(**P, option_type="put", **kw) == pytest.approx(g["10000x50_put"], rel=REL)
+    assert orc.european_price_control_variate(**P, option_type="call", num_simulations=100000, num_steps=1, seed=42) == pytest.approx(g["100000x1_call"], rel=REL)
+    assert orc.european_price_control_variate(105.0, 95.0, 0.75, 0.03, 0.35, "call", q=0.02, num_simulations=20000, num_steps=64, seed=7) == pytest.approx(g["20000x64_call_q"], rel=REL)
+
+
 def test_uni_matches_reference(goldens):
     if not _same_numpy(goldens):
         pytest.skip("goldens recorded with another NumPy build")

@@ -79,6 +79,33 @@ def main():
            lambda: float(bar.price(16_000_000, 365, "up-and-out")),
            lambda: float(orc.exotic_price("barrier", **P, seed=42, n_paths=100_000, n_steps=365, barrier=120.0)), 100_000 * 365,
            note="CPU oracle at 100k paths (16M x 366 doubles = 46.8 GB per array does not fit)")
+    # FP64 parity mode (HBM-bound by design: 8 bytes of Z per path-step, read once)
+    try:
+        import torch
+
+        dev = torch.device("cuda", 0)
+        n_paths, n_steps = 4_000_000, 252
+        Z = torch.randn((n_paths, n_steps), dtype=torch.float64, device=dev)
+        pay = torch.empty(2 * n_paths, dtype=torch.float64, device=dev)
+        mom = torch.empty(3, dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        for kind, name, anti in ((_ffi.EUROPEAN, "european", True), (_ffi.ASIAN_ARITH, "asian", False), (_ffi.BARRIER, "barrier", False)):
+            spec = _ffi.make_spec(kind, n_steps, antithetic=anti)
+            eng.set_kernel_timing(True)
+            for _ in range(4):
+                eng.payoffs_from_normals_device(spec, _ffi.make_params(**P, barrier=120.0), Z.data_ptr(), n_paths, pay.data_ptr(), mom.data_ptr(), stream)
+            torch.cuda.synchronize(dev)
+            kt = eng.kernel_timing()
+            eng.set_kernel_timing(False)
+            gbs = n_paths * n_steps * 8 / (kt["min_ms"] * 1e-3) / 1e9
+            rows.append({"config": f"FP64 parity mode {name} 4M x 252 (Z resident in HBM)", "kernel_ms": kt["min_ms"],
+                         "path_steps_per_s_kernel": n_paths * n_steps / (kt["min_ms"] * 1e-3), "hbm_gbs": gbs, "hbm_peak_gbs": hbm_peak,
+                         "hbm_frac": gbs / hbm_peak})
+            print(json.dumps(rows[-1]), flush=True)
+        del Z, pay
+    except Exception as exc:  # measurement extra; never fatal
+        print(json.dumps({"parity_mode_timing_failed": repr(exc)}), flush=True)
     out = {"peaks": peaks, "device": eng.info(), "rows": rows}
     path = os.path.join(ROOT, "gpurun_out", "configs_r01.json")
     os.makedirs(os.path.dirname(path), exist_ok=True)
