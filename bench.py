@@ -38,9 +38,9 @@ WORKLOAD = (f"C5: {N_OPT}-option European call grid ({N_STRIKES} strikes 60..140
             f"S=100 r=0.05 sigma=0.2) x {N_PATHS} paths x {N_STEPS} steps, each option simulated independently "
             f"(antithetic, own Philox stream)")
 # Instruction budget of the dominant kernel (european_kernel<1,true> inner loop, counted from the shipped SASS
-# with cuobjdump — profiles/r01_sass_european.txt): 202 issued instructions per 16 path-steps, of which 32 MUFU,
-# 48 IMAD.WIDE (fmaheavy pipe), 62 LOP3 + 12 LEA (ALU pipe).
-INSTR_PER_STEP, MUFU_PER_STEP, IMAD_PER_STEP, LOP_PER_STEP = 202 / 16, 2.0, 3.0, 74 / 16
+# with cuobjdump — profiles/r01_sass_european.txt): 88 issued instructions per Philox call = 8 path-steps, of which
+# 16 MUFU, 16 IMAD.WIDE (fmaheavy pipe), 18 LOP3 + 8 LEA.HI + 4 PRMT (ALU pipe).
+INSTR_PER_STEP, MUFU_PER_STEP, IMAD_PER_STEP, LOP_PER_STEP = 88 / 8, 2.0, 2.0, 30 / 8
 
 
 def grid_params():

@@ -127,8 +127,8 @@ void plan_tiles(const b200mc_engine* e, uint32_t n_opt, uint64_t n_paths, uint32
 // __launch_bounds__ minBlocksPerSM per kernel family, picked from measurements on B200
 // (profiles/r01_variants.txt): the schedulers want the three Philox chains of a superblock
 // interleaved, which needs ~60-75 registers; squeezing below 48 costs 5-10%.
-constexpr int kMinBlocksSmall = 4;    // European, 1-2 scenarios (61 registers)
-constexpr int kMinBlocksPathdep = 3;  // Asian / barrier / lookback, 1-2 scenarios (<= 78 registers)
+constexpr int kMinBlocksSmall = 6;    // European, 1-2 scenarios (40-47 registers)
+constexpr int kMinBlocksPathdep = 6;  // Asian / barrier / lookback, 1-2 scenarios (<= 40 registers)
 constexpr int kMinBlocksWide = 2;     // 4-16 scenarios (<= 128 registers)
 
 template <int NS>
@@ -543,7 +543,7 @@ int b200mc_measure_peaks(b200mc_engine_t* e, b200mc_peaks_t* out) {
   if (int rc = timed([&] { probe::philox_only<<<grid, block, 0, s>>>(it, 42u, 0u, (uint32_t*)buf); })) return rc;
   out->philox_per_s = threads * it / (ms * 1e-3);
   if (int rc = timed([&] { probe::normals_only<<<grid, block, 0, s>>>(it, 42u, 0u, (float*)buf, (long long*)e->scratch_b.ptr); })) return rc;
-  out->normals_per_s = threads * (double)((it / 3) * 16) / (ms * 1e-3);
+  out->normals_per_s = threads * (double)(it * 8) / (ms * 1e-3);
   std::vector<long long> clk((size_t)grid * 2);
   CU_TRY(e, cudaMemcpy(clk.data(), e->scratch_b.ptr, clk.size() * sizeof(long long), cudaMemcpyDeviceToHost));
   std::vector<double> mhz;

@@ -41,7 +41,7 @@ struct SimArgs {
 // Per-scenario FP32 coefficients, computed in FP64 once per CTA (the reference's constants:
 // dt, drift, vol of gbm_numpy.py:35-39 / exotic_options.py:54-56, moved to log2 units).
 struct Coef {
-  float c;      // sgn * sigma*sqrt(dt) * sqrt(2/ln2): log2-diffusion per unit of log2-radius draw
+  float c;      // sgn * sigma*sqrt(dt) * kCoefScaleD: log2-diffusion per unit of log2-radius draw
   float d;      // sgn * (r - q - sigma^2/2)*dt / ln2: log2-drift per step
   float a;      // n_steps * (unsigned d): terminal log2-drift (European)
   float kappa;  // K / S
@@ -53,7 +53,7 @@ __device__ __forceinline__ Coef make_coef(const b200mc_params_t& p, uint32_t n_s
   const double inv_ln2 = 1.44269504088896340736;
   const double dt = p.T / (double)n_steps;
   const double d = (p.r - p.q - 0.5 * p.sigma * p.sigma) * dt * inv_ln2;
-  const double c = p.sigma * sqrt(dt) * 1.69864364966231197413;  // sqrt(2/ln 2)
+  const double c = p.sigma * sqrt(dt) * kCoefScaleD;
   Coef k;
   k.c = sgn * (float)c;
   k.d = sgn * (float)d;
@@ -98,53 +98,47 @@ __device__ __forceinline__ u32x4 draw4(uint64_t path, uint32_t call, uint32_t st
 }
 
 // Visit the Box-Muller pairs of one path in step order: f(pair, n_use) with n_use = 2 except for a
-// trailing odd step.  One "superblock" = 3 Philox calls = 12 words = 4 triples = 8 pairs = 16 steps.
-// All 12 words are drawn first (three independent multiply chains interleave on the fmaheavy pipe),
-// then consumed: measured 7% faster than call-by-call consumption (profiles/r01_variants.txt).
-struct Words12 {
-  uint32_t w[12];
-};
-
-__device__ __forceinline__ Words12 draw12(uint64_t path, uint32_t sb, uint32_t stream, uint32_t k0, uint32_t k1) {
-  const u32x4 a = draw4(path, 3 * sb, stream, k0, k1);
-  const u32x4 b = draw4(path, 3 * sb + 1, stream, k0, k1);
-  const u32x4 c = draw4(path, 3 * sb + 2, stream, k0, k1);
-  return Words12{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w}};
+// trailing odd step.  One Philox call = 4 words = 4 pairs = 8 steps (layout documented in normal.cuh).
+// UNROLL calls are drawn before any is consumed, so their multiply chains interleave on the fmaheavy
+// pipe; which UNROLL wins depends on the consumer's register appetite (profiles/r01_variants.txt).
+template <class F>
+__device__ __forceinline__ void consume_call(const u32x4& x, F&& f) {
+  f(box_muller(x.x), 2);
+  f(box_muller(x.y), 2);
+  f(box_muller(x.z), 2);
+  f(box_muller(x.w), 2);
 }
 
-template <class F>
+template <int UNROLL = 1, class F>
 __device__ __forceinline__ void for_each_pair(uint64_t path, uint32_t n_steps, uint32_t stream, uint32_t k0, uint32_t k1, F&& f) {
-  const uint32_t full = n_steps >> 4;
-  for (uint32_t sb = 0; sb < full; ++sb) {
-    const Words12 x = draw12(path, sb, stream, k0, k1);
+  const uint32_t full = n_steps >> 3;
+  uint32_t j = 0;
+  if (UNROLL > 1) {
+    for (; j + UNROLL <= full; j += UNROLL) {
+      u32x4 x[UNROLL];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      NormalPair A, B;
-      box_muller_quad(x.w[3 * t], x.w[3 * t + 1], x.w[3 * t + 2], A, B);
-      f(A, 2);
-      f(B, 2);
+      for (int u = 0; u < UNROLL; ++u) x[u] = draw4(path, j + u, stream, k0, k1);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) consume_call(x[u], f);
     }
   }
-  const int rem = (int)(n_steps & 15u);
-  if (rem) {  // 1..15 trailing steps: same word layout, only the pairs that are needed
-    const Words12 x = draw12(path, full, stream, k0, k1);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (4 * t < rem) {
-        NormalPair A, B;
-        box_muller_quad(x.w[3 * t], x.w[3 * t + 1], x.w[3 * t + 2], A, B);
-        f(A, rem - 4 * t >= 2 ? 2 : 1);
-        if (4 * t + 2 < rem) f(B, rem - 4 * t >= 4 ? 2 : 1);
-      }
-    }
+  for (; j < full; ++j) consume_call(draw4(path, j, stream, k0, k1), f);
+  const int rem = (int)(n_steps & 7u);
+  if (rem) {  // 1..7 trailing steps: same word layout, only the pairs that are needed
+    const u32x4 x = draw4(path, full, stream, k0, k1);
+    f(box_muller(x.x), rem >= 2 ? 2 : 1);
+    if (rem > 2) f(box_muller(x.y), rem >= 4 ? 2 : 1);
+    if (rem > 4) f(box_muller(x.z), rem >= 6 ? 2 : 1);
+    if (rem > 6) f(box_muller(x.w), 1);
   }
 }
 
 // ================================ European (terminal payoff) ====================================
 // W' = sum over steps of rad*cos / rad*sin (log2-radius units); everything else happens once per path.
+template <int UNROLL = 1>
 __device__ __forceinline__ float terminal_sum(uint64_t path, uint32_t n_steps, uint32_t stream, uint32_t k0, uint32_t k1) {
   float W = 0.0f;
-  for_each_pair(path, n_steps, stream, k0, k1, [&](const NormalPair& p, int n_use) {
+  for_each_pair<UNROLL>(path, n_steps, stream, k0, k1, [&](const NormalPair& p, int n_use) {
     W = fmaf(p.rad, p.cs, W);
     if (n_use > 1) W = fmaf(p.rad, p.sn, W);
   });
@@ -153,7 +147,7 @@ __device__ __forceinline__ float terminal_sum(uint64_t path, uint32_t n_steps, u
 
 // CV = true additionally accumulates sum S_T, sum S_T^2 and sum payoff*S_T per scenario (the
 // terminal-spot control variate of monte_carlo.py:154-186): 5 sums instead of 2.
-template <int NS, bool ANTI, int MINB, bool CV = false>
+template <int NS, bool ANTI, int MINB, bool CV = false, int UNROLL = 1>
 __global__ void __launch_bounds__(kBlock, MINB) european_kernel(const SimArgs a) {
   constexpr int NM = CV ? 5 : 2;
   __shared__ Coef coef[NS];
@@ -175,7 +169,7 @@ __global__ void __launch_bounds__(kBlock, MINB) european_kernel(const SimArgs a)
   for (uint32_t j = 0; j < a.paths_per_thread; ++j) {
     const uint64_t local = tile_first + (uint64_t)j * kBlock + threadIdx.x;
     if (local >= a.n_paths) break;  // paths are assigned in increasing order: nothing further for this thread
-    const float W = terminal_sum(a.path_begin + local, a.n_steps, stream, a.seed_lo, a.seed_hi);
+    const float W = terminal_sum<UNROLL>(a.path_begin + local, a.n_steps, stream, a.seed_lo, a.seed_hi);
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
       const Coef q = coef[k];
@@ -239,7 +233,7 @@ __device__ __forceinline__ float path_payoff(float l, float aux, const Coef& q, 
   return is_put ? e_ext - e_T : e_T - e_ext;
 }
 
-template <int KIND, int NS, int MINB>
+template <int KIND, int NS, int MINB, int UNROLL = 1>
 __global__ void __launch_bounds__(kBlock, MINB) pathdep_kernel(const SimArgs a) {
   __shared__ Coef coef_s[NS];
   const uint32_t opt = blockIdx.x / a.tiles;
@@ -265,8 +259,8 @@ __global__ void __launch_bounds__(kBlock, MINB) pathdep_kernel(const SimArgs a) 
     float l[NS], aux[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) l[k] = 0.0f, aux[k] = 0.0f;
-    for_each_pair(a.path_begin + local, a.n_steps, stream, a.seed_lo, a.seed_hi,
-                  [&](const NormalPair& p, int n_use) { advance_pair<KIND, NS>(p, n_use, q, l, aux); });
+    for_each_pair<UNROLL>(a.path_begin + local, a.n_steps, stream, a.seed_lo, a.seed_hi,
+                          [&](const NormalPair& p, int n_use) { advance_pair<KIND, NS>(p, n_use, q, l, aux); });
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
       const float p = path_payoff<KIND>(l[k], aux[k], q[k], a);

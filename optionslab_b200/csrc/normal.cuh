@@ -2,22 +2,29 @@
 //
 // RNG stream contract (restated in double precision in oracle/philox_oracle.c, tests only):
 //   The word stream of (seed, stream, path) is the concatenation of the Philox4x32-10 outputs for
-//   counters (path_lo, j, path_hi, stream), j = 0, 1, 2, ...   (key = seed).  Word triple t =
-//   (w[3t], w[3t+1], w[3t+2]) yields the four normals of steps 4t .. 4t+3 by two Box-Muller pairs:
-//     pair A: radius from w[3t],   angle from the LOW  16 bits of w[3t+2]  -> steps 4t   (cos), 4t+1 (sin)
-//     pair B: radius from w[3t+1], angle from the HIGH 16 bits of w[3t+2]  -> steps 4t+2 (cos), 4t+3 (sin)
-//   96 random bits per 4 normals: 3 Philox calls feed 16 path-steps.
+//   counters (path_lo, j, path_hi, stream), j = 0, 1, 2, ...   (key = seed).  Word n of the stream
+//   (n = 4j + i) is ONE Box-Muller pair and feeds steps 2n (cosine branch) and 2n+1 (sine branch):
+//   32 random bits per 2 normals, one Philox call per 8 path-steps.
 //
 // Box-Muller on the XU pipe: 4 MUFU per pair (LG2, SQRT, SIN, COS), no I2F anywhere.
-//   radius: f = float in [1,2) from the word's top 23 bits (one LEA.HI); u = 2 - f in [2^-23, 1];
-//           rad = sqrt(-log2 u).  The true radius is sqrt(-2 ln u) = kRadScale * rad with
-//           kRadScale = sqrt(2 ln 2); kernels fold kRadScale into their per-scenario diffusion
-//           coefficient instead of multiplying every draw.
-//   angle:  h = 16-bit integer; g = float 2^23 + h (bit pattern 0x4b000000 | h, exact);
-//           theta = fma(g, 2pi/65536, -(2^23 * 2pi/65536 + pi))  in [-pi, pi): one FFMA.  The grid of
-//           65536 equally spaced angles integrates every trigonometric polynomial of degree < 65536
-//           exactly, so all mixed moments of (z_cos, z_sin) up to that degree are those of the
-//           continuous angle (the float32 sin/cos resolve ~2^-22 of a turn anyway).
+//   word w = bytes [b3 b2 b1 b0] (b3 most significant).
+//   radius: f = float in [1,2) whose mantissa is the word's TOP 23 bits [b3 b2 b1>>1] (one LEA.HI);
+//           u = 2 - f in [2^-23, 1]; rad = sqrt(-log2 u).  The true radius is sqrt(-2 ln u) =
+//           sqrt(2 ln 2) * rad; kernels fold kRadScale into their per-scenario diffusion coefficient
+//           instead of multiplying every draw.  kRadScale also carries the factor 1 + 5.3e-7 that
+//           makes the second moment of the 2^23-point radius grid exactly 2 (E[-2 ln u] over
+//           u = j/2^23 is 2 * (1 - 1.0598e-6)), so E[z^2] = 1 exactly; the radius is capped at 5.65.
+//   angle:  g = float in [1,2) whose mantissa is the top 23 bits of the BYTE-REVERSED word
+//           [b0 b1 b2>>1] (one PRMT + one LEA.HI) = the angle in turns; theta = fma(g, 2pi, -3pi) in
+//           [-pi, pi).  The angle's leading 9 bits (b0 and bit 0 of b1) are bits the radius never
+//           sees, so every one of the 2^23 radius values is paired with exactly 512 equally spaced
+//           angles: every product moment E[r^a cos^b sin^c] with b + c < 512 equals that of a
+//           continuous uniform angle.  The angle's trailing bits re-use the radius' LEAST significant
+//           bits (b1>>1 moves r by < 2^-16 relative), which shifts those 512-angle combs by a
+//           quasi-independent offset: the 2^32 (u, theta) points fill the square evenly instead of
+//           stacking on 512 lines (a fixed 512-angle grid puts an atom of mass 1/256 at z = 0; taking
+//           the offset from the radius' leading bits skews z near 0 and in the tails -- both fail a
+//           Kolmogorov-Smirnov test at 1e7 draws; this layout passes at 3e7, tests/test_philox_oracle.py).
 //   z_cos = kRadScale*rad*cos(theta), z_sin = kRadScale*rad*sin(theta)
 #pragma once
 #include <cuda_runtime.h>
@@ -25,10 +32,12 @@
 
 namespace b200mc {
 
-constexpr float kRadScale = 1.17741002251547469101f;    // sqrt(2 ln 2)
-constexpr double kRadScaleD = 1.17741002251547469101;
-constexpr float kAngleStep = 9.58737992428525768573e-5f;   // 2*pi / 65536
-constexpr float kAngleBias = -807.38931197248091f;          // -(2^23 * 2*pi/65536 + pi) = -(256 + 1) * pi
+constexpr double kRadNormD = 1.000000529893528569531;    // sqrt(2 / E[-2 ln u]) on the 2^23-point grid u = j / 2^23
+constexpr double kRadScaleD = 1.177410646417426094868;   // sqrt(2 ln 2) * kRadNormD
+constexpr float kRadScale = (float)kRadScaleD;
+constexpr double kCoefScaleD = 1.698644500676289376733;  // sqrt(2 / ln 2) * kRadNormD: sigma*sqrt(dt) -> log2 units per rad
+constexpr float kTwoPi = 6.28318530717958647692f;
+constexpr float kMinusThreePi = -9.42477796076937971538f;
 
 __device__ __forceinline__ float mufu_lg2(float x) {
   float y;
@@ -56,30 +65,20 @@ __device__ __forceinline__ float mufu_cos(float x) {
   return y;
 }
 
-__device__ __forceinline__ float word_to_unit_1_2(uint32_t x) {
-  return __uint_as_float((x >> 9) | 0x3f800000u);
-}
-
-// One Box-Muller pair from a radius word and a 16-bit angle (passed already OR-ed under 0x4b000000).
-// Normals are kRadScale*rad*cs and kRadScale*rad*sn.
+// One Box-Muller pair from one 32-bit word.  Normals are kRadScale*rad*cs and kRadScale*rad*sn.
 struct NormalPair {
   float rad, cs, sn;
 };
 
-__device__ __forceinline__ NormalPair box_muller(uint32_t radius_word, uint32_t angle_bits_4b) {
+__device__ __forceinline__ NormalPair box_muller(uint32_t w) {
   NormalPair p;
-  const float u = 2.0f - word_to_unit_1_2(radius_word);
+  const float u = 2.0f - __uint_as_float((w >> 9) | 0x3f800000u);
   p.rad = mufu_sqrt(-mufu_lg2(u));
-  const float theta = fmaf(__uint_as_float(angle_bits_4b), kAngleStep, kAngleBias);
+  const float turns = __uint_as_float((__byte_perm(w, 0u, 0x0123) >> 9) | 0x3f800000u);
+  const float theta = fmaf(turns, kTwoPi, kMinusThreePi);
   p.cs = mufu_cos(theta);
   p.sn = mufu_sin(theta);
   return p;
-}
-
-// Word triple -> two pairs (four consecutive steps).
-__device__ __forceinline__ void box_muller_quad(uint32_t wa, uint32_t wb, uint32_t wc, NormalPair& A, NormalPair& B) {
-  A = box_muller(wa, (wc & 0xffffu) | 0x4b000000u);
-  B = box_muller(wb, (wc >> 16) | 0x4b000000u);
 }
 
 }  // namespace b200mc

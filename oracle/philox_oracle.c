@@ -34,34 +34,40 @@ void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-static double word_to_unit(uint32_t x) { /* float in [1,2) built from the top 23 bits */
-  uint32_t bits = (x >> 9) | 0x3f800000u;
+static double mantissa_to_1_2(uint32_t mantissa23) { /* float in [1,2) with the given 23-bit mantissa */
+  uint32_t bits = (mantissa23 & 0x007fffffu) | 0x3f800000u;
   float f;
   memcpy(&f, &bits, sizeof f);
   return (double)f;
 }
 
-/* One Box-Muller pair: radius from a full word, angle from a 16-bit integer h.
- * theta = (2^23 + h) * step + bias with the device's FP32 constants (normal.cuh kAngleStep /
- * kAngleBias), evaluated here in double: 65536 equally spaced angles covering [-pi, pi). */
-static void pair_to_normals(uint32_t radius_word, uint32_t h, double* z_cos, double* z_sin) {
-  const float step_f = 9.58737992428525768573e-5f;
-  const float bias_f = -807.38931197248091f;
-  double u = 2.0 - word_to_unit(radius_word);       /* (0, 1], grid 2^-23 */
-  double theta = (8388608.0 + (double)h) * (double)step_f + (double)bias_f;
-  double radius = sqrt(-2.0 * log(u));
+static uint32_t byte_reverse(uint32_t w) {
+  return (w >> 24) | ((w >> 8) & 0x0000ff00u) | ((w << 8) & 0x00ff0000u) | (w << 24);
+}
+
+/* One Box-Muller pair from one word (normal.cuh): radius mantissa = top 23 bits of the word, angle
+ * mantissa = top 23 bits of the byte-reversed word (angle in turns, [1,2)); theta = turns * 2pi - 3pi
+ * with the device's FP32 constants, evaluated here in double.  The radius carries the grid
+ * normalisation kRadNormD (E[z^2] = 1). */
+static void pair_to_normals(uint32_t w, double* z_cos, double* z_sin) {
+  const float two_pi_f = 6.28318530717958647692f;
+  const float minus_three_pi_f = -9.42477796076937971538f;
+  const double rad_norm = 1.000000529893528569531;
+  double u = 2.0 - mantissa_to_1_2(w >> 9);           /* (0, 1], grid 2^-23 */
+  double theta = mantissa_to_1_2(byte_reverse(w) >> 9) * (double)two_pi_f + (double)minus_three_pi_f;
+  double radius = rad_norm * sqrt(-2.0 * log(u));
   *z_cos = radius * cos(theta);
   *z_sin = radius * sin(theta);
 }
 
 /* out[(p - path_begin) * n_steps + s] = normal for step s of global path p.
  * Word stream of a path: Philox outputs of counters (path_lo, j, path_hi, stream), j = 0,1,2,...
- * Triple t = words 3t, 3t+1, 3t+2 -> steps 4t..4t+3 (see optionslab_b200/csrc/normal.cuh). */
+ * Word n = 4j + i -> steps 2n (cos) and 2n+1 (sin)  (see optionslab_b200/csrc/normal.cuh). */
 void b200mc_oracle_normals(uint64_t seed, uint32_t stream, uint64_t path_begin, uint64_t n_paths,
                            uint32_t n_steps, double* out) {
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-  uint32_t n_triples = (n_steps + 3u) / 4u;
-  uint32_t n_calls = (3u * n_triples + 3u) / 4u;
+  uint32_t n_pairs = (n_steps + 1u) / 2u;
+  uint32_t n_calls = (n_pairs + 3u) / 4u;
   uint32_t* w = (uint32_t*)malloc(sizeof(uint32_t) * 4u * (n_calls ? n_calls : 1u));
   for (uint64_t i = 0; i < n_paths; ++i) {
     uint64_t p = path_begin + i;
@@ -69,11 +75,11 @@ void b200mc_oracle_normals(uint64_t seed, uint32_t stream, uint64_t path_begin, 
       uint32_t ctr[4] = {(uint32_t)p, j, (uint32_t)(p >> 32), stream};
       philox4x32_10(ctr, key, w + 4u * j);
     }
-    for (uint32_t t = 0; t < n_triples; ++t) {
-      double z[4];
-      pair_to_normals(w[3u * t], w[3u * t + 2u] & 0xffffu, &z[0], &z[1]);
-      pair_to_normals(w[3u * t + 1u], w[3u * t + 2u] >> 16, &z[2], &z[3]);
-      for (uint32_t j = 0; j < 4u && 4u * t + j < n_steps; ++j) out[i * n_steps + 4u * t + j] = z[j];
+    for (uint32_t n = 0; n < n_pairs; ++n) {
+      double z[2];
+      pair_to_normals(w[n], &z[0], &z[1]);
+      out[i * n_steps + 2u * n] = z[0];
+      if (2u * n + 1u < n_steps) out[i * n_steps + 2u * n + 1u] = z[1];
     }
   }
   free(w);

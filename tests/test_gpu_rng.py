@@ -39,3 +39,16 @@ def test_device_normal_moments(engine):
     assert abs(z.var() - 1) < 4 * np.sqrt(2 / n)
     assert abs((z**4).mean() - 3) < 4 * np.sqrt(96 / n)
     assert np.abs(z).max() < 5.7
+
+
+def test_device_normals_ks_and_pair_independence(engine):
+    """8e6 device draws: Kolmogorov-Smirnov against the normal CDF (a fixed 512-angle grid would put an atom of
+    mass 1/256 at z = 0 and fail), and the two normals of one Box-Muller pair have uncorrelated squares."""
+    from scipy import stats
+
+    zz = engine.generate_normals(2025, 1_000_000, 8).astype(np.float64)
+    assert stats.kstest(zz.ravel(), "norm").pvalue > 1e-3
+    n = len(zz)
+    assert abs(np.corrcoef(zz[:, 0] ** 2, zz[:, 1] ** 2)[0, 1]) < 4 / np.sqrt(n)
+    assert abs(np.corrcoef(zz[:, 1], zz[:, 2])[0, 1]) < 4 / np.sqrt(n)
+    assert abs(np.corrcoef(zz[:-1, 7], zz[1:, 0])[0, 1]) < 4 / np.sqrt(n)

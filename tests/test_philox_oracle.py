@@ -67,3 +67,46 @@ def test_normal_mapping_moments():
     zz = z.reshape(-1, 8)
     assert abs(np.corrcoef(zz[:, 0], zz[:, 1])[0, 1]) < 4 / np.sqrt(len(zz))
     assert abs(np.corrcoef(zz[:-1, 0], zz[1:, 0])[0, 1]) < 4 / np.sqrt(len(zz))
+    # the two normals of one Box-Muller pair share a radius: their squares must still be uncorrelated
+    assert abs(np.corrcoef(zz[:, 0] ** 2, zz[:, 1] ** 2)[0, 1]) < 4 / np.sqrt(len(zz))
+    assert abs(np.corrcoef(zz[:, 1] ** 2, zz[:, 2] ** 2)[0, 1]) < 4 / np.sqrt(len(zz))
+
+
+def test_normal_mapping_ks_at_3e7_draws_and_symmetric_tails():
+    """The (radius, angle) bit layout matters at this sample size: a fixed 512-angle grid, or fine angle bits
+    taken from the radius' leading bits, both fail here."""
+    from scipy import stats
+    z = po.normals(2025, 4_000_000, 8).ravel()
+    assert stats.kstest(z, "norm").pvalue > 1e-3
+    expect = z.size * stats.norm.sf(4.0)
+    for tail in ((z > 4.0).sum(), (z < -4.0).sum()):
+        assert abs(tail - expect) < 5 * np.sqrt(expect)
+
+
+def test_word_to_pair_mapping_matches_the_documented_contract():
+    """normal.cuh: word n = 4j+i of a path -> steps 2n, 2n+1; radius mantissa = top 23 bits, angle mantissa =
+    top 23 bits of the byte-reversed word (turns), radius normalised so that the 2^23-point grid has E[r^2] = 2."""
+    seed, stream, path = 99, 5, 123456789012
+    z = po.normals(seed, 1, 16, stream=stream, path_begin=path)[0]
+    rad_norm = 1.000000529893528569531
+    two_pi, m3pi = float(np.float32(6.28318530717958647692)), float(np.float32(-9.42477796076937971538))
+    for j in range(2):
+        w = po.philox4x32_10([path & 0xFFFFFFFF, j, path >> 32, stream], [seed, 0])
+        for i in range(4):
+            word = int(w[i])
+            u = 2.0 - (1.0 + (word >> 9) / 2.0**23)
+            rev = int.from_bytes(word.to_bytes(4, "little"), "big")
+            turns = 1.0 + (rev >> 9) / 2.0**23
+            theta = turns * two_pi + m3pi
+            r = rad_norm * np.sqrt(-2.0 * np.log(u))
+            n = 4 * j + i
+            assert z[2 * n] == pytest.approx(r * np.cos(theta), abs=1e-14)
+            assert z[2 * n + 1] == pytest.approx(r * np.sin(theta), abs=1e-14)
+
+
+def test_radius_grid_second_moment_is_normalised():
+    """E[-2 ln u] over u = j/2^23 (j = 1..2^23) times kRadNorm^2 equals 2 (so E[z^2] = 1 on the grid)."""
+    from math import lgamma, log
+    M = 2.0**23
+    e_r2 = 2.0 * (log(M) - lgamma(M + 1.0) / M)
+    assert e_r2 * 1.000000529893528569531**2 == pytest.approx(2.0, rel=1e-9)
