@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200MC_ABI_VERSION 1
+#define B200MC_ABI_VERSION 2
 #define B200MC_MAX_SCENARIOS 16
 
 typedef struct b200mc_engine b200mc_engine_t;
@@ -138,6 +138,29 @@ int b200mc_simulate_device(b200mc_engine_t* eng, const b200mc_spec_t* spec, cons
 int b200mc_simulate_control_variate(b200mc_engine_t* eng, const b200mc_spec_t* spec, const b200mc_params_t* params_host,
                                     uint32_t n_opt, uint32_t n_scen, uint64_t seed, uint32_t stream_base,
                                     uint64_t path_begin, uint64_t n_paths, b200mc_cv_moments_t* out_host);
+
+/* ---- quasi-Monte Carlo: scrambled Sobol points generated on the device ------------------------- *
+ * Replaces simulate_gbm_qmc (src/simulation/gbm_qmc.py:14-47), the MCMethod.QMC backend of
+ * src/pricing_models/monte_carlo.py:94-97: Sobol(d = n_steps, scramble=True, seed).random(N) ->
+ * norm.ppf(clip(u, 1e-10, 1 - 1e-10)) -> terminal GBM -> payoff -> moments (no mirroring).
+ *
+ * The point set is passed as its GF(2)-linear description, in NATURAL (binary) order of the point index:
+ *     x_j(i) = shift[j] XOR (XOR over the set bits b of i) dirnums[j][b],    u_j(i) = x_j(i) * 2^-bits
+ * dirnums : [spec->n_steps][32] words (entries b >= bits must be 0), shift : [spec->n_steps].
+ *           For a Gray-code generator with direction numbers v_j[b] (scipy: Sobol._sv, Sobol._shift),
+ *           dirnums[j][b] = v_j[b] ^ v_j[b-1] reproduces its points bit for bit.
+ * points  : indices [point_begin, point_begin + n_points) of the sequence; point_begin must be a multiple
+ *           of 4096 (one CTA) — ranks take disjoint ranges of the same sequence.
+ * spec    : kind = B200MC_EUROPEAN, antithetic = 0.  All options / scenarios share the points (CRN).
+ */
+int b200mc_simulate_sobol(b200mc_engine_t* eng, const b200mc_spec_t* spec, const b200mc_params_t* params_host,
+                          uint32_t n_opt, uint32_t n_scen, const uint32_t* dirnums_host, const uint32_t* shift_host,
+                          uint32_t bits, uint64_t point_begin, uint64_t n_points, b200mc_moments_t* out_host);
+/* Inspection: out_host[(i - point_begin) * n_dims + j] = x_j(i), the integers the QMC kernel works from. */
+int b200mc_sobol_points(b200mc_engine_t* eng, const uint32_t* dirnums_host, const uint32_t* shift_host, uint32_t n_dims,
+                        uint32_t bits, uint64_t point_begin, uint64_t n_points, uint32_t* out_host);
+/* Inspection: the FP32 inverse-normal values the QMC kernel derives from the given Sobol integers. */
+int b200mc_sobol_normals(b200mc_engine_t* eng, const uint32_t* x_host, uint64_t n, uint32_t bits, float* out_host);
 
 /* ---- FP64 parity mode: price from caller-supplied normal draws ------------------------------- *
  * Z is row-major [n_paths][spec->n_steps] FP64 — exactly the array the reference draws at

@@ -17,7 +17,7 @@ from .exceptions import AccelerationError, MonteCarloError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200mc.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_SCENARIOS = 16
 
 EUROPEAN, ASIAN_ARITH, ASIAN_GEOM, BARRIER, LOOKBACK = range(5)
@@ -61,6 +61,9 @@ SIGNATURES = {
                                          C.c_uint64, C.c_uint64, _P, _P]),
     "b200mc_simulate_control_variate": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
                                                   C.c_uint64, C.c_uint64, _P]),
+    "b200mc_simulate_sobol": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_uint32, C.c_uint32, _P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P]),
+    "b200mc_sobol_points": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, _P]),
+    "b200mc_sobol_normals": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P]),
     "b200mc_payoffs_from_normals": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_int, _P, C.c_uint64, _P, _P]),
     "b200mc_payoffs_from_normals_device": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_int, _P, C.c_uint64, _P, _P, _P]),
     "b200mc_generate_normals": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, _P]),
@@ -194,6 +197,39 @@ class Engine:
                                               int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF,
                                               int(path_begin), int(n_paths), out_ptr, cuda_stream)
         self._check(rc, "b200mc_simulate_device")
+
+    # -- quasi-Monte Carlo ------------------------------------------------------------------
+    def simulate_sobol(self, spec: Spec, params: np.ndarray, dirnums: np.ndarray, shift: np.ndarray, bits: int, n_points: int,
+                       *, point_begin: int = 0) -> np.ndarray:
+        """params [n_opt, n_scen] -> MOMENTS_DTYPE [n_opt, n_scen] over Sobol points [point_begin, point_begin+n_points)."""
+        params = np.ascontiguousarray(params, dtype=PARAMS_DTYPE)
+        if params.ndim != 2:
+            raise MonteCarloError("params must have shape [n_opt, n_scen]")
+        dirnums = np.ascontiguousarray(dirnums, dtype=np.uint32)
+        shift = np.ascontiguousarray(shift, dtype=np.uint32)
+        if dirnums.shape != (spec.n_steps, 32) or shift.shape != (spec.n_steps,):
+            raise MonteCarloError("Sobol table must have shape [n_steps, 32] and shift [n_steps]")
+        out = np.empty(params.shape, dtype=MOMENTS_DTYPE)
+        rc = self._lib.b200mc_simulate_sobol(self._h, C.byref(spec), params.ctypes.data, params.shape[0], params.shape[1],
+                                             dirnums.ctypes.data, shift.ctypes.data, int(bits), int(point_begin), int(n_points),
+                                             out.ctypes.data)
+        self._check(rc, "b200mc_simulate_sobol")
+        return out
+
+    def sobol_points(self, dirnums: np.ndarray, shift: np.ndarray, bits: int, n_points: int, *, point_begin: int = 0) -> np.ndarray:
+        dirnums = np.ascontiguousarray(dirnums, dtype=np.uint32)
+        shift = np.ascontiguousarray(shift, dtype=np.uint32)
+        out = np.empty((n_points, dirnums.shape[0]), dtype=np.uint32)
+        rc = self._lib.b200mc_sobol_points(self._h, dirnums.ctypes.data, shift.ctypes.data, dirnums.shape[0], int(bits),
+                                           int(point_begin), int(n_points), out.ctypes.data)
+        self._check(rc, "b200mc_sobol_points")
+        return out
+
+    def sobol_normals(self, x: np.ndarray, bits: int) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.uint32)
+        out = np.empty(x.shape, dtype=np.float32)
+        self._check(self._lib.b200mc_sobol_normals(self._h, x.ctypes.data, x.size, int(bits), out.ctypes.data), "b200mc_sobol_normals")
+        return out
 
     # -- FP64 parity mode -------------------------------------------------------------------
     def payoffs_from_normals(self, spec: Spec, params: np.ndarray, Z: np.ndarray, *, accumulate: bool = False,

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -17,6 +18,7 @@
 #include "f64_kernels.cuh"
 #include "mc_kernels.cuh"
 #include "peaks.cuh"
+#include "sobol.cuh"
 
 using namespace b200mc;
 
@@ -111,17 +113,36 @@ uint32_t pad_scenarios(uint32_t n) {
   return p;
 }
 
-// Tile shape: enough CTAs to fill 148 SMs x 8 resident CTAs for ~4 waves when the problem allows,
-// at most kMaxPathsPerThread paths per thread, evenly spread so the last tile is not ragged-heavy.
-void plan_tiles(const b200mc_engine* e, uint32_t n_opt, uint64_t n_paths, uint32_t& tiles, uint32_t& ppt) {
-  const uint64_t want_ctas = (uint64_t)e->prop.multiProcessorCount * 8 * 4;
-  const uint64_t want_tiles = std::max<uint64_t>(1, (want_ctas + n_opt - 1) / n_opt);
-  uint64_t p = n_paths / ((uint64_t)kBlock * want_tiles);
-  p = std::min<uint64_t>(std::max<uint64_t>(p, 1), kMaxPathsPerThread);
-  const uint64_t t = (n_paths + (uint64_t)kBlock * p - 1) / ((uint64_t)kBlock * p);
-  p = (n_paths + (uint64_t)kBlock * t - 1) / ((uint64_t)kBlock * t);
-  tiles = (uint32_t)t;
-  ppt = (uint32_t)p;
+// Tile shape.  A tile = one CTA = kBlock threads x ppt paths of one option.  Large problems simply take
+// ppt = kMaxPathsPerThread (the per-CTA prologue/reduction is amortised over 32 paths per thread).  Small ones
+// (one option, 1e5..1e6 paths) trade three things: CTA overhead (favours few fat CTAs), SM load balance
+// (ceil(ctas / n_sm) CTAs on the busiest SM) and latency hiding (an SM needs ~kSaturatingCtas resident CTAs to
+// keep the XU pipe fed) plus a drain tail (the last resident CTAs of an SM finish at different times and run
+// under-occupied: ~0.3 of one full residency).  Every ppt in [1, 32] is scored and the cheapest wins; the plan depends
+// only on (n_opt, n_paths, n_steps, n_scen, SM count), so a given call is reproducible bit for bit.
+void plan_tiles(const b200mc_engine* e, uint32_t n_opt, uint64_t n_paths, uint32_t n_steps, uint32_t ns, bool path_dependent,
+                uint32_t& tiles, uint32_t& ppt) {
+  const int resident = ns <= 2 ? 6 : ns == 4 ? 3 : 2;    // CTAs per SM the register budgets below allow
+  constexpr double kSaturatingCtas = 3.0;
+  const double n_sm = (double)e->prop.multiProcessorCount;
+  // issued instructions per path: step loop (+ per-scenario state updates of the path-dependent kinds) + payoff epilogue
+  const double per_path = (11.0 + (path_dependent ? 3.5 * ns : 0.0)) * n_steps + 14.0 * ns;
+  const double per_cta = 600.0 + 40.0 * ns;              // coefficient set-up + FP64 block reduction
+  double best = 0.0;
+  uint32_t best_p = 1, best_t = 1;
+  for (uint32_t p = 1; p <= (uint32_t)kMaxPathsPerThread; ++p) {
+    const uint64_t t = (n_paths + (uint64_t)kBlock * p - 1) / ((uint64_t)kBlock * p);
+    const uint64_t p_even = (n_paths + (uint64_t)kBlock * t - 1) / ((uint64_t)kBlock * t);  // spread evenly over t tiles
+    if (p_even != p) continue;                                                               // same tiling as a smaller p
+    const double ctas = (double)t * n_opt;
+    const double per_sm = std::ceil(ctas / n_sm);
+    const double concurrency = std::min(per_sm, (double)resident);
+    const double eff = std::min(1.0, concurrency / kSaturatingCtas);
+    const double cost = (per_sm + 0.3 * resident) * ((double)p * per_path + per_cta) / eff;
+    if (best == 0.0 || cost < best * 0.999) best = cost, best_p = p, best_t = (uint32_t)t;
+  }
+  tiles = best_t;
+  ppt = best_p;
 }
 
 // __launch_bounds__ minBlocksPerSM per kernel family, picked from measurements on B200
@@ -169,7 +190,7 @@ int enqueue_simulation(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc
   if (cv && spec->kind != B200MC_EUROPEAN) return fail(e, B200MC_ERR_INVALID, "the control variate is defined for the European payoff only");
   const uint32_t ns = pad_scenarios(n_scen);
   uint32_t tiles, ppt;
-  plan_tiles(e, n_opt, n_paths, tiles, ppt);
+  plan_tiles(e, n_opt, n_paths, spec->n_steps, ns, spec->kind != B200MC_EUROPEAN, tiles, ppt);
   const uint64_t ctas = (uint64_t)tiles * n_opt;
   if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
   if (int rc = reserve(e, e->partials, ctas * (cv ? 5 : 2) * ns * sizeof(double))) return rc;
@@ -447,6 +468,137 @@ int b200mc_generate_normals(b200mc_engine_t* e, uint64_t seed, uint32_t stream, 
   CU_TRY(e, cudaGetLastError());
   e->launches += 1;
   CU_TRY(e, cudaMemcpyAsync(out_host, e->scratch_a.ptr, bytes, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+// ---- quasi-Monte Carlo (Sobol) ---------------------------------------------------------------
+static int check_sobol_table(b200mc_engine_t* e, const uint32_t* dirnums_host, const uint32_t* shift_host, uint32_t n_dims, uint32_t bits) {
+  if (!dirnums_host || !shift_host) return fail(e, B200MC_ERR_INVALID, "direction-number / shift pointer is null");
+  if (n_dims == 0) return fail(e, B200MC_ERR_INVALID, "n_dims must be >= 1");
+  if (bits < 1 || bits > 31) return fail(e, B200MC_ERR_INVALID, "bits must be in [1, 31], got %u", bits);
+  return 0;
+}
+
+// Stage [n_dims][32] direction words + [n_dims] shifts into scratch_a (pinned bounce, async on the engine stream).
+static int upload_sobol_table(b200mc_engine_t* e, const uint32_t* dirnums_host, const uint32_t* shift_host, uint32_t n_dims,
+                              const uint32_t** dir_dev, const uint32_t** shift_dev, size_t extra_pinned) {
+  const size_t dir_bytes = (size_t)n_dims * kSobolWords * sizeof(uint32_t), shift_bytes = (size_t)n_dims * sizeof(uint32_t);
+  if (int rc = reserve(e, e->scratch_a, dir_bytes + shift_bytes)) return rc;
+  if (int rc = reserve_pinned(e, dir_bytes + shift_bytes + extra_pinned)) return rc;
+  memcpy(e->pinned, dirnums_host, dir_bytes);
+  memcpy((char*)e->pinned + dir_bytes, shift_host, shift_bytes);
+  CU_TRY(e, cudaMemcpyAsync(e->scratch_a.ptr, e->pinned, dir_bytes + shift_bytes, cudaMemcpyHostToDevice, e->stream));
+  *dir_dev = (const uint32_t*)e->scratch_a.ptr;
+  *shift_dev = (const uint32_t*)((char*)e->scratch_a.ptr + dir_bytes);
+  return 0;
+}
+
+int b200mc_simulate_sobol(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_host, uint32_t n_opt,
+                          uint32_t n_scen, const uint32_t* dirnums_host, const uint32_t* shift_host, uint32_t bits,
+                          uint64_t point_begin, uint64_t n_points, b200mc_moments_t* out_host) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  if (int rc = check_spec(e, spec)) return rc;
+  if (spec->kind != B200MC_EUROPEAN || spec->antithetic)
+    return fail(e, B200MC_ERR_INVALID, "the Sobol path prices the plain European payoff (gbm_qmc.py:14-47): kind must be EUROPEAN, antithetic 0");
+  if (!params_host || !out_host) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
+  if (n_opt == 0 || n_scen == 0 || n_scen > B200MC_MAX_SCENARIOS) return fail(e, B200MC_ERR_INVALID, "bad n_opt / n_scen");
+  if (int rc = check_sobol_table(e, dirnums_host, shift_host, spec->n_steps, bits)) return rc;
+  constexpr uint64_t kTilePoints = (uint64_t)kBlock * kSobolPoints;
+  if (n_points == 0) return fail(e, B200MC_ERR_INVALID, "n_points must be >= 1");
+  if (point_begin % kTilePoints != 0)
+    return fail(e, B200MC_ERR_INVALID, "point_begin must be a multiple of %llu (one CTA of Sobol points)", (unsigned long long)kTilePoints);
+  if (point_begin + n_points > (1ull << bits))
+    return fail(e, B200MC_ERR_INVALID, "points [%llu, %llu) exceed the 2^%u points of the sequence", (unsigned long long)point_begin,
+                (unsigned long long)(point_begin + n_points), bits);
+  CU_TRY(e, cudaSetDevice(e->device));
+  const size_t n = (size_t)n_opt * n_scen;
+  const size_t in_bytes = n * sizeof(b200mc_params_t), out_bytes = n * sizeof(b200mc_moments_t);
+  const uint32_t* dir_dev;
+  const uint32_t* shift_dev;
+  if (int rc = upload_sobol_table(e, dirnums_host, shift_host, spec->n_steps, &dir_dev, &shift_dev, in_bytes + out_bytes)) return rc;
+  if (int rc = reserve(e, e->params_dev, in_bytes)) return rc;
+  if (int rc = reserve(e, e->moments_dev, out_bytes)) return rc;
+  const size_t table_bytes = (size_t)spec->n_steps * (kSobolWords + 1) * sizeof(uint32_t);
+  char* pin_in = (char*)e->pinned + table_bytes;
+  char* pin_out = pin_in + in_bytes;
+  memcpy(pin_in, params_host, in_bytes);
+  CU_TRY(e, cudaMemcpyAsync(e->params_dev.ptr, pin_in, in_bytes, cudaMemcpyHostToDevice, e->stream));
+
+  const uint32_t ns = pad_scenarios(n_scen);
+  const uint64_t tiles = (n_points + kTilePoints - 1) / kTilePoints;
+  const uint64_t ctas = tiles * n_opt;
+  if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
+  if (int rc = reserve(e, e->partials, ctas * 2 * ns * sizeof(double))) return rc;
+  SobolArgs a{};
+  a.params = (const b200mc_params_t*)e->params_dev.ptr;
+  a.partials = (double*)e->partials.ptr;
+  a.dirnums = dir_dev;
+  a.shift = shift_dev;
+  a.point_begin = point_begin;
+  a.n_points = n_points;
+  a.n_opt = n_opt, a.n_scen = n_scen, a.tiles = (uint32_t)tiles, a.n_steps = spec->n_steps, a.bits = bits;
+  a.is_put = spec->is_put;
+  const dim3 grid((unsigned)ctas);
+  const int slot = (int)(e->timed % b200mc_engine::kRing);
+  if (e->timing) CU_TRY(e, cudaEventRecord(e->ring0[slot], e->stream));
+  switch (ns) {
+    case 1: qmc_european_kernel<1><<<grid, kBlock, 0, e->stream>>>(a); break;
+    case 2: qmc_european_kernel<2><<<grid, kBlock, 0, e->stream>>>(a); break;
+    case 4: qmc_european_kernel<4><<<grid, kBlock, 0, e->stream>>>(a); break;
+    case 8: qmc_european_kernel<8><<<grid, kBlock, 0, e->stream>>>(a); break;
+    default: qmc_european_kernel<16><<<grid, kBlock, 0, e->stream>>>(a); break;
+  }
+  CU_TRY(e, cudaGetLastError());
+  if (e->timing) {
+    CU_TRY(e, cudaEventRecord(e->ring1[slot], e->stream));
+    e->timed += 1;
+  }
+  fold_kernel<<<n_opt * n_scen, 32, 0, e->stream>>>((const double*)e->partials.ptr, a.params, (b200mc_moments_t*)e->moments_dev.ptr, n_scen, ns,
+                                                   (uint32_t)tiles, (double)n_points);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 2;
+  CU_TRY(e, cudaMemcpyAsync(pin_out, e->moments_dev.ptr, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  memcpy(out_host, pin_out, out_bytes);
+  return 0;
+}
+
+int b200mc_sobol_points(b200mc_engine_t* e, const uint32_t* dirnums_host, const uint32_t* shift_host, uint32_t n_dims, uint32_t bits,
+                        uint64_t point_begin, uint64_t n_points, uint32_t* out_host) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  if (int rc = check_sobol_table(e, dirnums_host, shift_host, n_dims, bits)) return rc;
+  if (!out_host || n_points == 0 || point_begin + n_points > (1ull << bits)) return fail(e, B200MC_ERR_INVALID, "bad point range");
+  CU_TRY(e, cudaSetDevice(e->device));
+  const uint32_t* dir_dev;
+  const uint32_t* shift_dev;
+  if (int rc = upload_sobol_table(e, dirnums_host, shift_host, n_dims, &dir_dev, &shift_dev, 0)) return rc;
+  const size_t bytes = (size_t)n_points * n_dims * sizeof(uint32_t);
+  if (int rc = reserve(e, e->scratch_b, bytes)) return rc;
+  const unsigned grid = (unsigned)std::min<uint64_t>((n_points * n_dims + 255) / 256, (uint64_t)e->prop.multiProcessorCount * 32);
+  sobol_points_kernel<<<grid, 256, 0, e->stream>>>(dir_dev, shift_dev, point_begin, n_points, n_dims, (uint32_t*)e->scratch_b.ptr);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 1;
+  CU_TRY(e, cudaMemcpyAsync(out_host, e->scratch_b.ptr, bytes, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int b200mc_sobol_normals(b200mc_engine_t* e, const uint32_t* x_host, uint64_t n, uint32_t bits, float* out_host) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  if (!x_host || !out_host || n == 0 || bits < 1 || bits > 31) return fail(e, B200MC_ERR_INVALID, "bad argument");
+  CU_TRY(e, cudaSetDevice(e->device));
+  if (int rc = reserve(e, e->scratch_a, n * sizeof(uint32_t))) return rc;
+  if (int rc = reserve(e, e->scratch_b, n * sizeof(float))) return rc;
+  CU_TRY(e, cudaMemcpyAsync(e->scratch_a.ptr, x_host, n * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+  const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)e->prop.multiProcessorCount * 32);
+  sobol_normals_kernel<<<grid, 256, 0, e->stream>>>((const uint32_t*)e->scratch_a.ptr, n, bits, (float*)e->scratch_b.ptr);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 1;
+  CU_TRY(e, cudaMemcpyAsync(out_host, e->scratch_b.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
   return 0;
 }

@@ -24,8 +24,9 @@ NUMBA_AVAILABLE = False  # kept for import compatibility (monte_carlo.py:189); n
 
 
 class MCMethod(Enum):
-    """monte_carlo.py:28-34.  Accepted for signature compatibility; every value runs the CUDA engine
-    (FAST and ``num_steps == 1`` both mean one exact step, as in monte_carlo.py:86-92)."""
+    """monte_carlo.py:28-34.  NUMPY / NUMBA / FAST all run the fused Philox kernels (FAST and
+    ``num_steps == 1`` both mean one exact step, as in monte_carlo.py:86-92); QMC runs the Sobol kernel on
+    the reference's own scrambled point set (gbm_qmc.py:14-47; N samples, no mirroring)."""
 
     NUMPY = "numpy"
     NUMBA = "numba"
@@ -59,13 +60,18 @@ class MonteCarloPricer:
     def _steps(self) -> int:
         if self.method == MCMethod.FAST:
             return 1
+        if self.method == MCMethod.QMC:
+            return min(max(int(self.num_steps), 1), 21201)  # gbm_qmc.py:30
         return max(int(self.num_steps), 1)
 
     def _moments(self, scenarios: Sequence, option_type: str, seed: Optional[int]):
         actual_seed = seed if seed is not None else self.seed  # seed=0 is honoured (monte_carlo.py:84)
-        spec = _ffi.make_spec(_ffi.EUROPEAN, self._steps(), is_put=runtime.validate_option_type(option_type), antithetic=True)
+        qmc = self.method == MCMethod.QMC
+        spec = _ffi.make_spec(_ffi.EUROPEAN, self._steps(), is_put=runtime.validate_option_type(option_type), antithetic=not qmc)
         sc = np.asarray(scenarios, dtype=np.float64).reshape(-1, 6)
         params = _ffi.make_params(sc[:, 0], sc[:, 1], sc[:, 2], sc[:, 3], sc[:, 4], sc[:, 5])[None, :]
+        if qmc:  # monte_carlo.py:94-97 -> gbm_qmc.py:14-47
+            return runtime.simulate_sobol(spec, params, actual_seed, self.num_simulations)[0], sc
         return runtime.simulate(spec, params, actual_seed, self.num_simulations)[0], sc
 
     # -- reference surface --------------------------------------------------------------------

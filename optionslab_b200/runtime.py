@@ -9,7 +9,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-from . import _ffi, distributed
+from . import _ffi, distributed, sobol
 from .exceptions import MonteCarloError
 
 
@@ -41,6 +41,26 @@ def simulate(spec: _ffi.Spec, params: np.ndarray, seed: int, n_paths: int, *, st
                              control_variate=control_variate)
     else:
         local = np.zeros(np.shape(params), dtype=_ffi.CV_MOMENTS_DTYPE if control_variate else _ffi.MOMENTS_DTYPE)
+    return distributed.allreduce_moments(local, ctx)
+
+
+def simulate_sobol(spec: _ffi.Spec, params: np.ndarray, seed, n_points: int) -> np.ndarray:
+    """Moments [n_opt, n_scen] over the first ``n_points`` points of the reference's scrambled Sobol sequence
+    (gbm_qmc.py:32-33: d = n_steps, scramble=True, seed).  Ranks take 4096-aligned slices of the same sequence."""
+    if n_points < 1:
+        raise MonteCarloError("n_points must be >= 1")
+    table, shift, bits = sobol.sobol_table(spec.n_steps, seed)
+    if n_points > (1 << bits):
+        raise MonteCarloError(f"a {bits}-bit Sobol sequence has 2^{bits} points; asked for {n_points}")
+    eng = _ffi.get_engine()
+    ctx = distributed.current()
+    if ctx is None or ctx.world_size == 1:
+        return eng.simulate_sobol(spec, params, table, shift, bits, n_points)
+    begin, count = sobol.partition_points(n_points, ctx.rank, ctx.world_size)
+    if count > 0:
+        local = eng.simulate_sobol(spec, params, table, shift, bits, count, point_begin=begin)
+    else:
+        local = np.zeros(np.shape(params), dtype=_ffi.MOMENTS_DTYPE)
     return distributed.allreduce_moments(local, ctx)
 
 

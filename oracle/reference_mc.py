@@ -127,6 +127,42 @@ def european_price(S, K, T, r, sigma, option_type, q=0.0, *, num_simulations, nu
     return OracleResult(discounted_mean(pay, r, T), discounted_std_error(pay, r, T), len(pay), pay)
 
 
+def qmc_uniforms(seed, n_points: int, n_steps: int) -> np.ndarray:
+    """The reference's point set: scrambled Sobol, d = min(n_steps, 21201) (src/simulation/gbm_qmc.py:30-33)."""
+    from scipy.stats.qmc import Sobol
+
+    return Sobol(d=min(n_steps, 21201), scramble=True, seed=seed).random(n_points)
+
+
+def qmc_normals_from_uniforms(uniforms: np.ndarray) -> np.ndarray:
+    """src/simulation/gbm_qmc.py:36: ``norm.ppf(np.clip(u, 1e-10, 1 - 1e-10))``."""
+    from scipy.stats import norm
+
+    return norm.ppf(np.clip(uniforms, 1e-10, 1 - 1e-10))
+
+
+def qmc_terminal_from_normals(S, T, r, sigma, q, normals: np.ndarray) -> np.ndarray:
+    """src/simulation/gbm_qmc.py:38-47: ``ln S + drift*n + vol*sum(normals, axis=1)`` -> exp (N prices, no mirror)."""
+    effective_steps = normals.shape[1]
+    dt = T / effective_steps
+    drift = (r - q - 0.5 * sigma * sigma) * dt
+    vol = sigma * np.sqrt(dt)
+    log_S0 = np.log(S)
+    log_S_T = log_S0 + drift * effective_steps + vol * np.sum(normals, axis=1)
+    return np.exp(log_S_T)
+
+
+def european_price_qmc(S, K, T, r, sigma, option_type, q=0.0, *, num_simulations, num_steps, seed) -> OracleResult:
+    """``MonteCarloPricer(N, n, seed, method=MCMethod.QMC).price(..., return_error=True)``:
+    src/pricing_models/monte_carlo.py:94-97 -> gbm_qmc.py:14-47, then :140-150 (std error over the N samples)."""
+    if T <= 0:
+        intrinsic = max(S - K, 0) if option_type == "call" else max(K - S, 0)
+        return OracleResult(intrinsic, 0.0, 0, np.empty(0))
+    normals = qmc_normals_from_uniforms(qmc_uniforms(seed, num_simulations, num_steps))
+    pay = vanilla_payoffs(qmc_terminal_from_normals(S, T, r, sigma, q, normals), K, option_type)
+    return OracleResult(discounted_mean(pay, r, T), discounted_std_error(pay, r, T), len(pay), pay)
+
+
 def control_variate_from_terminal(terminal: np.ndarray, S, K, T, r, q, option_type: str) -> float:
     """``price_with_control_variate`` given the simulated terminals.
 

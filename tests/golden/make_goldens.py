@@ -39,10 +39,10 @@ def import_reference():
     from src.greeks.unified_greeks import ExoticAdapter, compute_greeks_unified
     from src.pricing_models.black_scholes import black_scholes
     from src.pricing_models.exotic_options import AsianOption, BarrierOption, LookbackOption
-    from src.pricing_models.monte_carlo import MonteCarloPricer
+    from src.pricing_models.monte_carlo import MCMethod, MonteCarloPricer
     from src.pricing_models.monte_carlo_unified import MonteCarloPricerUni
 
-    return dict(MonteCarloPricer=MonteCarloPricer, MonteCarloPricerUni=MonteCarloPricerUni,
+    return dict(MCMethod=MCMethod, MonteCarloPricer=MonteCarloPricer, MonteCarloPricerUni=MonteCarloPricerUni,
                 AsianOption=AsianOption, BarrierOption=BarrierOption, LookbackOption=LookbackOption,
                 compute_greeks_unified=compute_greeks_unified, ExoticAdapter=ExoticAdapter,
                 black_scholes=black_scholes)
@@ -80,6 +80,24 @@ def main():
         "100000x1_call": MCP(100000, 1, seed=42).price_with_control_variate(**P, option_type="call"),
         "20000x64_call_q": MCP(20000, 64, seed=7).price_with_control_variate(105.0, 95.0, 0.75, 0.03, 0.35, "call", q=0.02),
     }
+
+    # --- MCMethod.QMC backend (monte_carlo.py:94-97 -> gbm_qmc.py:14-47) -----------------
+    qmc = {}
+    import warnings
+    for n_sims, n_steps in [(4096, 7), (16384, 64), (65536, 252), (10000, 50)]:
+        for ot in ("call", "put"):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")  # scipy warns when N is not a power of two; the reference lets it through
+                pr = MCP(n_sims, n_steps, seed=42, method=ref["MCMethod"].QMC)
+                res = pr.price(**P, option_type=ot, return_error=True)
+                term = pr._simulate(P["S"], P["T"], P["r"], P["sigma"], 0.0)
+            pay = np.maximum(term - P["K"], 0.0) if ot == "call" else np.maximum(P["K"] - term, 0.0)
+            qmc[f"{n_sims}x{n_steps}_{ot}"] = {"price": res.price, "std_error": res.std_error, "n_paths": res.n_paths,
+                                               "payoff_head": pay[:8].tolist(), "payoff_sum": float(np.sum(pay))}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        qmc["16384x32_call_q"] = {"price": MCP(16384, 32, seed=7, method=ref["MCMethod"].QMC).price(105.0, 95.0, 0.75, 0.03, 0.35, "call", q=0.02)}
+    g["qmc"] = qmc
 
     # --- MonteCarloPricerUni NumPy backend (monte_carlo_unified.py:451-689) ---------
     uni = Uni(10000, 50, seed=42, use_numba=False, use_gpu=False)

@@ -158,3 +158,23 @@ def test_barrier_rejects_nonpositive_barrier():
     # reference tests/test_exotic_options.py:187-193
     with pytest.raises(ValueError, match="positive"):
         orc.exotic_price("barrier", **P, seed=1, n_paths=10, n_steps=2, barrier=0.0)
+
+
+@pytest.mark.parametrize("n_sims,n_steps", [(4096, 7), (16384, 64), (65536, 252), (10000, 50)])
+@pytest.mark.parametrize("ot", ["call", "put"])
+def test_qmc_backend_matches_reference(goldens, n_sims, n_steps, ot):
+    """MCMethod.QMC (monte_carlo.py:94-97 -> gbm_qmc.py:14-47): scipy's scrambled Sobol + norm.ppf."""
+    import scipy
+    import warnings
+
+    if not _same_numpy(goldens) or goldens["scipy"] != scipy.__version__:
+        pytest.skip("goldens recorded with another NumPy / SciPy build")
+    g = goldens["qmc"][f"{n_sims}x{n_steps}_{ot}"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # scipy: N not a power of two
+        res = orc.european_price_qmc(**P, option_type=ot, num_simulations=n_sims, num_steps=n_steps, seed=42)
+    assert res.price == pytest.approx(g["price"], rel=REL)
+    assert res.std_error == pytest.approx(g["std_error"], rel=1e-12)
+    assert res.n_paths == g["n_paths"] == n_sims
+    np.testing.assert_allclose(res.payoffs[:8], g["payoff_head"], rtol=REL, atol=0)
+    assert float(np.sum(res.payoffs)) == pytest.approx(g["payoff_sum"], rel=REL)

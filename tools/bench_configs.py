@@ -19,7 +19,7 @@ from oracle import reference_mc as orc  # noqa: E402  (CPU baseline / checker on
 
 P = dict(S=100.0, K=100.0, T=1.0, r=0.05, sigma=0.2)
 # per path-step (instructions, MUFU) of each kernel family, from the shipped SASS (profiles/r01_sass_*.txt)
-BUDGET = {"european": (202 / 16, 2.0), "asian": (266 / 16, 3.0), "barrier": (250 / 16, 2.0)}
+BUDGET = {"european": (88 / 8, 2.0), "asian": (116 / 8, 3.0), "barrier": (104 / 8, 2.0)}  # tools/sass_loop.py
 
 
 def timed(fn, reps=5):
