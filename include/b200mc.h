@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200MC_ABI_VERSION 2
+#define B200MC_ABI_VERSION 3
 #define B200MC_MAX_SCENARIOS 16
 
 typedef struct b200mc_engine b200mc_engine_t;
@@ -75,6 +75,26 @@ typedef struct {
 typedef struct {
   double sum_payoff, sum_payoff_sq, sum_terminal, sum_terminal_sq, sum_payoff_terminal, n;
 } b200mc_cv_moments_t;
+
+/* Heston stochastic-volatility parameters of one option (src/pricing_models/heston.py:41-58 + the
+ * arguments of price_monte_carlo, :184-195). */
+typedef struct {
+  double S, K, T, r, q;
+  double kappa, theta, sigma_v, rho, v0;
+  double reserved[2];
+} b200mc_heston_params_t;
+
+/* Jump part of a jump-diffusion (src/pricing_models/jump_diffusion.py:43-67, :274-308).
+ *   model = B200MC_JUMP_MERTON : a = mu_j, b = sigma_j           (log-normal jumps)
+ *   model = B200MC_JUMP_KOU    : a = p,    b = eta1, c = eta2    (double-exponential jumps) */
+typedef enum { B200MC_JUMP_MERTON = 0, B200MC_JUMP_KOU = 1 } b200mc_jump_model;
+typedef struct {
+  int32_t model;
+  int32_t reserved0;
+  double lambda_j;
+  double a, b, c;
+  double reserved[3];
+} b200mc_jump_params_t;
 
 typedef struct {
   int32_t device;
@@ -161,6 +181,31 @@ int b200mc_sobol_points(b200mc_engine_t* eng, const uint32_t* dirnums_host, cons
                         uint32_t bits, uint64_t point_begin, uint64_t n_points, uint32_t* out_host);
 /* Inspection: the FP32 inverse-normal values the QMC kernel derives from the given Sobol integers. */
 int b200mc_sobol_normals(b200mc_engine_t* eng, const uint32_t* x_host, uint64_t n, uint32_t bits, float* out_host);
+
+/* ---- other Euler Monte Carlo models of the reference -------------------- *
+ * Heston, full-truncation Euler: replaces HestonPricer.price_monte_carlo (src/pricing_models/heston.py:184-255).
+ * One Box-Muller pair per step (Z1 and the independent part of Z2).  params: [n_opt]; out: [n_opt].
+ * Paths / seed / stream conventions as b200mc_simulate (option i uses stream stream_base + i). */
+int b200mc_simulate_heston(b200mc_engine_t* eng, const b200mc_heston_params_t* params_host, uint32_t n_opt, int is_put,
+                           uint32_t n_steps, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
+                           b200mc_moments_t* out_host);
+/* Merton / Kou jump diffusion: replaces MertonJumpDiffusion.price_monte_carlo and KouJumpDiffusion.price_monte_carlo
+ * (src/pricing_models/jump_diffusion.py:160-225, :325-377).  The diffusion is stepped n_steps times with the
+ * compensated drift; the compound-Poisson jump sum of each path is drawn once with its exact law.
+ * params: [n_opt] (S, K, T, r, sigma, q); jumps: [n_opt]; out: [n_opt]. */
+int b200mc_simulate_jump_diffusion(b200mc_engine_t* eng, const b200mc_params_t* params_host, const b200mc_jump_params_t* jumps_host,
+                                   uint32_t n_opt, int is_put, uint32_t n_steps, uint64_t seed, uint32_t stream_base,
+                                   uint64_t path_begin, uint64_t n_paths, b200mc_moments_t* out_host);
+/* FP64 parity mode for those models.  Draws are STEP-major, the order the reference consumes its generator:
+ *   Heston : Z  [n_steps][2][n_paths]  (heston.py:228-229: Z1, then the normal mixed into Z2)
+ *   jumps  : dW [n_steps][n_paths] and J [n_steps][n_paths] = sum of the jump sizes hitting path i in step t
+ *            (jump_diffusion.py:205-216 / :352-367; J may be NULL); lambda_kappa = lambda_j * E[e^Y - 1].
+ * payoffs: per-path undiscounted payoffs [n_paths] (may be NULL); out: their moments. */
+int b200mc_heston_from_normals(b200mc_engine_t* eng, const b200mc_heston_params_t* p, int is_put, uint32_t n_steps,
+                               const double* Z_host, uint64_t n_paths, double* payoffs_host, b200mc_moments_t* out_host);
+int b200mc_jump_diffusion_from_draws(b200mc_engine_t* eng, const b200mc_params_t* p, double lambda_kappa, int is_put,
+                                     uint32_t n_steps, const double* dW_host, const double* J_host, uint64_t n_paths,
+                                     double* payoffs_host, b200mc_moments_t* out_host);
 
 /* ---- FP64 parity mode: price from caller-supplied normal draws ------------------------------- *
  * Z is row-major [n_paths][spec->n_steps] FP64 — exactly the array the reference draws at

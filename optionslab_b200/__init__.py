@@ -10,6 +10,7 @@ library or the device is missing — there is no CPU fallback.
 from .exceptions import AccelerationError, ConvergenceError, GreeksError, InputValidationError, MonteCarloError
 from .exotic_options import AsianOption, BarrierOption, LookbackOption, price_asian, price_barrier, price_lookback
 from .greeks import ExerciseStyle, ExoticAdapter, OptionType, PricerProtocol, compute_greeks_unified
+from .models import HestonPricer, KouJumpDiffusion, MertonJumpDiffusion
 from .monte_carlo import MCMethod, MCResult, MonteCarloPricer
 from .monte_carlo_unified import MonteCarloPricerUni
 
@@ -17,6 +18,7 @@ __version__ = "0.1.0"
 __all__ = [
     "MonteCarloPricer", "MCMethod", "MCResult", "MonteCarloPricerUni",
     "AsianOption", "BarrierOption", "LookbackOption", "price_asian", "price_barrier", "price_lookback",
+    "HestonPricer", "MertonJumpDiffusion", "KouJumpDiffusion",
     "PricerProtocol", "ExoticAdapter", "compute_greeks_unified", "OptionType", "ExerciseStyle",
     "MonteCarloError", "InputValidationError", "ConvergenceError", "AccelerationError", "GreeksError",
 ]

@@ -17,7 +17,7 @@ from .exceptions import AccelerationError, MonteCarloError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200mc.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_SCENARIOS = 16
 
 EUROPEAN, ASIAN_ARITH, ASIAN_GEOM, BARRIER, LOOKBACK = range(5)
@@ -47,6 +47,11 @@ MOMENTS_DTYPE = np.dtype([("sum", "f8"), ("sum_sq", "f8"), ("n", "f8")])
 CV_MOMENTS_DTYPE = np.dtype([("sum_payoff", "f8"), ("sum_payoff_sq", "f8"), ("sum_terminal", "f8"), ("sum_terminal_sq", "f8"),
                              ("sum_payoff_terminal", "f8"), ("n", "f8")])
 
+HESTON_PARAMS_DTYPE = np.dtype([(n, "f8") for n in ("S", "K", "T", "r", "q", "kappa", "theta", "sigma_v", "rho", "v0")] + [("reserved", "f8", (2,))])
+JUMP_PARAMS_DTYPE = np.dtype([("model", "i4"), ("reserved0", "i4"), ("lambda_j", "f8"), ("a", "f8"), ("b", "f8"), ("c", "f8"),
+                              ("reserved", "f8", (3,))])
+JUMP_MERTON, JUMP_KOU = 0, 1
+
 # name -> (restype, argtypes); also the list the CPU tests check the .so exports against the header.
 _P = C.c_void_p
 SIGNATURES = {
@@ -64,6 +69,11 @@ SIGNATURES = {
     "b200mc_simulate_sobol": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_uint32, C.c_uint32, _P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P]),
     "b200mc_sobol_points": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, _P]),
     "b200mc_sobol_normals": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P]),
+    "b200mc_simulate_heston": (C.c_int, [_P, _P, C.c_uint32, C.c_int, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _P]),
+    "b200mc_simulate_jump_diffusion": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_int, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64,
+                                                 C.c_uint64, _P]),
+    "b200mc_heston_from_normals": (C.c_int, [_P, _P, C.c_int, C.c_uint32, _P, C.c_uint64, _P, _P]),
+    "b200mc_jump_diffusion_from_draws": (C.c_int, [_P, _P, C.c_double, C.c_int, C.c_uint32, _P, _P, C.c_uint64, _P, _P]),
     "b200mc_payoffs_from_normals": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_int, _P, C.c_uint64, _P, _P]),
     "b200mc_payoffs_from_normals_device": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_int, _P, C.c_uint64, _P, _P, _P]),
     "b200mc_generate_normals": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, _P]),
@@ -230,6 +240,63 @@ class Engine:
         out = np.empty(x.shape, dtype=np.float32)
         self._check(self._lib.b200mc_sobol_normals(self._h, x.ctypes.data, x.size, int(bits), out.ctypes.data), "b200mc_sobol_normals")
         return out
+
+    # -- Heston / jump-diffusion models -----------------------------------------------------
+    def simulate_heston(self, params: np.ndarray, is_put: bool, n_steps: int, seed: int, n_paths: int, *, stream_base: int = 0,
+                        path_begin: int = 0) -> np.ndarray:
+        """params: HESTON_PARAMS_DTYPE [n_opt] -> MOMENTS_DTYPE [n_opt]."""
+        params = np.ascontiguousarray(params, dtype=HESTON_PARAMS_DTYPE).reshape(-1)
+        out = np.empty(params.shape, dtype=MOMENTS_DTYPE)
+        rc = self._lib.b200mc_simulate_heston(self._h, params.ctypes.data, params.size, int(bool(is_put)), int(n_steps),
+                                              int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF, int(path_begin), int(n_paths),
+                                              out.ctypes.data)
+        self._check(rc, "b200mc_simulate_heston")
+        return out
+
+    def simulate_jump_diffusion(self, params: np.ndarray, jumps: np.ndarray, is_put: bool, n_steps: int, seed: int, n_paths: int, *,
+                                stream_base: int = 0, path_begin: int = 0) -> np.ndarray:
+        """params: PARAMS_DTYPE [n_opt], jumps: JUMP_PARAMS_DTYPE [n_opt] -> MOMENTS_DTYPE [n_opt]."""
+        params = np.ascontiguousarray(params, dtype=PARAMS_DTYPE).reshape(-1)
+        jumps = np.ascontiguousarray(jumps, dtype=JUMP_PARAMS_DTYPE).reshape(-1)
+        if jumps.size != params.size:
+            raise MonteCarloError("one jump parameter set per option")
+        out = np.empty(params.shape, dtype=MOMENTS_DTYPE)
+        rc = self._lib.b200mc_simulate_jump_diffusion(self._h, params.ctypes.data, jumps.ctypes.data, params.size, int(bool(is_put)),
+                                                      int(n_steps), int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF,
+                                                      int(path_begin), int(n_paths), out.ctypes.data)
+        self._check(rc, "b200mc_simulate_jump_diffusion")
+        return out
+
+    def heston_from_normals(self, params: np.ndarray, is_put: bool, Z: np.ndarray):
+        """Z: [n_steps, 2, n_paths] FP64 (step-major, as heston.py:228-229 draws) -> (payoffs [n_paths], moments)."""
+        Z = np.ascontiguousarray(Z, dtype=np.float64)
+        if Z.ndim != 3 or Z.shape[1] != 2:
+            raise MonteCarloError("Z must have shape [n_steps, 2, n_paths]")
+        p = np.ascontiguousarray(params, dtype=HESTON_PARAMS_DTYPE).reshape(-1)
+        pay = np.empty(Z.shape[2], dtype=np.float64)
+        mom = np.empty(1, dtype=MOMENTS_DTYPE)
+        rc = self._lib.b200mc_heston_from_normals(self._h, p.ctypes.data, int(bool(is_put)), Z.shape[0], Z.ctypes.data, Z.shape[2],
+                                                  pay.ctypes.data, mom.ctypes.data)
+        self._check(rc, "b200mc_heston_from_normals")
+        return pay, mom[0]
+
+    def jump_diffusion_from_draws(self, params: np.ndarray, lambda_kappa: float, is_put: bool, dW: np.ndarray, J: Optional[np.ndarray]):
+        """dW, J: [n_steps, n_paths] FP64 (step-major) -> (payoffs [n_paths], moments)."""
+        dW = np.ascontiguousarray(dW, dtype=np.float64)
+        if dW.ndim != 2:
+            raise MonteCarloError("dW must have shape [n_steps, n_paths]")
+        if J is not None:
+            J = np.ascontiguousarray(J, dtype=np.float64)
+            if J.shape != dW.shape:
+                raise MonteCarloError("J must have the shape of dW")
+        p = np.ascontiguousarray(params, dtype=PARAMS_DTYPE).reshape(-1)
+        pay = np.empty(dW.shape[1], dtype=np.float64)
+        mom = np.empty(1, dtype=MOMENTS_DTYPE)
+        rc = self._lib.b200mc_jump_diffusion_from_draws(self._h, p.ctypes.data, float(lambda_kappa), int(bool(is_put)), dW.shape[0],
+                                                        dW.ctypes.data, J.ctypes.data if J is not None else None, dW.shape[1],
+                                                        pay.ctypes.data, mom.ctypes.data)
+        self._check(rc, "b200mc_jump_diffusion_from_draws")
+        return pay, mom[0]
 
     # -- FP64 parity mode -------------------------------------------------------------------
     def payoffs_from_normals(self, spec: Spec, params: np.ndarray, Z: np.ndarray, *, accumulate: bool = False,

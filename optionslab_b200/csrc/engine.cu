@@ -17,6 +17,7 @@
 #include "../../include/b200mc.h"
 #include "f64_kernels.cuh"
 #include "mc_kernels.cuh"
+#include "models.cuh"
 #include "peaks.cuh"
 #include "sobol.cuh"
 
@@ -470,6 +471,157 @@ int b200mc_generate_normals(b200mc_engine_t* e, uint64_t seed, uint32_t stream, 
   CU_TRY(e, cudaMemcpyAsync(out_host, e->scratch_a.ptr, bytes, cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
   return 0;
+}
+
+// ---- Heston / jump-diffusion models -----------------------------------------------------------
+}  // extern "C" (templates below)
+
+// Shared host wrapper: stage `in_bytes` of parameters (two blocks), launch, fold with the spot taken from the
+// first block at a stride, copy [n_opt] moments back.
+template <class Launch>
+static int simulate_model_host(b200mc_engine_t* e, const void* block_a, size_t bytes_a, const void* block_b, size_t bytes_b,
+                               uint32_t n_opt, uint32_t n_steps, uint32_t per_step_cost, uint64_t n_paths, size_t spot_stride_doubles,
+                               b200mc_moments_t* out_host, Launch&& launch) {
+  if (!block_a || !out_host) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
+  if (n_opt == 0 || n_paths == 0 || n_steps == 0) return fail(e, B200MC_ERR_INVALID, "n_opt, n_paths and n_steps must be >= 1");
+  CU_TRY(e, cudaSetDevice(e->device));
+  const size_t in_bytes = bytes_a + bytes_b, out_bytes = (size_t)n_opt * sizeof(b200mc_moments_t);
+  if (int rc = reserve(e, e->params_dev, in_bytes)) return rc;
+  if (int rc = reserve(e, e->moments_dev, out_bytes)) return rc;
+  if (int rc = reserve_pinned(e, in_bytes + out_bytes)) return rc;
+  char* pin_in = (char*)e->pinned;
+  char* pin_out = pin_in + in_bytes;
+  memcpy(pin_in, block_a, bytes_a);
+  if (bytes_b) memcpy(pin_in + bytes_a, block_b, bytes_b);
+  CU_TRY(e, cudaMemcpyAsync(e->params_dev.ptr, pin_in, in_bytes, cudaMemcpyHostToDevice, e->stream));
+  uint32_t tiles, ppt;
+  plan_tiles(e, n_opt, n_paths, n_steps * per_step_cost, 1, false, tiles, ppt);
+  const uint64_t ctas = (uint64_t)tiles * n_opt;
+  if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
+  if (int rc = reserve(e, e->partials, ctas * 2 * sizeof(double))) return rc;
+  const int slot = (int)(e->timed % b200mc_engine::kRing);
+  if (e->timing) CU_TRY(e, cudaEventRecord(e->ring0[slot], e->stream));
+  launch((const char*)e->params_dev.ptr, (const char*)e->params_dev.ptr + bytes_a, (double*)e->partials.ptr, tiles, ppt, dim3((unsigned)ctas));
+  CU_TRY(e, cudaGetLastError());
+  if (e->timing) {
+    CU_TRY(e, cudaEventRecord(e->ring1[slot], e->stream));
+    e->timed += 1;
+  }
+  fold_strided_kernel<<<n_opt, 32, 0, e->stream>>>((const double*)e->partials.ptr, (const double*)e->params_dev.ptr, (uint32_t)spot_stride_doubles,
+                                                    (b200mc_moments_t*)e->moments_dev.ptr, tiles, (double)n_paths);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 2;
+  CU_TRY(e, cudaMemcpyAsync(pin_out, e->moments_dev.ptr, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  memcpy(out_host, pin_out, out_bytes);
+  return 0;
+}
+
+extern "C" {
+
+int b200mc_simulate_heston(b200mc_engine_t* e, const b200mc_heston_params_t* params_host, uint32_t n_opt, int is_put, uint32_t n_steps,
+                           uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths, b200mc_moments_t* out_host) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  if (n_steps > 0x7fffffffu) return fail(e, B200MC_ERR_INVALID, "n_steps too large");
+  return simulate_model_host(e, params_host, (size_t)n_opt * sizeof(b200mc_heston_params_t), nullptr, 0, n_opt, n_steps, 2, n_paths,
+                             sizeof(b200mc_heston_params_t) / sizeof(double), out_host,
+                             [&](const char* pa, const char*, double* partials, uint32_t tiles, uint32_t ppt, dim3 grid) {
+                               HestonArgs a{};
+                               a.params = (const b200mc_heston_params_t*)pa;
+                               a.partials = partials;
+                               a.path_begin = path_begin, a.n_paths = n_paths;
+                               a.n_opt = n_opt, a.tiles = tiles, a.paths_per_thread = ppt, a.n_steps = n_steps;
+                               a.seed_lo = (uint32_t)seed, a.seed_hi = (uint32_t)(seed >> 32), a.stream_base = stream_base;
+                               a.is_put = is_put;
+                               heston_kernel<<<grid, kBlock, 0, e->stream>>>(a);
+                             });
+}
+
+int b200mc_simulate_jump_diffusion(b200mc_engine_t* e, const b200mc_params_t* params_host, const b200mc_jump_params_t* jumps_host,
+                                   uint32_t n_opt, int is_put, uint32_t n_steps, uint64_t seed, uint32_t stream_base,
+                                   uint64_t path_begin, uint64_t n_paths, b200mc_moments_t* out_host) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  if (!jumps_host) return fail(e, B200MC_ERR_INVALID, "jump parameter pointer is null");
+  for (uint32_t i = 0; i < n_opt; ++i) {
+    const b200mc_jump_params_t& j = jumps_host[i];
+    if (j.model != B200MC_JUMP_MERTON && j.model != B200MC_JUMP_KOU) return fail(e, B200MC_ERR_INVALID, "unknown jump model %d", j.model);
+    if (!(j.lambda_j >= 0.0)) return fail(e, B200MC_ERR_INVALID, "lambda_j must be non-negative");
+  }
+  return simulate_model_host(e, params_host, (size_t)n_opt * sizeof(b200mc_params_t), jumps_host, (size_t)n_opt * sizeof(b200mc_jump_params_t),
+                             n_opt, n_steps, 1, n_paths, sizeof(b200mc_params_t) / sizeof(double), out_host,
+                             [&](const char* pa, const char* pb, double* partials, uint32_t tiles, uint32_t ppt, dim3 grid) {
+                               JumpArgs a{};
+                               a.params = (const b200mc_params_t*)pa;
+                               a.jumps = (const b200mc_jump_params_t*)pb;
+                               a.partials = partials;
+                               a.path_begin = path_begin, a.n_paths = n_paths;
+                               a.n_opt = n_opt, a.tiles = tiles, a.paths_per_thread = ppt, a.n_steps = n_steps;
+                               a.seed_lo = (uint32_t)seed, a.seed_hi = (uint32_t)(seed >> 32), a.stream_base = stream_base;
+                               a.is_put = is_put;
+                               jump_kernel<<<grid, kBlock, 0, e->stream>>>(a);
+                             });
+}
+
+}  // extern "C" (template below)
+
+// FP64 parity mode of the two models: upload step-major draws, one thread per path, fixed-order fold.
+template <class Launch>
+static int model_from_draws_host(b200mc_engine_t* e, const double* draws_a, size_t count_a, const double* draws_b, size_t count_b,
+                                 uint64_t n_paths, double* payoffs_host, b200mc_moments_t* out_host, Launch&& launch) {
+  if (!draws_a || !out_host || n_paths == 0) return fail(e, B200MC_ERR_INVALID, "null pointer or zero size");
+  CU_TRY(e, cudaSetDevice(e->device));
+  const size_t bytes_a = count_a * sizeof(double), bytes_b = draws_b ? count_b * sizeof(double) : 0;
+  if (int rc = reserve(e, e->scratch_a, bytes_a + bytes_b)) return rc;
+  if (int rc = reserve(e, e->scratch_b, n_paths * sizeof(double))) return rc;
+  if (int rc = reserve(e, e->moments_dev, sizeof(b200mc_moments_t))) return rc;
+  const uint64_t ctas = (n_paths + kBlock - 1) / kBlock;
+  if (int rc = reserve(e, e->partials, ctas * 2 * sizeof(double))) return rc;
+  CU_TRY(e, cudaMemcpyAsync(e->scratch_a.ptr, draws_a, bytes_a, cudaMemcpyHostToDevice, e->stream));
+  if (bytes_b) CU_TRY(e, cudaMemcpyAsync((char*)e->scratch_a.ptr + bytes_a, draws_b, bytes_b, cudaMemcpyHostToDevice, e->stream));
+  launch((const double*)e->scratch_a.ptr, bytes_b ? (const double*)((char*)e->scratch_a.ptr + bytes_a) : nullptr,
+         payoffs_host ? (double*)e->scratch_b.ptr : nullptr, (double*)e->partials.ptr, dim3((unsigned)ctas));
+  CU_TRY(e, cudaGetLastError());
+  fold_kernel<<<1, 32, 0, e->stream>>>((const double*)e->partials.ptr, nullptr, (b200mc_moments_t*)e->moments_dev.ptr, 1, 1, (uint32_t)ctas, (double)n_paths);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 2;
+  if (payoffs_host) CU_TRY(e, cudaMemcpyAsync(payoffs_host, e->scratch_b.ptr, n_paths * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaMemcpyAsync(out_host, e->moments_dev.ptr, sizeof(b200mc_moments_t), cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+extern "C" {
+
+int b200mc_heston_from_normals(b200mc_engine_t* e, const b200mc_heston_params_t* p, int is_put, uint32_t n_steps, const double* Z_host,
+                               uint64_t n_paths, double* payoffs_host, b200mc_moments_t* out_host) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  if (!p || n_steps == 0) return fail(e, B200MC_ERR_INVALID, "null parameters or zero steps");
+  return model_from_draws_host(e, Z_host, (size_t)n_steps * 2 * n_paths, nullptr, 0, n_paths, payoffs_host, out_host,
+                               [&](const double* Z, const double*, double* pay, double* partials, dim3 grid) {
+                                 HestonF64Args a{};
+                                 a.Z = Z, a.payoffs = pay, a.partials = partials, a.n_paths = n_paths, a.n_steps = n_steps, a.is_put = is_put;
+                                 a.S = p->S, a.K = p->K, a.T = p->T, a.r = p->r, a.q = p->q;
+                                 a.kappa = p->kappa, a.theta = p->theta, a.sigma_v = p->sigma_v, a.rho = p->rho, a.v0 = p->v0;
+                                 heston_from_normals_kernel<<<grid, kBlock, 0, e->stream>>>(a);
+                               });
+}
+
+int b200mc_jump_diffusion_from_draws(b200mc_engine_t* e, const b200mc_params_t* p, double lambda_kappa, int is_put, uint32_t n_steps,
+                                     const double* dW_host, const double* J_host, uint64_t n_paths, double* payoffs_host,
+                                     b200mc_moments_t* out_host) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  if (!p || n_steps == 0) return fail(e, B200MC_ERR_INVALID, "null parameters or zero steps");
+  return model_from_draws_host(e, dW_host, (size_t)n_steps * n_paths, J_host, (size_t)n_steps * n_paths, n_paths, payoffs_host, out_host,
+                               [&](const double* dW, const double* J, double* pay, double* partials, dim3 grid) {
+                                 JumpF64Args a{};
+                                 a.dW = dW, a.J = J, a.payoffs = pay, a.partials = partials, a.n_paths = n_paths, a.n_steps = n_steps, a.is_put = is_put;
+                                 a.S = p->S, a.K = p->K, a.T = p->T, a.r = p->r, a.sigma = p->sigma, a.q = p->q, a.lambda_kappa = lambda_kappa;
+                                 jump_from_draws_kernel<<<grid, kBlock, 0, e->stream>>>(a);
+                               });
 }
 
 // ---- quasi-Monte Carlo (Sobol) ---------------------------------------------------------------

@@ -24,9 +24,25 @@ POINT_ALIGNMENT = 4096  # ranks split the sequence at multiples of one CTA of po
 MAX_DIMS = 21201        # scipy's table of direction numbers (gbm_qmc.py:30)
 
 
+_TABLE_CACHE: "dict[tuple, tuple]" = {}
+
+
 def sobol_table(n_dims: int, seed) -> Tuple[np.ndarray, np.ndarray, int]:
     """-> (dirnums [n_dims, 32] uint32 in natural order, shift [n_dims] uint32, bits) for the sampler
-    ``Sobol(d=n_dims, scramble=True, seed=seed)``."""
+    ``Sobol(d=n_dims, scramble=True, seed=seed)``.  Integer seeds are cached (the reference rebuilds the sampler on
+    every price call; a bump-and-revalue sweep asks for the same table 8-14 times)."""
+    key = (int(n_dims), int(seed)) if isinstance(seed, (int, np.integer)) else None
+    if key is not None and key in _TABLE_CACHE:
+        return _TABLE_CACHE[key]
+    out = _build_table(n_dims, seed)
+    if key is not None:
+        if len(_TABLE_CACHE) >= 8:
+            _TABLE_CACHE.pop(next(iter(_TABLE_CACHE)))
+        _TABLE_CACHE[key] = out
+    return out
+
+
+def _build_table(n_dims: int, seed) -> Tuple[np.ndarray, np.ndarray, int]:
     from scipy.stats.qmc import Sobol
 
     if not (1 <= n_dims <= MAX_DIMS):

@@ -465,3 +465,166 @@ def cpu_grid_sample(option_indices, num_simulations, num_steps, seed, option_typ
                              seed=seed + int(i))
         out[j] = res.price
     return out
+
+
+# --------------------------------------------------------------------------
+# Heston and jump-diffusion Monte Carlo
+# --------------------------------------------------------------------------
+
+
+def heston_draws(seed: Optional[int], n_paths: int, n_steps: int) -> np.ndarray:
+    """The normals ``HestonPricer.price_monte_carlo`` consumes, in its order: per step ``standard_normal(n_paths)``
+    for Z1 and again for the independent part of Z2 (src/pricing_models/heston.py:207-229, legacy global
+    generator).  One C-ordered draw of shape (n_steps, 2, n_paths) is the same stream."""
+    return np.random.RandomState(seed).standard_normal((n_steps, 2, n_paths))
+
+
+def heston_payoffs_from_normals(S, K, T, r, q, kappa, theta, sigma_v, rho, v0, Z, option_type="call") -> np.ndarray:
+    """src/pricing_models/heston.py:210-252 with the draws supplied (full-truncation Euler)."""
+    n_steps, _, n_paths = Z.shape
+    dt = T / n_steps
+    sqrt_dt = np.sqrt(dt)
+    log_S = np.full(n_paths, np.log(S))
+    v = np.full(n_paths, v0)
+    rho_sqrt = np.sqrt(1 - rho**2)
+    for t in range(n_steps):
+        Z1 = Z[t, 0]
+        Z2 = rho * Z1 + rho_sqrt * Z[t, 1]
+        v_pos = np.maximum(v, 0)
+        sqrt_v = np.sqrt(v_pos)
+        log_S += (r - q - 0.5 * v_pos) * dt + sqrt_v * sqrt_dt * Z1
+        v += kappa * (theta - v_pos) * dt + sigma_v * sqrt_v * sqrt_dt * Z2
+        v = np.maximum(v, 0)
+    return vanilla_payoffs(np.exp(log_S), K, option_type)
+
+
+def heston_price_mc(S, K, T, r, q=0.0, option_type="call", *, kappa, theta, sigma_v, rho, v0, n_paths, n_steps, seed) -> float:
+    """``HestonPricer(kappa, theta, sigma_v, rho, v0).price_monte_carlo(...)`` (heston.py:184-255)."""
+    pay = heston_payoffs_from_normals(S, K, T, r, q, kappa, theta, sigma_v, rho, v0, heston_draws(seed, n_paths, n_steps), option_type)
+    return discounted_mean(pay, r, T)
+
+
+def merton_kappa(mu_j, sigma_j) -> float:
+    """src/pricing_models/jump_diffusion.py:65-67."""
+    return float(np.exp(mu_j + 0.5 * sigma_j**2) - 1)
+
+
+def kou_kappa(p, eta1, eta2) -> float:
+    """src/pricing_models/jump_diffusion.py:302-308."""
+    return p * eta1 / (eta1 - 1) + (1 - p) * eta2 / (eta2 + 1) - 1
+
+
+def merton_draws(seed, lambda_j, mu_j, sigma_j, T, n_paths, n_steps):
+    """Replay of the generator calls of ``MertonJumpDiffusion.price_monte_carlo`` (jump_diffusion.py:203-216):
+    per step ``standard_normal(n_paths)``, ``poisson(lambda_j*dt, n_paths)``, then ``normal(mu_j, sigma_j, k)`` for each
+    path with k > 0 jumps in path order (the legacy Gaussian keeps its cached second value across calls, so one
+    draw of all the step's jump sizes is the same stream).  -> dW [n_steps, n_paths], J [n_steps, n_paths] with
+    J[t, i] = ``np.sum(jump_sizes)`` of path i at step t (0 where there is no jump)."""
+    rs = np.random.RandomState(seed)
+    dt = T / n_steps
+    dW = np.empty((n_steps, n_paths))
+    J = np.zeros((n_steps, n_paths))
+    for t in range(n_steps):
+        dW[t] = rs.standard_normal(n_paths)
+        n_jumps = rs.poisson(lambda_j * dt, n_paths)
+        hit = np.flatnonzero(n_jumps)
+        if hit.size:
+            sizes = rs.normal(mu_j, sigma_j, int(n_jumps[hit].sum()))
+            idx = 0
+            for i in hit:
+                J[t, i] = np.sum(sizes[idx:idx + n_jumps[i]])
+                idx += n_jumps[i]
+    return dW, J
+
+
+def kou_draws(seed, lambda_j, p, eta1, eta2, T, n_paths, n_steps):
+    """Replay of ``KouJumpDiffusion.price_monte_carlo`` (jump_diffusion.py:352-367) and ``simulate_jump`` (:310-323):
+    per step ``standard_normal``, ``poisson``, and when any jump occurred ``uniform(0, 1, total)``, then
+    ``exponential(1/eta1, #up)`` and ``exponential(1/eta2, #down)`` scattered by the up/down masks."""
+    rs = np.random.RandomState(seed)
+    dt = T / n_steps
+    dW = np.empty((n_steps, n_paths))
+    J = np.zeros((n_steps, n_paths))
+    for t in range(n_steps):
+        dW[t] = rs.standard_normal(n_paths)
+        n_jumps = rs.poisson(lambda_j * dt, n_paths)
+        total = int(np.sum(n_jumps))
+        if total > 0:
+            jumps = np.zeros(total)
+            u = rs.uniform(0, 1, total)
+            up = u < p
+            jumps[up] = rs.exponential(1 / eta1, int(np.sum(up)))
+            jumps[~up] = -rs.exponential(1 / eta2, int(np.sum(~up)))
+            idx = 0
+            for i in np.flatnonzero(n_jumps):
+                J[t, i] = np.sum(jumps[idx:idx + n_jumps[i]])
+                idx += n_jumps[i]
+    return dW, J
+
+
+def jump_payoffs_from_draws(S, K, T, r, sigma, q, lambda_kappa, dW, J, option_type="call") -> np.ndarray:
+    """jump_diffusion.py:197-223 / :345-375 with the draws supplied: per step ``log_S += drift + vol*dW`` and then the
+    step's jump sum on the paths it hit."""
+    n_steps, n_paths = dW.shape
+    dt = T / n_steps
+    drift = (r - q - lambda_kappa - 0.5 * sigma**2) * dt
+    vol = sigma * np.sqrt(dt)
+    log_S = np.full(n_paths, np.log(S))
+    for t in range(n_steps):
+        log_S += drift + vol * dW[t]
+        hit = J[t] != 0.0
+        log_S[hit] += J[t][hit]
+    return vanilla_payoffs(np.exp(log_S), K, option_type)
+
+
+def merton_price_mc(S, K, T, r, sigma, option_type="call", q=0.0, *, lambda_j, mu_j, sigma_j, n_paths, n_steps, seed) -> float:
+    dW, J = merton_draws(seed, lambda_j, mu_j, sigma_j, T, n_paths, n_steps)
+    pay = jump_payoffs_from_draws(S, K, T, r, sigma, q, lambda_j * merton_kappa(mu_j, sigma_j), dW, J, option_type)
+    return discounted_mean(pay, r, T)
+
+
+def kou_price_mc(S, K, T, r, sigma, option_type="call", q=0.0, *, lambda_j, p, eta1, eta2, n_paths, n_steps, seed) -> float:
+    dW, J = kou_draws(seed, lambda_j, p, eta1, eta2, T, n_paths, n_steps)
+    pay = jump_payoffs_from_draws(S, K, T, r, sigma, q, lambda_j * kou_kappa(p, eta1, eta2), dW, J, option_type)
+    return discounted_mean(pay, r, T)
+
+
+def merton_series_price(S, K, T, r, sigma, option_type="call", q=0.0, *, lambda_j, mu_j, sigma_j, n_terms=50) -> float:
+    """``MertonJumpDiffusion.price`` (jump_diffusion.py:69-132): Poisson-weighted Black-Scholes prices with
+    lambda' = lambda(1+kappa), sigma_n^2 = sigma^2 + n sigma_j^2/T, r_n = r - lambda kappa + n ln(1+kappa)/T."""
+    from math import factorial
+
+    if T <= 0:
+        return max(S - K, 0) if option_type == "call" else max(K - S, 0)
+    kappa = merton_kappa(mu_j, sigma_j)
+    lambda_prime = lambda_j * (1 + kappa)
+    price = 0.0
+    for n in range(n_terms):
+        poisson_weight = np.exp(-lambda_prime * T) * (lambda_prime * T) ** n / factorial(n)
+        sigma_n = np.sqrt(sigma**2 + n * sigma_j**2 / T)
+        r_n = r - lambda_j * kappa + n * np.log(1 + kappa) / T
+        price += poisson_weight * black_scholes(S, K, T, r_n, sigma_n, option_type, q)
+        if poisson_weight < 1e-12:
+            break
+    return float(price)
+
+
+def jump_terminal_exact_law(model, S, T, r, sigma, q, jump_params: dict, n_paths: int, seed: int) -> np.ndarray:
+    """Independent statistical cross-check (NOT the reference's algorithm): S_T of a Merton / Kou jump diffusion
+    sampled from its exact law in one step -- Gaussian diffusion over [0, T], N ~ Poisson(lambda T) jumps with the
+    model's jump-size law, compensated drift.  Same distribution as the reference's step-wise scheme."""
+    rng = np.random.default_rng(seed)
+    lam = jump_params["lambda_j"]
+    n_jumps = rng.poisson(lam * T, n_paths)
+    total = int(n_jumps.sum())
+    owner = np.repeat(np.arange(n_paths), n_jumps)
+    if model == "merton":
+        kappa = merton_kappa(jump_params["mu_j"], jump_params["sigma_j"])
+        sizes = rng.normal(jump_params["mu_j"], jump_params["sigma_j"], total)
+    else:
+        kappa = kou_kappa(jump_params["p"], jump_params["eta1"], jump_params["eta2"])
+        up = rng.uniform(0, 1, total) < jump_params["p"]
+        sizes = np.where(up, rng.exponential(1 / jump_params["eta1"], total), -rng.exponential(1 / jump_params["eta2"], total))
+    jump_sum = np.bincount(owner, weights=sizes, minlength=n_paths)
+    log_S_T = np.log(S) + (r - q - lam * kappa - 0.5 * sigma**2) * T + sigma * np.sqrt(T) * rng.standard_normal(n_paths) + jump_sum
+    return np.exp(log_S_T)

@@ -39,10 +39,12 @@ def import_reference():
     from src.greeks.unified_greeks import ExoticAdapter, compute_greeks_unified
     from src.pricing_models.black_scholes import black_scholes
     from src.pricing_models.exotic_options import AsianOption, BarrierOption, LookbackOption
+    from src.pricing_models.heston import HestonPricer
+    from src.pricing_models.jump_diffusion import KouJumpDiffusion, MertonJumpDiffusion
     from src.pricing_models.monte_carlo import MCMethod, MonteCarloPricer
     from src.pricing_models.monte_carlo_unified import MonteCarloPricerUni
 
-    return dict(MCMethod=MCMethod, MonteCarloPricer=MonteCarloPricer, MonteCarloPricerUni=MonteCarloPricerUni,
+    return dict(HestonPricer=HestonPricer, MertonJumpDiffusion=MertonJumpDiffusion, KouJumpDiffusion=KouJumpDiffusion, MCMethod=MCMethod, MonteCarloPricer=MonteCarloPricer, MonteCarloPricerUni=MonteCarloPricerUni,
                 AsianOption=AsianOption, BarrierOption=BarrierOption, LookbackOption=LookbackOption,
                 compute_greeks_unified=compute_greeks_unified, ExoticAdapter=ExoticAdapter,
                 black_scholes=black_scholes)
@@ -153,6 +155,37 @@ def main():
     out = ref["compute_greeks_unified"](ad, **P, option_type="call")
     ex["asian_adapter_greeks_20000x32"] = {k: float(v) for k, v in out.items()}
     g["exotics"] = ex
+
+    # --- Heston / Merton / Kou Monte Carlo (heston.py:184-255, jump_diffusion.py:160-225, :325-377) ------------
+    import warnings
+    md = {}
+    hp = dict(kappa=2.0, theta=0.04, sigma_v=0.3, rho=-0.7, v0=0.04)
+    hes = ref["HestonPricer"](**hp)
+    md["heston_params"] = hp
+    for n_paths, n_steps in [(20000, 50), (4097, 7), (100000, 252)]:
+        for ot in ("call", "put"):
+            md[f"heston_{ot}_{n_paths}x{n_steps}"] = float(hes.price_monte_carlo(100.0, 100.0, 1.0, 0.05, 0.01, ot, n_paths, n_steps, seed=42))
+    md["heston_analytic_call"] = float(hes.price_european(100.0, 100.0, 1.0, 0.05, 0.01, "call"))
+    md["heston_analytic_put"] = float(hes.price_european(100.0, 100.0, 1.0, 0.05, 0.01, "put"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        hes2 = ref["HestonPricer"](kappa=1.0, theta=0.09, sigma_v=0.8, rho=-0.3, v0=0.02)  # Feller violated: truncation active
+    md["heston_feller_violated_call_20000x50"] = float(hes2.price_monte_carlo(100.0, 110.0, 0.5, 0.03, 0.0, "call", 20000, 50, seed=7))
+    mp = dict(lambda_j=1.0, mu_j=-0.1, sigma_j=0.15)
+    mer = ref["MertonJumpDiffusion"](**mp)
+    md["merton_params"] = mp
+    for n_paths, n_steps in [(5000, 20), (20000, 50)]:
+        for ot in ("call", "put"):
+            md[f"merton_{ot}_{n_paths}x{n_steps}"] = float(mer.price_monte_carlo(100.0, 100.0, 1.0, 0.05, 0.2, ot, 0.01, n_paths, n_steps, seed=42))
+    md["merton_analytic_call"] = float(mer.price(100.0, 100.0, 1.0, 0.05, 0.2, "call", 0.01))
+    md["merton_analytic_put"] = float(mer.price(100.0, 100.0, 1.0, 0.05, 0.2, "put", 0.01))
+    kp = dict(lambda_j=2.0, p=0.4, eta1=10.0, eta2=5.0)
+    kou = ref["KouJumpDiffusion"](**kp)
+    md["kou_params"] = kp
+    for n_paths, n_steps in [(5000, 20), (20000, 50)]:
+        for ot in ("call", "put"):
+            md[f"kou_{ot}_{n_paths}x{n_steps}"] = float(kou.price_monte_carlo(100.0, 100.0, 1.0, 0.05, 0.2, ot, 0.01, n_paths, n_steps, seed=42))
+    g["models"] = md
 
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_goldens.json")
     with open(path, "w") as f:

@@ -178,3 +178,40 @@ def test_qmc_backend_matches_reference(goldens, n_sims, n_steps, ot):
     assert res.n_paths == g["n_paths"] == n_sims
     np.testing.assert_allclose(res.payoffs[:8], g["payoff_head"], rtol=REL, atol=0)
     assert float(np.sum(res.payoffs)) == pytest.approx(g["payoff_sum"], rel=REL)
+
+
+HES = dict(kappa=2.0, theta=0.04, sigma_v=0.3, rho=-0.7, v0=0.04)
+MER = dict(lambda_j=1.0, mu_j=-0.1, sigma_j=0.15)
+KOU = dict(lambda_j=2.0, p=0.4, eta1=10.0, eta2=5.0)
+
+
+@pytest.mark.parametrize("n_paths,n_steps", [(20000, 50), (4097, 7), (100000, 252)])
+@pytest.mark.parametrize("ot", ["call", "put"])
+def test_heston_mc_matches_reference(goldens, n_paths, n_steps, ot):
+    """HestonPricer.price_monte_carlo (heston.py:184-255), full-truncation Euler on the legacy global generator."""
+    if not _same_numpy(goldens):
+        pytest.skip("goldens recorded with another NumPy build")
+    got = orc.heston_price_mc(100.0, 100.0, 1.0, 0.05, 0.01, ot, **HES, n_paths=n_paths, n_steps=n_steps, seed=42)
+    assert got == pytest.approx(goldens["models"][f"heston_{ot}_{n_paths}x{n_steps}"], rel=REL)
+
+
+def test_heston_mc_with_truncation_active_matches_reference(goldens):
+    if not _same_numpy(goldens):
+        pytest.skip("goldens recorded with another NumPy build")
+    got = orc.heston_price_mc(100.0, 110.0, 0.5, 0.03, 0.0, "call", kappa=1.0, theta=0.09, sigma_v=0.8, rho=-0.3, v0=0.02,
+                              n_paths=20000, n_steps=50, seed=7)
+    assert got == pytest.approx(goldens["models"]["heston_feller_violated_call_20000x50"], rel=REL)
+
+
+@pytest.mark.parametrize("n_paths,n_steps", [(5000, 20), (20000, 50)])
+@pytest.mark.parametrize("ot", ["call", "put"])
+def test_jump_diffusion_mc_matches_reference(goldens, n_paths, n_steps, ot):
+    """Merton / Kou price_monte_carlo (jump_diffusion.py:160-225, :325-377): the oracle replays the reference's
+    interleaved standard_normal / poisson / jump-size draws."""
+    if not _same_numpy(goldens):
+        pytest.skip("goldens recorded with another NumPy build")
+    kw = dict(n_paths=n_paths, n_steps=n_steps, seed=42)
+    got = orc.merton_price_mc(100.0, 100.0, 1.0, 0.05, 0.2, ot, 0.01, **MER, **kw)
+    assert got == pytest.approx(goldens["models"][f"merton_{ot}_{n_paths}x{n_steps}"], rel=REL)
+    got = orc.kou_price_mc(100.0, 100.0, 1.0, 0.05, 0.2, ot, 0.01, **KOU, **kw)
+    assert got == pytest.approx(goldens["models"][f"kou_{ot}_{n_paths}x{n_steps}"], rel=REL)

@@ -19,7 +19,7 @@ from oracle import reference_mc as orc  # noqa: E402  (CPU baseline / checker on
 
 P = dict(S=100.0, K=100.0, T=1.0, r=0.05, sigma=0.2)
 # per path-step (instructions, MUFU) of each kernel family, from the shipped SASS (profiles/r01_sass_*.txt)
-BUDGET = {"european": (88 / 8, 2.0), "asian": (116 / 8, 3.0), "barrier": (104 / 8, 2.0)}  # tools/sass_loop.py
+BUDGET = {"european": (88 / 8, 2.0), "asian": (116 / 8, 3.0), "barrier": (104 / 8, 2.0), "qmc": (459 / 16, 1.0)}  # tools/sass_loop.py
 
 
 def timed(fn, reps=5):
@@ -79,6 +79,14 @@ def main():
            lambda: float(bar.price(16_000_000, 365, "up-and-out")),
            lambda: float(orc.exotic_price("barrier", **P, seed=42, n_paths=100_000, n_steps=365, barrier=120.0)), 100_000 * 365,
            note="CPU oracle at 100k paths (16M x 366 doubles = 46.8 GB per array does not fit)")
+    # QMC: scrambled Sobol, 2^20 points x 252 dimensions (MCMethod.QMC; N samples, no mirroring)
+    import warnings
+    warnings.simplefilter("ignore")  # scipy: N not a power of two (CPU sample below)
+    prq = ob.MonteCarloPricer(1 << 20, 252, seed=42, method=ob.MCMethod.QMC)
+    record("QMC European call 2^20 Sobol points x 252", "qmc", (1 << 20) * 252, (1 << 20) * 252,
+           lambda: prq.price(**P, option_type="call"),
+           lambda: orc.european_price_qmc(**P, option_type="call", num_simulations=1 << 16, num_steps=252, seed=42).price, (1 << 16) * 252,
+           note="CPU oracle (scipy Sobol + norm.ppf) at 2^16 points; api_ms includes building scipy's direction table on the host")
     # FP64 parity mode (HBM-bound by design: 8 bytes of Z per path-step, read once)
     try:
         import torch
