@@ -13,12 +13,14 @@ from .greeks import ExerciseStyle, ExoticAdapter, OptionType, PricerProtocol, co
 from .models import HestonPricer, KouJumpDiffusion, MertonJumpDiffusion
 from .monte_carlo import MCMethod, MCResult, MonteCarloPricer
 from .monte_carlo_unified import MonteCarloPricerUni
+from .validation import monte_carlo_convergence_test
 
 __version__ = "0.1.0"
 __all__ = [
     "MonteCarloPricer", "MCMethod", "MCResult", "MonteCarloPricerUni",
     "AsianOption", "BarrierOption", "LookbackOption", "price_asian", "price_barrier", "price_lookback",
     "HestonPricer", "MertonJumpDiffusion", "KouJumpDiffusion",
+    "monte_carlo_convergence_test",
     "PricerProtocol", "ExoticAdapter", "compute_greeks_unified", "OptionType", "ExerciseStyle",
     "MonteCarloError", "InputValidationError", "ConvergenceError", "AccelerationError", "GreeksError",
 ]

@@ -657,10 +657,10 @@ int b200mc_simulate_sobol(b200mc_engine_t* e, const b200mc_spec_t* spec, const b
   if (!params_host || !out_host) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
   if (n_opt == 0 || n_scen == 0 || n_scen > B200MC_MAX_SCENARIOS) return fail(e, B200MC_ERR_INVALID, "bad n_opt / n_scen");
   if (int rc = check_sobol_table(e, dirnums_host, shift_host, spec->n_steps, bits)) return rc;
-  constexpr uint64_t kTilePoints = (uint64_t)kBlock * kSobolPoints;
+  constexpr uint64_t kAlign = 1ull << kSobolAlignShift;
   if (n_points == 0) return fail(e, B200MC_ERR_INVALID, "n_points must be >= 1");
-  if (point_begin % kTilePoints != 0)
-    return fail(e, B200MC_ERR_INVALID, "point_begin must be a multiple of %llu (one CTA of Sobol points)", (unsigned long long)kTilePoints);
+  if (point_begin % kAlign != 0)
+    return fail(e, B200MC_ERR_INVALID, "point_begin must be a multiple of %llu (one full-size CTA of Sobol points)", (unsigned long long)kAlign);
   if (point_begin + n_points > (1ull << bits))
     return fail(e, B200MC_ERR_INVALID, "points [%llu, %llu) exceed the 2^%u points of the sequence", (unsigned long long)point_begin,
                 (unsigned long long)(point_begin + n_points), bits);
@@ -679,7 +679,13 @@ int b200mc_simulate_sobol(b200mc_engine_t* e, const b200mc_spec_t* spec, const b
   CU_TRY(e, cudaMemcpyAsync(e->params_dev.ptr, pin_in, in_bytes, cudaMemcpyHostToDevice, e->stream));
 
   const uint32_t ns = pad_scenarios(n_scen);
-  const uint64_t tiles = (n_points + kTilePoints - 1) / kTilePoints;
+  // points per thread 2^pb: 16 when that still gives every SM a CTA, else 4, else 1.  (At 2^20 points 256 CTAs of 16
+  // points per thread beat 1024 CTAs of 4: 0.291 vs 0.301 ms; the smaller tiles only pay when SMs would sit idle.)
+  const uint64_t want_ctas = (uint64_t)e->prop.multiProcessorCount;
+  int pb = kSobolMaxPointBits;
+  while (pb > 0 && ((n_points >> (pb + kSobolTidBits)) * n_opt) < want_ctas) pb -= 2;
+  const uint64_t tile_points = (uint64_t)kBlock << pb;
+  const uint64_t tiles = (n_points + tile_points - 1) / tile_points;
   const uint64_t ctas = tiles * n_opt;
   if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
   if (int rc = reserve(e, e->partials, ctas * 2 * ns * sizeof(double))) return rc;
@@ -695,13 +701,20 @@ int b200mc_simulate_sobol(b200mc_engine_t* e, const b200mc_spec_t* spec, const b
   const dim3 grid((unsigned)ctas);
   const int slot = (int)(e->timed % b200mc_engine::kRing);
   if (e->timing) CU_TRY(e, cudaEventRecord(e->ring0[slot], e->stream));
-  switch (ns) {
-    case 1: qmc_european_kernel<1><<<grid, kBlock, 0, e->stream>>>(a); break;
-    case 2: qmc_european_kernel<2><<<grid, kBlock, 0, e->stream>>>(a); break;
-    case 4: qmc_european_kernel<4><<<grid, kBlock, 0, e->stream>>>(a); break;
-    case 8: qmc_european_kernel<8><<<grid, kBlock, 0, e->stream>>>(a); break;
-    default: qmc_european_kernel<16><<<grid, kBlock, 0, e->stream>>>(a); break;
+#define B200MC_QMC_LAUNCH(NS_)                                                                  \
+  switch (pb) {                                                                                  \
+    case 4: qmc_european_kernel<NS_, 4><<<grid, kBlock, 0, e->stream>>>(a); break;              \
+    case 2: qmc_european_kernel<NS_, 2><<<grid, kBlock, 0, e->stream>>>(a); break;              \
+    default: qmc_european_kernel<NS_, 0><<<grid, kBlock, 0, e->stream>>>(a); break;             \
   }
+  switch (ns) {
+    case 1: B200MC_QMC_LAUNCH(1) break;
+    case 2: B200MC_QMC_LAUNCH(2) break;
+    case 4: B200MC_QMC_LAUNCH(4) break;
+    case 8: B200MC_QMC_LAUNCH(8) break;
+    default: B200MC_QMC_LAUNCH(16) break;
+  }
+#undef B200MC_QMC_LAUNCH
   CU_TRY(e, cudaGetLastError());
   if (e->timing) {
     CU_TRY(e, cudaEventRecord(e->ring1[slot], e->stream));

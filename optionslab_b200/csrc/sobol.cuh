@@ -13,7 +13,9 @@
 // shift_j (`Sobol._shift`).  The host passes c (natural order) and shift; the integers produced here are
 // bit-identical to scipy's (tests/test_gpu_qmc.py).  u = x * 2^-bits.
 //
-// Work split.  Point index bits: [0,4) the 16 points a thread owns, [4,12) threadIdx, [12,...) the CTA.
+// Work split.  Point index bits: [0,PB) the 2^PB points a thread owns, [PB,PB+8) threadIdx, above that the CTA.
+// PB = 4 (16 points per thread, 4096 per CTA) amortises the per-thread work best; point sets too small to give
+// every SM a CTA that way take PB = 2 or 0 (2^16 points: 16 CTAs at PB = 4, 256 at PB = 0).
 // Dimensions are the OUTER loop (staged through shared memory 64 at a time), the thread's 16 running
 // sums of normals live in registers:
 //   per (CTA, dim)     : the CTA-bit contribution, computed once by one thread            (xcta_s)
@@ -27,10 +29,9 @@
 
 namespace b200mc {
 
-constexpr int kSobolPoints = 16;      // points per thread
-constexpr int kSobolPointBits = 4;
-constexpr int kSobolTidBits = 8;      // kBlock == 256
-constexpr int kSobolCtaShift = kSobolPointBits + kSobolTidBits;
+constexpr int kSobolMaxPointBits = 4;  // up to 16 points per thread
+constexpr int kSobolTidBits = 8;       // kBlock == 256
+constexpr int kSobolAlignShift = kSobolMaxPointBits + kSobolTidBits;  // ranks split the sequence at multiples of 4096
 constexpr int kSobolDimChunk = 64;    // dimensions staged in shared memory at a time
 constexpr int kSobolWords = 32;       // table words per dimension (bit b of the point index -> word b)
 static_assert(kBlock == 1 << kSobolTidBits, "thread-bit split assumes 256 threads");
@@ -40,53 +41,40 @@ struct SobolArgs {
   double* partials;               // [n_opt * tiles][2 * NS]
   const uint32_t* dirnums;        // [n_steps][kSobolWords], natural (binary) order
   const uint32_t* shift;          // [n_steps]
-  uint64_t point_begin;           // multiple of kBlock * kSobolPoints
+  uint64_t point_begin;           // multiple of 1 << kSobolAlignShift
   uint64_t n_points;
   uint32_t n_opt, n_scen, tiles, n_steps, bits;
   int32_t is_put;
 };
 
-// Phi^-1 in FP32.  t = min(u, 1-u) in [1e-10, 1/2], w = -ln(4t(1-t)), |x| = 1 - 2t:
-//   Phi^-1(u) = sign(u - 1/2) * |x| * P(w),  P = sqrt(2)*erfinv(x)/x as a polynomial in (w - 2.5) for w < 5
-//   and in (sqrt(w) - 3) for w >= 5 (the form of M. Giles' single-precision erfinv; coefficients re-fitted
-//   in FP64 by tools/fit_inverse_normal.py: max abs error 2.5e-6 at |z| = 6, 6.4e-7 relative).
-__device__ __forceinline__ float inverse_normal_central(float v) {  // v = w - 2.5
-  float p = 3.958320986e-08f;
-  p = fmaf(p, v, 4.851791015e-07f);
-  p = fmaf(p, v, -4.981194608e-06f);
-  p = fmaf(p, v, -6.207880342e-06f);
-  p = fmaf(p, v, 3.091150937e-04f);
-  p = fmaf(p, v, -1.773041744e-03f);
-  p = fmaf(p, v, -5.908129905e-03f);
-  p = fmaf(p, v, 3.488026846e-01f);
-  p = fmaf(p, v, 2.123313560e+00f);
-  return p;
-}
-__device__ __forceinline__ float inverse_normal_tail(float w) {
-  const float v = mufu_sqrt(w) - 3.0f;
-  float p = -7.605044245e-06f;
-  p = fmaf(p, v, -2.237582165e-04f);
-  p = fmaf(p, v, 1.646633081e-03f);
-  p = fmaf(p, v, -4.775961266e-03f);
-  p = fmaf(p, v, 8.189511418e-03f);
-  p = fmaf(p, v, -1.092221667e-02f);
-  p = fmaf(p, v, 1.334085408e-02f);
-  p = fmaf(p, v, 1.416593595e+00f);
-  p = fmaf(p, v, 4.006434678e+00f);
-  return p;
-}
-
+// Phi^-1 in FP32, branch-free.  t = min(u, 1-u) in [1e-10, 1/2], y = sqrt(-2 ln t) in [1.1774, 6.7861]:
+//   Phi^-1(u) = sign(u - 1/2) * P((y - c)/h),  P of degree 14 fitted in FP64 against scipy's ndtri by
+//   tools/fit_inverse_normal.py (max abs error of the FP32 Horner form: 1.3e-6, at |z| = 6).  2 MUFU + 15 FFMA.
+//   A piecewise central/tail form (Giles) is more accurate in relative terms near z = 0 but its tail branch
+//   diverges in 19% of the warps: measured 25% slower (profiles/r01_variants13_inverse_normal.txt).
 // x in [0, 2^bits): the Sobol integer.  u = x * 2^-bits clipped to [1e-10, 1 - 1e-10] (gbm_qmc.py:36).
 __device__ __forceinline__ float inverse_normal_from_sobol(uint32_t x, uint32_t one, float scale) {
   const uint32_t xr = one - x;
   const bool lower = x < xr;                                  // u < 1/2
   const float t = fmaxf((float)(lower ? x : xr) * scale, 1e-10f);
-  const float v = fmaf(mufu_lg2(fmaf(-t, t, t)), -0.69314718055994530942f, -3.88629436111989061883f);  // w - 2.5, w = -ln(4t(1-t))
-  const float ax = fmaf(-2.0f, t, 1.0f);
-  float p = inverse_normal_central(v);
-  if (v >= 2.5f) p = inverse_normal_tail(v + 2.5f);           // w >= 5: 0.67% of draws
-  const float z = p * ax;
-  return lower ? -z : z;
+  const float y = mufu_sqrt(mufu_lg2(t) * -1.38629436111989061883f);  // sqrt(-2 ln t)
+  const float v = fmaf(y, 3.565869380e-01f, -1.419849035e+00f);
+  float p = -2.964769098e-03f;
+  p = fmaf(p, v, 3.917148571e-03f);
+  p = fmaf(p, v, 5.165553951e-03f);
+  p = fmaf(p, v, -5.742339453e-03f);
+  p = fmaf(p, v, -8.094970152e-03f);
+  p = fmaf(p, v, 9.645064409e-03f);
+  p = fmaf(p, v, -2.167277874e-03f);
+  p = fmaf(p, v, 5.823089048e-03f);
+  p = fmaf(p, v, -1.531743127e-02f);
+  p = fmaf(p, v, 2.503921833e-02f);
+  p = fmaf(p, v, -4.184841491e-02f);
+  p = fmaf(p, v, 7.395411314e-02f);
+  p = fmaf(p, v, -1.353623019e-01f);
+  p = fmaf(p, v, 3.068033996e+00f);
+  p = fmaf(p, v, 3.381260124e+00f);
+  return lower ? -p : p;
 }
 
 struct QmcCoef {
@@ -95,8 +83,10 @@ struct QmcCoef {
   float kappa;  // K / S
 };
 
-template <int NS>
+template <int NS, int PB>
 __global__ void __launch_bounds__(kBlock, NS <= 2 ? 4 : 2) qmc_european_kernel(const SobolArgs a) {
+  constexpr int kPoints = 1 << PB;
+  constexpr int kCtaShift = PB + kSobolTidBits;
   __shared__ __align__(16) uint32_t c_s[kSobolDimChunk][kSobolWords];
   __shared__ uint32_t xcta_s[kSobolDimChunk];
   __shared__ QmcCoef coef[NS];
@@ -114,16 +104,16 @@ __global__ void __launch_bounds__(kBlock, NS <= 2 ? 4 : 2) qmc_european_kernel(c
     coef[threadIdx.x] = q;
   }
 
-  const uint32_t cta_index = (uint32_t)(a.point_begin >> kSobolCtaShift) + tile;  // point-index bits [12, bits)
+  const uint32_t cta_index = (uint32_t)(a.point_begin >> kCtaShift) + tile;  // point-index bits [PB + 8, bits)
   uint32_t tid_mask[kSobolTidBits];
 #pragma unroll
   for (int b = 0; b < kSobolTidBits; ++b) tid_mask[b] = 0u - ((threadIdx.x >> b) & 1u);
   const uint32_t one = 1u << a.bits;
   const float scale = 1.0f / (float)one;
 
-  float W[kSobolPoints];
+  float W[kPoints];
 #pragma unroll
-  for (int k = 0; k < kSobolPoints; ++k) W[k] = 0.0f;
+  for (int k = 0; k < kPoints; ++k) W[k] = 0.0f;
 
   for (uint32_t d0 = 0; d0 < a.n_steps; d0 += kSobolDimChunk) {
     const uint32_t nd = min((uint32_t)kSobolDimChunk, a.n_steps - d0);
@@ -132,24 +122,25 @@ __global__ void __launch_bounds__(kBlock, NS <= 2 ? 4 : 2) qmc_european_kernel(c
     __syncthreads();
     if (threadIdx.x < nd) {
       uint32_t x = a.shift[d0 + threadIdx.x];
-      for (uint32_t ci = cta_index, b = kSobolCtaShift; ci != 0; ci >>= 1, ++b)
+      for (uint32_t ci = cta_index, b = kCtaShift; ci != 0; ci >>= 1, ++b)
         if (ci & 1u) x ^= c_s[threadIdx.x][b];
       xcta_s[threadIdx.x] = x;
     }
     __syncthreads();
     for (uint32_t j = 0; j < nd; ++j) {
-      const uint4 lo = *reinterpret_cast<const uint4*>(&c_s[j][0]);
-      const uint4 t0 = *reinterpret_cast<const uint4*>(&c_s[j][kSobolPointBits]);
-      const uint4 t1 = *reinterpret_cast<const uint4*>(&c_s[j][kSobolPointBits + 4]);
-      uint32_t x = xcta_s[j];
-      x ^= (t0.x & tid_mask[0]) ^ (t0.y & tid_mask[1]);
-      x ^= (t0.z & tid_mask[2]) ^ (t0.w & tid_mask[3]);
-      x ^= (t1.x & tid_mask[4]) ^ (t1.y & tid_mask[5]);
-      x ^= (t1.z & tid_mask[6]) ^ (t1.w & tid_mask[7]);
-      const uint32_t flip[kSobolPointBits] = {lo.x, lo.y, lo.z, lo.w};
+      // words [0, PB) flip the thread's own points, words [PB, PB + 8) belong to the threadIdx bits
+      uint32_t word[kSobolMaxPointBits + kSobolTidBits];
 #pragma unroll
-      for (int g = 0; g < kSobolPoints; ++g) {  // local point bits visited in Gray order: one XOR per point
-        if (g > 0) x ^= flip[(g & 1) ? 0 : (g & 2) ? 1 : (g & 4) ? 2 : 3];  // lowest set bit of g
+      for (int q = 0; q < (PB + kSobolTidBits + 3) / 4; ++q) {
+        const uint4 v4 = *reinterpret_cast<const uint4*>(&c_s[j][4 * q]);
+        word[4 * q] = v4.x, word[4 * q + 1] = v4.y, word[4 * q + 2] = v4.z, word[4 * q + 3] = v4.w;
+      }
+      uint32_t x = xcta_s[j];
+#pragma unroll
+      for (int b = 0; b < kSobolTidBits; ++b) x ^= word[PB + b] & tid_mask[b];
+#pragma unroll
+      for (int g = 0; g < kPoints; ++g) {  // local point bits visited in Gray order: one XOR per point
+        if (g > 0) x ^= word[(g & 1) ? 0 : (g & 2) ? 1 : (g & 4) ? 2 : 3];  // lowest set bit of g
         W[g ^ (g >> 1)] += inverse_normal_from_sobol(x, one, scale);
       }
     }
@@ -159,9 +150,9 @@ __global__ void __launch_bounds__(kBlock, NS <= 2 ? 4 : 2) qmc_european_kernel(c
 #pragma unroll
   for (int i = 0; i < 2 * NS; ++i) acc[i] = 0.0f;
   const bool is_put = a.is_put != 0;
-  const uint64_t first = ((uint64_t)tile * kBlock + threadIdx.x) * kSobolPoints;  // local index of this thread's point 0
+  const uint64_t first = ((uint64_t)tile * kBlock + threadIdx.x) * kPoints;  // local index of this thread's point 0
 #pragma unroll
-  for (int k = 0; k < kSobolPoints; ++k) {
+  for (int k = 0; k < kPoints; ++k) {
     if (first + k < a.n_points) {
 #pragma unroll
       for (int s = 0; s < NS; ++s) {

@@ -1,5 +1,7 @@
 #!/bin/bash
 # GPU pass: parity tests, smoke, bench, per-config numbers, ncu launch list + full captures.
+# ncu reports are summarised ON the box (tools/ncu_summary.py) and only the European one travels back:
+# gpurun refuses to copy more than 64 MiB of gpurun_out/.
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
@@ -11,9 +13,14 @@ python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r01.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
 echo "ncu list exit $?"
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:european_kernel -s 3 -c 1 -o gpurun_out/prof_european_r01 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:european_kernel -s 3 -c 1 -f -o gpurun_out/prof_european_r01 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $?"
+python tools/ncu_summary.py gpurun_out/prof_european_r01.ncu-rep > gpurun_out/ncu_european_summary.txt 2>&1
 python tools/bench_configs.py > gpurun_out/plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:pathdep_kernel -c 12 -o gpurun_out/prof_pathdep_r01 python tools/bench_configs.py > gpurun_out/ncu_full2.log 2>&1
+ncu --set full --clock-control none -k regex:pathdep_kernel -c 6 -f -o /tmp/prof_pathdep_r01 python tools/bench_configs.py > gpurun_out/ncu_full2.log 2>&1
 echo "ncu pathdep exit $?"
-ls -la gpurun_out
+python tools/ncu_summary.py /tmp/prof_pathdep_r01.ncu-rep > gpurun_out/ncu_pathdep_summary.txt 2>&1
+ncu --set full --clock-control none -k "regex:qmc_european_kernel|heston_kernel|jump_kernel" -c 9 -f -o /tmp/prof_models_r01 python tools/bench_configs.py > gpurun_out/ncu_full3.log 2>&1
+echo "ncu models exit $?"
+python tools/ncu_summary.py /tmp/prof_models_r01.ncu-rep > gpurun_out/ncu_models_summary.txt 2>&1
+ls -la gpurun_out; du -sh gpurun_out

@@ -123,3 +123,19 @@ def test_engine_error_paths(engine):
         engine.simulate(_ffi.make_spec(_ffi.EUROPEAN, 4), np.zeros((1, 17), dtype=_ffi.PARAMS_DTYPE), 1, 10)
     info = engine.info()
     assert info["cc_major"] >= 10 and info["sm_count"] > 0
+
+
+def test_monte_carlo_convergence_test_with_fresh_seeds():
+    """src/pricing_models/validation.py:202-239 driven by the GPU pricer: the spread of repeated estimates shrinks
+    like 1/sqrt(N) (each trial uses a fresh seed, as a seed=None reference pricer would)."""
+    import optionslab_b200 as ob
+
+    def price(n_sims):
+        return ob.MonteCarloPricer(n_sims, 16).price(100.0, 100.0, 1.0, 0.05, 0.2, "call")
+
+    out = ob.monte_carlo_convergence_test(price, n_trials=12, base_sims=20000)
+    assert out["converging"]
+    assert list(out["results"]) == [20000, 40000, 80000, 200000]
+    assert out["stds"][-1] < out["stds"][0]
+    assert 0.3 < out["stds"][-1] / out["expected_rate"][-1] < 3.0
+    assert all(abs(v["mean"] - 10.4506) < 0.15 for v in out["results"].values())

@@ -19,7 +19,8 @@ from oracle import reference_mc as orc  # noqa: E402  (CPU baseline / checker on
 
 P = dict(S=100.0, K=100.0, T=1.0, r=0.05, sigma=0.2)
 # per path-step (instructions, MUFU) of each kernel family, from the shipped SASS (profiles/r01_sass_*.txt)
-BUDGET = {"european": (88 / 8, 2.0), "asian": (116 / 8, 3.0), "barrier": (104 / 8, 2.0), "qmc": (459 / 16, 1.0)}  # tools/sass_loop.py
+BUDGET = {"european": (88 / 8, 2.0), "asian": (116 / 8, 3.0), "barrier": (104 / 8, 2.0), "qmc": (461 / 16, 2.0),
+          "heston": (34.0, 5.0), "jump": (88 / 8, 2.0)}  # tools/sass_loop.py (Heston: one Box-Muller pair + sqrt(v) per step)
 
 
 def timed(fn, reps=5):
@@ -87,6 +88,18 @@ def main():
            lambda: prq.price(**P, option_type="call"),
            lambda: orc.european_price_qmc(**P, option_type="call", num_simulations=1 << 16, num_steps=252, seed=42).price, (1 << 16) * 252,
            note="CPU oracle (scipy Sobol + norm.ppf) at 2^16 points; api_ms includes building scipy's direction table on the host")
+    # Heston full-truncation Euler and Merton jump diffusion, 4M paths x 252 steps
+    hes = ob.HestonPricer(kappa=2.0, theta=0.04, sigma_v=0.3, rho=-0.7, v0=0.04)
+    record("Heston European call 4M x 252", "heston", 4_000_000 * 252, 4_000_000 * 252,
+           lambda: hes.price_monte_carlo(100.0, 100.0, 1.0, 0.05, 0.01, "call", 4_000_000, 252, seed=42),
+           lambda: orc.heston_price_mc(100.0, 100.0, 1.0, 0.05, 0.01, "call", kappa=2.0, theta=0.04, sigma_v=0.3, rho=-0.7, v0=0.04,
+                                       n_paths=100_000, n_steps=252, seed=42), 100_000 * 252, note="CPU oracle at 100k paths")
+    mer = ob.MertonJumpDiffusion(lambda_j=1.0, mu_j=-0.1, sigma_j=0.15)
+    record("Merton jump-diffusion call 4M x 252", "jump", 4_000_000 * 252, 4_000_000 * 252,
+           lambda: mer.price_monte_carlo(100.0, 100.0, 1.0, 0.05, 0.2, "call", 0.01, 4_000_000, 252, seed=42),
+           lambda: orc.merton_price_mc(100.0, 100.0, 1.0, 0.05, 0.2, "call", 0.01, lambda_j=1.0, mu_j=-0.1, sigma_j=0.15,
+                                       n_paths=20_000, n_steps=252, seed=42), 20_000 * 252,
+           note="CPU oracle at 20k paths (vectorised replay of the reference's draws; the reference itself loops over paths in Python)")
     # FP64 parity mode (HBM-bound by design: 8 bytes of Z per path-step, read once)
     try:
         import torch
