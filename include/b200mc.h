@@ -43,6 +43,10 @@ typedef enum {
   B200MC_LOOKBACK = 4     /* running max / min, t=0..n;  exotic_options.py:382-399 */
 } b200mc_kind;
 
+/* ASIAN_ARITH: always evaluate S_t = S_0 * 2^(l_t) with MUFU.EX2 instead of the multiplicative
+ * small-move update the kernel picks per option when |log2 increment| <= 0.25 (mc_kernels.cuh). */
+#define B200MC_FLAG_EXACT_EX2 1u
+
 typedef struct {
   int32_t kind;           /* b200mc_kind */
   int32_t is_put;         /* 0 call, 1 put */
@@ -52,7 +56,7 @@ typedef struct {
   int32_t barrier_in;     /* BARRIER: 0 = knock-out, 1 = knock-in */
   int32_t lookback_fixed; /* LOOKBACK: 0 = floating strike, 1 = fixed strike */
   uint32_t n_steps;       /* time steps per path (>= 1) */
-  uint32_t reserved;
+  uint32_t flags;         /* B200MC_FLAG_* (0 = defaults) */
 } b200mc_spec_t;
 
 /* One (option, scenario) parameter set, FP64.  Scenarios of an option share its normal draws

@@ -21,12 +21,13 @@ ABI_VERSION = 3
 MAX_SCENARIOS = 16
 
 EUROPEAN, ASIAN_ARITH, ASIAN_GEOM, BARRIER, LOOKBACK = range(5)
+FLAG_EXACT_EX2 = 1
 
 
 class Spec(C.Structure):
     _fields_ = [("kind", C.c_int32), ("is_put", C.c_int32), ("antithetic", C.c_int32),
                 ("barrier_down", C.c_int32), ("barrier_in", C.c_int32), ("lookback_fixed", C.c_int32),
-                ("n_steps", C.c_uint32), ("reserved", C.c_uint32)]
+                ("n_steps", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class Info(C.Structure):
@@ -113,9 +114,9 @@ def load_library():
 
 
 def make_spec(kind: int, n_steps: int, *, is_put=False, antithetic=False, barrier_down=False, barrier_in=False,
-              lookback_fixed=False) -> Spec:
+              lookback_fixed=False, exact_ex2=False) -> Spec:
     return Spec(int(kind), int(bool(is_put)), int(bool(antithetic)), int(bool(barrier_down)), int(bool(barrier_in)),
-                int(bool(lookback_fixed)), int(n_steps), 0)
+                int(bool(lookback_fixed)), int(n_steps), FLAG_EXACT_EX2 if exact_ex2 else 0)
 
 
 def make_params(S, K, T, r, sigma, q=0.0, barrier=0.0) -> np.ndarray:

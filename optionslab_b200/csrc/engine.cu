@@ -206,12 +206,12 @@ int enqueue_simulation(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc
   a.tiles = tiles;
   a.paths_per_thread = ppt;
   a.n_steps = spec->n_steps;
-  a.seed_lo = (uint32_t)seed;
-  a.seed_hi = (uint32_t)(seed >> 32);
+  a.rk = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32));
   a.stream_base = stream_base;
   a.is_put = spec->is_put;
   a.barrier_in = spec->barrier_in;
   a.lookback_fixed = spec->lookback_fixed;
+  a.force_mufu_ex2 = (spec->flags & B200MC_FLAG_EXACT_EX2) ? 1 : 0;
   // which extremum the path-dependent kernels track (they follow sgn * log2(S_t/S_0) and keep its max)
   a.sgn_negative = 0;
   if (spec->kind == B200MC_BARRIER) a.sgn_negative = spec->barrier_down ? 1 : 0;
@@ -464,7 +464,7 @@ int b200mc_generate_normals(b200mc_engine_t* e, uint64_t seed, uint32_t stream, 
   const size_t bytes = (size_t)n_paths * n_steps * sizeof(float);
   if (int rc = reserve(e, e->scratch_a, bytes)) return rc;
   const unsigned grid = (unsigned)std::min<uint64_t>((n_paths + 255) / 256, (uint64_t)e->prop.multiProcessorCount * 32);
-  normals_kernel<<<grid, 256, 0, e->stream>>>((uint32_t)seed, (uint32_t)(seed >> 32), stream, path_begin, n_paths, n_steps,
+  normals_kernel<<<grid, 256, 0, e->stream>>>(philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32)), stream, path_begin, n_paths, n_steps,
                                               (float*)e->scratch_a.ptr);
   CU_TRY(e, cudaGetLastError());
   e->launches += 1;
@@ -532,7 +532,7 @@ int b200mc_simulate_heston(b200mc_engine_t* e, const b200mc_heston_params_t* par
                                a.partials = partials;
                                a.path_begin = path_begin, a.n_paths = n_paths;
                                a.n_opt = n_opt, a.tiles = tiles, a.paths_per_thread = ppt, a.n_steps = n_steps;
-                               a.seed_lo = (uint32_t)seed, a.seed_hi = (uint32_t)(seed >> 32), a.stream_base = stream_base;
+                               a.rk = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32)), a.stream_base = stream_base;
                                a.is_put = is_put;
                                heston_kernel<<<grid, kBlock, 0, e->stream>>>(a);
                              });
@@ -558,7 +558,7 @@ int b200mc_simulate_jump_diffusion(b200mc_engine_t* e, const b200mc_params_t* pa
                                a.partials = partials;
                                a.path_begin = path_begin, a.n_paths = n_paths;
                                a.n_opt = n_opt, a.tiles = tiles, a.paths_per_thread = ppt, a.n_steps = n_steps;
-                               a.seed_lo = (uint32_t)seed, a.seed_hi = (uint32_t)(seed >> 32), a.stream_base = stream_base;
+                               a.rk = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32)), a.stream_base = stream_base;
                                a.is_put = is_put;
                                jump_kernel<<<grid, kBlock, 0, e->stream>>>(a);
                              });
@@ -859,7 +859,7 @@ int b200mc_measure_peaks(b200mc_engine_t* e, b200mc_peaks_t* out) {
   out->issue_per_s = threads * it * 4.0 * (probe::kChains / 2) * 3.0 / (ms * 1e-3);
   if (int rc = timed([&] { probe::philox_only<<<grid, block, 0, s>>>(it, 42u, 0u, (uint32_t*)buf); })) return rc;
   out->philox_per_s = threads * it / (ms * 1e-3);
-  if (int rc = timed([&] { probe::normals_only<<<grid, block, 0, s>>>(it, 42u, 0u, (float*)buf, (long long*)e->scratch_b.ptr); })) return rc;
+  if (int rc = timed([&] { probe::normals_only<<<grid, block, 0, s>>>(it, philox_expand_key(42u, 0u), (float*)buf, (long long*)e->scratch_b.ptr); })) return rc;
   out->normals_per_s = threads * (double)(it * 8) / (ms * 1e-3);
   std::vector<long long> clk((size_t)grid * 2);
   CU_TRY(e, cudaMemcpy(clk.data(), e->scratch_b.ptr, clk.size() * sizeof(long long), cudaMemcpyDeviceToHost));

@@ -33,9 +33,10 @@ struct SimArgs {
   uint32_t tiles;                 // tiles per option
   uint32_t paths_per_thread;
   uint32_t n_steps;
-  uint32_t seed_lo, seed_hi;
+  PhiloxKeys rk;                  // expanded from the 64-bit seed on the host
   uint32_t stream_base;
   int32_t is_put, barrier_in, lookback_fixed, sgn_negative;
+  int32_t force_mufu_ex2;         // arithmetic Asian: always take the MUFU.EX2 form (tests / A-B timing)
 };
 
 // Per-scenario FP32 coefficients, computed in FP64 once per CTA (the reference's constants:
@@ -93,8 +94,8 @@ __device__ __forceinline__ void block_reduce_store(const float (&v)[NV], double*
 // The fast-varying word (call index) sits in c1, which round 1 only XORs: with path/stream/seed
 // loop-invariant the compiler hoists both round-1 multiplies and one round-2 multiply out of the
 // step loop (16 IMAD.WIDE + 18 LOP3 per call instead of 20 + 20).
-__device__ __forceinline__ u32x4 draw4(uint64_t path, uint32_t call, uint32_t stream, uint32_t k0, uint32_t k1) {
-  return philox4x32<10>((uint32_t)path, call, (uint32_t)(path >> 32), stream, k0, k1);
+__device__ __forceinline__ u32x4 draw4(uint64_t path, uint32_t call, uint32_t stream, const PhiloxKeys& rk) {
+  return philox4x32_10((uint32_t)path, call, (uint32_t)(path >> 32), stream, rk);
 }
 
 // Visit the Box-Muller pairs of one path in step order: f(pair, n_use) with n_use = 2 except for a
@@ -110,22 +111,22 @@ __device__ __forceinline__ void consume_call(const u32x4& x, F&& f) {
 }
 
 template <int UNROLL = 1, class F>
-__device__ __forceinline__ void for_each_pair(uint64_t path, uint32_t n_steps, uint32_t stream, uint32_t k0, uint32_t k1, F&& f) {
+__device__ __forceinline__ void for_each_pair(uint64_t path, uint32_t n_steps, uint32_t stream, const PhiloxKeys& rk, F&& f) {
   const uint32_t full = n_steps >> 3;
   uint32_t j = 0;
   if (UNROLL > 1) {
     for (; j + UNROLL <= full; j += UNROLL) {
       u32x4 x[UNROLL];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) x[u] = draw4(path, j + u, stream, k0, k1);
+      for (int u = 0; u < UNROLL; ++u) x[u] = draw4(path, j + u, stream, rk);
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) consume_call(x[u], f);
     }
   }
-  for (; j < full; ++j) consume_call(draw4(path, j, stream, k0, k1), f);
+  for (; j < full; ++j) consume_call(draw4(path, j, stream, rk), f);
   const int rem = (int)(n_steps & 7u);
   if (rem) {  // 1..7 trailing steps: same word layout, only the pairs that are needed
-    const u32x4 x = draw4(path, full, stream, k0, k1);
+    const u32x4 x = draw4(path, full, stream, rk);
     f(box_muller(x.x), rem >= 2 ? 2 : 1);
     if (rem > 2) f(box_muller(x.y), rem >= 4 ? 2 : 1);
     if (rem > 4) f(box_muller(x.z), rem >= 6 ? 2 : 1);
@@ -136,9 +137,9 @@ __device__ __forceinline__ void for_each_pair(uint64_t path, uint32_t n_steps, u
 // ================================ European (terminal payoff) ====================================
 // W' = sum over steps of rad*cos / rad*sin (log2-radius units); everything else happens once per path.
 template <int UNROLL = 1>
-__device__ __forceinline__ float terminal_sum(uint64_t path, uint32_t n_steps, uint32_t stream, uint32_t k0, uint32_t k1) {
+__device__ __forceinline__ float terminal_sum(uint64_t path, uint32_t n_steps, uint32_t stream, const PhiloxKeys& rk) {
   float W = 0.0f;
-  for_each_pair<UNROLL>(path, n_steps, stream, k0, k1, [&](const NormalPair& p, int n_use) {
+  for_each_pair<UNROLL>(path, n_steps, stream, rk, [&](const NormalPair& p, int n_use) {
     W = fmaf(p.rad, p.cs, W);
     if (n_use > 1) W = fmaf(p.rad, p.sn, W);
   });
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(kBlock, MINB) european_kernel(const SimArgs a)
   for (uint32_t j = 0; j < a.paths_per_thread; ++j) {
     const uint64_t local = tile_first + (uint64_t)j * kBlock + threadIdx.x;
     if (local >= a.n_paths) break;  // paths are assigned in increasing order: nothing further for this thread
-    const float W = terminal_sum<UNROLL>(a.path_begin + local, a.n_steps, stream, a.seed_lo, a.seed_hi);
+    const float W = terminal_sum<UNROLL>(a.path_begin + local, a.n_steps, stream, a.rk);
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
       const Coef q = coef[k];
@@ -215,6 +216,39 @@ __device__ __forceinline__ void advance_pair(const NormalPair& p, int n_use, con
   }
 }
 
+// ---- arithmetic Asian, small per-step moves: multiplicative update without MUFU.EX2 -------------------
+// The arithmetic average needs S_t itself every step, i.e. a third MUFU per path-step on a kernel the XU pipe
+// already bounds.  When every possible log2-increment x = d + c*rad*cos of an option is small
+// (|d| + |c|*kRadMax <= kSmallMove; daily steps up to sigma ~ 0.48) the kernel tracks s_t = S_t/S_0 directly:
+//   s_t = s_{t-1} + s_{t-1} * (2^x - 1),   2^x - 1 = x*ln2 * (1 + x*ln2/2 * (1 + ...)) to degree 5 on the FMA pipe.
+// Truncation: (ln2 x)^6/720 <= 3.8e-8 relative at the bound (a 5.65-sigma draw), ~1e-14 for a typical draw;
+// rounding is half an ulp of s per step, the same order as the additive form's 3e-8 on l_t.
+// The choice is made per CTA (= per option, over all its scenarios) from the coefficients alone.
+constexpr float kRadMax = 4.79583152331271954f;  // sqrt(23): u >= 2^-23 (normal.cuh)
+constexpr float kSmallMove = 0.25f;
+
+__device__ __forceinline__ float exp2m1_small(float x) {
+  float t = fmaf(x, 1.3333558146e-3f, 9.6181291076e-3f);  // ln2^5/120, ln2^4/24
+  t = fmaf(x, t, 5.5504108665e-2f);                       // ln2^3/6
+  t = fmaf(x, t, 2.4022650696e-1f);                       // ln2^2/2
+  t = fmaf(x, t, 6.9314718056e-1f);                       // ln2
+  return x * t;
+}
+
+template <int NS>
+__device__ __forceinline__ void advance_pair_small(const NormalPair& p, int n_use, const Coef (&q)[NS], float (&s)[NS], float (&aux)[NS]) {
+#pragma unroll
+  for (int k = 0; k < NS; ++k) {
+    const float rc = p.rad * q[k].c;
+    s[k] = fmaf(s[k], exp2m1_small(fmaf(rc, p.cs, q[k].d)), s[k]);
+    aux[k] += s[k];
+    if (n_use > 1) {
+      s[k] = fmaf(s[k], exp2m1_small(fmaf(rc, p.sn, q[k].d)), s[k]);
+      aux[k] += s[k];
+    }
+  }
+}
+
 template <int KIND>
 __device__ __forceinline__ float path_payoff(float l, float aux, const Coef& q, const SimArgs& a) {
   const bool is_put = a.is_put != 0;
@@ -231,6 +265,29 @@ __device__ __forceinline__ float path_payoff(float l, float aux, const Coef& q, 
   const float e_ext = mufu_ex2(sgn * aux);
   if (a.lookback_fixed) return vanilla(e_ext, q.kappa, is_put);
   return is_put ? e_ext - e_T : e_T - e_ext;
+}
+
+// One CTA's share of one option: paths_per_thread paths per thread, payoffs accumulated in FP32 per thread.
+// SMALL selects the multiplicative arithmetic-Asian update (state = S_t/S_0 instead of log2 of it).
+template <int KIND, int NS, bool SMALL, int UNROLL>
+__device__ __forceinline__ void simulate_tile(const SimArgs& a, const Coef (&q)[NS], uint32_t stream, uint64_t tile_first, float (&acc)[2 * NS]) {
+  for (uint32_t j = 0; j < a.paths_per_thread; ++j) {
+    const uint64_t local = tile_first + (uint64_t)j * kBlock + threadIdx.x;
+    if (local >= a.n_paths) break;
+    float l[NS], aux[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) l[k] = SMALL ? 1.0f : 0.0f, aux[k] = 0.0f;
+    for_each_pair<UNROLL>(a.path_begin + local, a.n_steps, stream, a.rk, [&](const NormalPair& p, int n_use) {
+      if (SMALL) advance_pair_small<NS>(p, n_use, q, l, aux);
+      else advance_pair<KIND, NS>(p, n_use, q, l, aux);
+    });
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      const float p = path_payoff<KIND>(l[k], aux[k], q[k], a);
+      acc[2 * k] += p;
+      acc[2 * k + 1] = fmaf(p, p, acc[2 * k + 1]);
+    }
+  }
 }
 
 template <int KIND, int NS, int MINB, int UNROLL = 1>
@@ -253,21 +310,13 @@ __global__ void __launch_bounds__(kBlock, MINB) pathdep_kernel(const SimArgs a) 
 
   const uint32_t stream = a.stream_base + opt;
   const uint64_t tile_first = (uint64_t)tile * (uint64_t)(kBlock * a.paths_per_thread);
-  for (uint32_t j = 0; j < a.paths_per_thread; ++j) {
-    const uint64_t local = tile_first + (uint64_t)j * kBlock + threadIdx.x;
-    if (local >= a.n_paths) break;
-    float l[NS], aux[NS];
+  bool small = KIND == B200MC_ASIAN_ARITH && !a.force_mufu_ex2;
+  if (KIND == B200MC_ASIAN_ARITH) {
 #pragma unroll
-    for (int k = 0; k < NS; ++k) l[k] = 0.0f, aux[k] = 0.0f;
-    for_each_pair<UNROLL>(a.path_begin + local, a.n_steps, stream, a.seed_lo, a.seed_hi,
-                          [&](const NormalPair& p, int n_use) { advance_pair<KIND, NS>(p, n_use, q, l, aux); });
-#pragma unroll
-    for (int k = 0; k < NS; ++k) {
-      const float p = path_payoff<KIND>(l[k], aux[k], q[k], a);
-      acc[2 * k] += p;
-      acc[2 * k + 1] = fmaf(p, p, acc[2 * k + 1]);
-    }
+    for (int k = 0; k < NS; ++k) small = small && (fabsf(q[k].d) + fabsf(q[k].c) * kRadMax <= kSmallMove);  // NaN -> false
   }
+  if (small) simulate_tile<B200MC_ASIAN_ARITH, NS, true, UNROLL>(a, q, stream, tile_first, acc);  // CTA-uniform branch
+  else simulate_tile<KIND, NS, false, UNROLL>(a, q, stream, tile_first, acc);
   block_reduce_store<2 * NS>(acc, a.partials + (size_t)blockIdx.x * (2 * NS));
 }
 
@@ -326,12 +375,12 @@ __global__ void __launch_bounds__(32) fold_cv_kernel(const double* __restrict__ 
 }
 
 // ================================ stream inspection kernels ====================================
-__global__ void normals_kernel(uint32_t k0, uint32_t k1, uint32_t stream, uint64_t path_begin, uint64_t n_paths,
+__global__ void normals_kernel(const PhiloxKeys rk, uint32_t stream, uint64_t path_begin, uint64_t n_paths,
                                uint32_t n_steps, float* __restrict__ out) {
   for (uint64_t local = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; local < n_paths; local += (uint64_t)gridDim.x * blockDim.x) {
     float* row = out + local * n_steps;
     uint32_t s = 0;
-    for_each_pair(path_begin + local, n_steps, stream, k0, k1, [&](const NormalPair& p, int n_use) {
+    for_each_pair(path_begin + local, n_steps, stream, rk, [&](const NormalPair& p, int n_use) {
       row[s++] = kRadScale * p.rad * p.cs;
       if (n_use > 1) row[s++] = kRadScale * p.rad * p.sn;
     });

@@ -23,7 +23,8 @@ struct HestonArgs {
   double* partials;                      // [n_opt * tiles][2]
   uint64_t path_begin, n_paths;
   uint32_t n_opt, tiles, paths_per_thread, n_steps;
-  uint32_t seed_lo, seed_hi, stream_base;
+  PhiloxKeys rk;
+  uint32_t stream_base;
   int32_t is_put;
 };
 
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(kBlock, 4) heston_kernel(const HestonArgs a) {
     if (local >= a.n_paths) break;
     float l = 0.0f, v = c.v0;
     // n_steps pairs = 2*n_steps draws of the path's stream
-    for_each_pair(a.path_begin + local, 2u * a.n_steps, stream, a.seed_lo, a.seed_hi, [&](const NormalPair& p, int) {
+    for_each_pair(a.path_begin + local, 2u * a.n_steps, stream, a.rk, [&](const NormalPair& p, int) {
       const float g = (p.rad * c.a) * mufu_sqrt(v);                  // sqrt(v) * sqrt(dt) * |draw|, log2 units
       l = fmaf(g, p.cs, fmaf(-c.half, v, l + c.mu));                 // heston.py:236
       const float w = fmaf(c.rho, p.cs, c.rho_bar * p.sn);           // heston.py:229 (direction of Z2)
@@ -120,7 +121,8 @@ struct JumpArgs {
   double* partials;
   uint64_t path_begin, n_paths;
   uint32_t n_opt, tiles, paths_per_thread, n_steps;
-  uint32_t seed_lo, seed_hi, stream_base;
+  PhiloxKeys rk;
+  uint32_t stream_base;
   int32_t is_put;
 };
 
@@ -178,10 +180,10 @@ __global__ void __launch_bounds__(kBlock, 4) jump_kernel(const JumpArgs a) {
     const uint64_t local = tile_first + (uint64_t)j * kBlock + threadIdx.x;
     if (local >= a.n_paths) break;
     const uint64_t path = a.path_begin + local;
-    const float W = terminal_sum(path, a.n_steps, stream, a.seed_lo, a.seed_hi);
+    const float W = terminal_sum(path, a.n_steps, stream, a.rk);
     float l = fmaf(c.c, W, c.a);
     // --- compound Poisson part: one call for (count uniform, Merton normal) -------------------------------------
-    const u32x4 x = draw4(path, kJumpCallBase, stream, a.seed_lo, a.seed_hi);
+    const u32x4 x = draw4(path, kJumpCallBase, stream, a.rk);
     const double u = ((double)x.x + 0.5) * 2.3283064365386963e-10;  // (0, 1), 32 bits
     uint32_t n_jumps = 0;
     if (u > c.p0) {  // CDF inversion of Poisson(lam_T); not taken by exp(-lam_T) of the paths
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(kBlock, 4) jump_kernel(const JumpArgs a) {
       } else {
         float jump_log2 = 0.0f;
         for (uint32_t k = 0; k < n_jumps; k += 2) {  // two jumps per Philox call: (direction, magnitude) x 2
-          const u32x4 y = draw4(path, kJumpCallBase + 1u + (k >> 1), stream, a.seed_lo, a.seed_hi);
+          const u32x4 y = draw4(path, kJumpCallBase + 1u + (k >> 1), stream, a.rk);
           const float m0 = -mufu_lg2(uniform_open_closed(y.y));  // Exp(1) / ln2
           jump_log2 += (uniform_open_closed(y.x) <= c.j1) ? m0 * c.j2 : -m0 * c.j3;
           if (k + 1 < n_jumps) {

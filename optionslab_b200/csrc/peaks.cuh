@@ -152,13 +152,13 @@ __device__ __forceinline__ unsigned long long global_ns() {
 
 // clocks[2*cta] = SM cycles, clocks[2*cta+1] = nanoseconds spent by that CTA: their ratio is the SM
 // clock actually sustained under this (integer + XU) load.
-__global__ void normals_only(uint32_t iters, uint32_t k0, uint32_t k1, float* out, long long* clocks) {
+__global__ void normals_only(uint32_t iters, const PhiloxKeys rk, float* out, long long* clocks) {
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long n0 = global_ns();
   const long long t0 = clock64();
   // iters Philox calls -> iters * 8 normals, through the production word layout (mc_kernels.cuh)
   float W = 0.f;
-  for_each_pair((uint64_t)gid, iters * 8, 7u, k0, k1, [&](const NormalPair& p, int n_use) {
+  for_each_pair((uint64_t)gid, iters * 8, 7u, rk, [&](const NormalPair& p, int n_use) {
     W = fmaf(p.rad, p.cs, W);
     if (n_use > 1) W = fmaf(p.rad, p.sn, W);
   });

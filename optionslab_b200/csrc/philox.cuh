@@ -51,4 +51,36 @@ B200MC_HD u32x4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
   return u32x4{c0, c1, c2, c3};
 }
 
+// The ten round keys, expanded once.  Kernels take them as launch parameters (constant bank operands of the
+// round XORs) so that no kernel spends loop instructions or registers re-deriving the Weyl sequence.
+struct PhiloxKeys {
+  uint32_t k[20];  // k[2r], k[2r+1] = key words of round r
+};
+
+B200MC_HD PhiloxKeys philox_expand_key(uint32_t k0, uint32_t k1) {
+  PhiloxKeys rk;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    rk.k[2 * r] = k0 + (uint32_t)r * kPhiloxW0;
+    rk.k[2 * r + 1] = k1 + (uint32_t)r * kPhiloxW1;
+  }
+  return rk;
+}
+
+B200MC_HD u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& rk) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, lo0, hi1, lo1;
+    mulhilo(kPhiloxM0, c0, hi0, lo0);
+    mulhilo(kPhiloxM1, c2, hi1, lo1);
+    const uint32_t n0 = hi1 ^ c1 ^ rk.k[2 * r];
+    const uint32_t n2 = hi0 ^ c3 ^ rk.k[2 * r + 1];
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+  }
+  return u32x4{c0, c1, c2, c3};
+}
+
 }  // namespace b200mc

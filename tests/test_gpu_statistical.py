@@ -208,3 +208,82 @@ def test_ragged_and_tiny_sizes(engine):
             pay = orc.vanilla_payoffs(orc.gbm_terminal_from_normals(P["S"], P["T"], P["r"], P["sigma"], 0.0, Z), P["K"], "call")
             assert m["n"] == 2 * n_paths
             assert m["sum"] == pytest.approx(pay.sum(), rel=3e-4, abs=1e-3)
+
+
+# ---------------- arithmetic Asian: multiplicative small-move update vs the MUFU.EX2 form --------
+
+def test_asian_small_move_update_agrees_with_exact_ex2_form_and_fp64_oracle(engine):
+    """mc_kernels.cuh picks, per option, s_t = s_{t-1} + s_{t-1}*(2^x - 1) with a degree-5 polynomial when every
+    possible per-step log2 move is <= 0.25; B200MC_FLAG_EXACT_EX2 forces l_t += x, S_t = 2^l_t.  Same draws:
+    the two agree to FP32 rounding, and both sit within 2e-4 of the FP64 oracle evaluation of the stream."""
+    n, n_steps, seed = 50_000, 252, 17
+    Z = po.normals(seed, n, n_steps)
+    for sigma in (0.2, 0.45):  # 0.45: a 5.65-sigma daily draw moves log2 S by 0.23 (just inside the bound)
+        p = dict(P, sigma=sigma)
+        paths = orc.exotic_paths_from_normals(p["S"], p["T"], p["r"], sigma, 0.0, Z)
+        for ot in ("call", "put"):
+            want = orc.asian_payoffs(paths, p["K"], "arithmetic", ot)
+            fast = engine.simulate(_ffi.make_spec(_ffi.ASIAN_ARITH, n_steps, is_put=ot == "put"), _ffi.make_params(**p).reshape(1, 1), seed, n)[0, 0]
+            exact = engine.simulate(_ffi.make_spec(_ffi.ASIAN_ARITH, n_steps, is_put=ot == "put", exact_ex2=True),
+                                    _ffi.make_params(**p).reshape(1, 1), seed, n)[0, 0]
+            assert fast["sum"] == pytest.approx(exact["sum"], rel=2e-5)
+            assert fast["sum_sq"] == pytest.approx(exact["sum_sq"], rel=4e-5)
+            assert fast["sum"] == pytest.approx(want.sum(), rel=2e-4)
+            assert exact["sum"] == pytest.approx(want.sum(), rel=2e-4)
+
+
+def test_asian_large_moves_take_the_ex2_form_bit_for_bit(engine):
+    """Above the bound (here sigma = 1.5 on 12 monthly steps) the kernel must not use the polynomial:
+    default and EXACT_EX2 launches are the same code path, hence identical bits; a launch whose scenarios
+    straddle the bound takes the EX2 form for all of them."""
+    n, n_steps, seed = 30_000, 12, 4
+    big = dict(P, sigma=1.5)
+    a = engine.simulate(_ffi.make_spec(_ffi.ASIAN_ARITH, n_steps), _ffi.make_params(**big).reshape(1, 1), seed, n)[0, 0]
+    b = engine.simulate(_ffi.make_spec(_ffi.ASIAN_ARITH, n_steps, exact_ex2=True), _ffi.make_params(**big).reshape(1, 1), seed, n)[0, 0]
+    assert a["sum"] == b["sum"] and a["sum_sq"] == b["sum_sq"]
+    Z = po.normals(seed, n, n_steps)
+    want = orc.asian_payoffs(orc.exotic_paths_from_normals(big["S"], big["T"], big["r"], big["sigma"], 0.0, Z), big["K"], "arithmetic", "call")
+    assert a["sum"] == pytest.approx(want.sum(), rel=2e-4)
+    # scenarios straddling the bound: sigma = 0.2 (small moves) next to sigma = 1.5 in one launch
+    both = _ffi.make_params([P["S"]] * 2, P["K"], P["T"], P["r"], [0.2, 1.5]).reshape(1, 2)
+    m = engine.simulate(_ffi.make_spec(_ffi.ASIAN_ARITH, n_steps), both, seed, n)[0]
+    solo = engine.simulate(_ffi.make_spec(_ffi.ASIAN_ARITH, n_steps, exact_ex2=True), _ffi.make_params(**P).reshape(1, 1), seed, n)[0, 0]
+    assert m[0]["sum"] == solo["sum"] and m[1]["sum"] == a["sum"]
+
+
+def test_asian_fused_scenarios_equal_separate_repricings_bitwise():
+    opt = ob.AsianOption(**P, seed=11)
+    sc = [(100.0, 100.0, 1.0, 0.05, 0.2, 0.0), (101.0, 100.0, 1.0, 0.05, 0.2, 0.0), (100.0, 100.0, 1.0, 0.05, 0.21, 0.0),
+          (100.0, 100.0, 1.0 - 1 / 365, 0.0501, 0.2, 0.01)]
+    fused = opt.price_scenarios(sc, n_paths=40_000, n_steps=64)
+    separate = [opt.price_scenarios([s], n_paths=40_000, n_steps=64)[0] for s in sc]
+    assert fused == separate
+
+
+# ---------------- C5 grid at full size: z-scores against Black-Scholes over all 4096 options -----
+
+def test_config5_grid_z_scores_are_standard_normal_where_the_clt_applies(engine):
+    """BASELINE.json configs[4] at full size (4096 options x 1M antithetic pairs x 252 steps, 0.5 s on a B200).
+    Options with >= 2000 expected in-the-money samples are in the Gaussian regime: their z-scores against the
+    closed form must look like N(0, <=1) (the reference's std error treats mirrored pairs as independent, which
+    over-states it in the money, so the spread may be below 1 but not above), with no option beyond 4.75 sigma
+    (two-sided tail probability 2e-6 per option).  Everywhere else |price - BS| <= 5 se + 1e-5."""
+    from math import erf, exp, log, sqrt
+
+    K, T = np.meshgrid(np.linspace(60.0, 140.0, 64), np.linspace(1.0 / 12.0, 2.0, 64), indexing="ij")
+    K, T = K.ravel(), T.ravel()
+    n_opt, n_paths, n_steps = K.size, 1_000_000, 252
+    S, r, sigma = 100.0, 0.05, 0.2
+    params = _ffi.make_params(S, K, T, r, sigma).reshape(n_opt, 1)
+    m = engine.simulate(_ffi.make_spec(_ffi.EUROPEAN, n_steps, antithetic=True), params, 42, n_paths)[:, 0]
+    price, se = runtime.discounted_price(m, r, T), runtime.discounted_std_error(m, r, T)
+    cdf = lambda x: 0.5 * (1.0 + erf(x / sqrt(2.0)))
+    d2 = np.array([(log(S / k) + (r - 0.5 * sigma**2) * t) / (sigma * sqrt(t)) for k, t in zip(K, T)])
+    bs = np.array([S * cdf(d + sigma * sqrt(t)) - k * exp(-r * t) * cdf(d) for d, k, t in zip(d2, K, T)])
+    assert np.all(np.abs(price - bs) <= 5.0 * se + 1e-5)
+    gaussian = np.array([cdf(d) for d in d2]) * 2 * n_paths >= 2000
+    assert gaussian.sum() > 3500
+    z = (price - bs)[gaussian] / se[gaussian]
+    assert abs(z.mean()) < 4.0 / np.sqrt(z.size), z.mean()
+    assert 0.5 < z.std() < 1.08, z.std()
+    assert np.max(np.abs(z)) < 4.75, np.max(np.abs(z))

@@ -19,7 +19,7 @@ from oracle import reference_mc as orc  # noqa: E402  (CPU baseline / checker on
 
 P = dict(S=100.0, K=100.0, T=1.0, r=0.05, sigma=0.2)
 # per path-step (instructions, MUFU) of each kernel family, from the shipped SASS (profiles/r01_sass_*.txt)
-BUDGET = {"european": (88 / 8, 2.0), "asian": (116 / 8, 3.0), "barrier": (104 / 8, 2.0), "qmc": (461 / 16, 2.0),
+BUDGET = {"european": (87 / 8, 2.0), "asian": (147 / 8, 2.0), "asian_ex2": (115 / 8, 3.0), "barrier": (104 / 8, 2.0), "qmc": (461 / 16, 2.0),
           "heston": (34.0, 5.0), "jump": (88 / 8, 2.0)}  # tools/sass_loop.py (Heston: one Box-Muller pair + sqrt(v) per step)
 
 
@@ -74,6 +74,12 @@ def main():
            lambda: float(asian.price(4_000_000, 252)),
            lambda: float(orc.exotic_price("asian", **P, seed=42, n_paths=100_000, n_steps=252)), 100_000 * 252,
            note="CPU oracle at 100k paths (the full path array of 4M x 253 doubles is 8 GB per temporary)")
+    # the same C3 launch with B200MC_FLAG_EXACT_EX2 (additive log2 state + MUFU.EX2 per step): A/B of the small-move update
+    a_params = _ffi.make_params(**P).reshape(1, 1)
+    a_price = lambda spec: float(ob.runtime.discounted_price(eng.simulate(spec, a_params, 42, 4_000_000)[0, 0], P["r"], P["T"]))
+    record("C3 Asian arithmetic call 4M x 252, MUFU.EX2 form (flag EXACT_EX2)", "asian_ex2", 4_000_000 * 252, 4_000_000 * 252,
+           lambda: a_price(_ffi.make_spec(_ffi.ASIAN_ARITH, 252, exact_ex2=True)), lambda: None, 1,
+           note="A/B row: the default C3 row above takes the multiplicative small-move update; no CPU leg")
     # C4: up-and-out barrier call, 16M x 365
     bar = ob.BarrierOption(**P, seed=42, barrier=120.0)
     record("C4 up-and-out barrier call 16M x 365", "barrier", 16_000_000 * 365, 16_000_000 * 365,

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Opcode histogram of the innermost MUFU-carrying loop of a kernel in libb200mc.so (runs here, no GPU).
-Usage: tools/sass_loop.py <mangled-name-regex> [--list]   e.g.  tools/sass_loop.py 'european_kernelILi1ELb1ELi6ELb0'"""
+Usage: tools/sass_loop.py <mangled-name-regex> [--list] [--all]   e.g.  tools/sass_loop.py 'european_kernelILi1ELb1ELi6ELb0'"""
 import collections
 import os
 import re
@@ -28,6 +28,22 @@ def functions():
         yield name, body
 
 
+def loops(body):
+    """Every backward-branch loop that carries MUFU work, innermost (shortest) first."""
+    found = []
+    for addr, text in body:
+        m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d+,\s*)?(0x[0-9a-f]+)", text)
+        if not m:
+            continue
+        tgt = int(m.group(1), 16)
+        if tgt >= addr:
+            continue
+        loop = [t for a, t in body if tgt <= a <= addr]
+        if any("MUFU" in t for t in loop):
+            found.append((tgt, addr, loop))
+    return sorted(found, key=lambda x: len(x[2]))
+
+
 def hot_loop(body):
     best = None
     for addr, text in body:
@@ -52,7 +68,12 @@ def main():
         hl = hot_loop(body)
         if hl is None:
             continue
-        tgt, addr, loop = hl
+        for tgt, addr, loop in (loops(body) if "--all" in sys.argv else [hl]):
+            report(name, tgt, addr, loop)
+
+
+def report(name, tgt, addr, loop):
+    if True:
         ops = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", t).split()[0] for t in loop)
         mufu = sum(v for k, v in ops.items() if k.startswith("MUFU"))
         print(f"== {name}\n   loop 0x{tgt:04x}..0x{addr:04x}: {len(loop)} instructions, {mufu} MUFU")
