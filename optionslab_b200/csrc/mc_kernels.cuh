@@ -227,23 +227,25 @@ __device__ __forceinline__ void advance_pair(const NormalPair& p, int n_use, con
 constexpr float kRadMax = 4.79583152331271954f;  // sqrt(23): u >= 2^-23 (normal.cuh)
 constexpr float kSmallMove = 0.25f;
 
+template <int DEG = 5>
 __device__ __forceinline__ float exp2m1_small(float x) {
-  float t = fmaf(x, 1.3333558146e-3f, 9.6181291076e-3f);  // ln2^5/120, ln2^4/24
-  t = fmaf(x, t, 5.5504108665e-2f);                       // ln2^3/6
-  t = fmaf(x, t, 2.4022650696e-1f);                       // ln2^2/2
-  t = fmaf(x, t, 6.9314718056e-1f);                       // ln2
+  float t = DEG >= 5 ? fmaf(x, 1.3333558146e-3f, 9.6181291076e-3f) : 9.6181291076e-3f;  // ln2^5/120, ln2^4/24
+  if (DEG >= 4) t = fmaf(x, t, 5.5504108665e-2f);                                         // ln2^3/6
+  else t = 5.5504108665e-2f;
+  t = fmaf(x, t, 2.4022650696e-1f);                                                       // ln2^2/2
+  t = fmaf(x, t, 6.9314718056e-1f);                                                       // ln2
   return x * t;
 }
 
-template <int NS>
+template <int NS, int DEG = 5>
 __device__ __forceinline__ void advance_pair_small(const NormalPair& p, int n_use, const Coef (&q)[NS], float (&s)[NS], float (&aux)[NS]) {
 #pragma unroll
   for (int k = 0; k < NS; ++k) {
     const float rc = p.rad * q[k].c;
-    s[k] = fmaf(s[k], exp2m1_small(fmaf(rc, p.cs, q[k].d)), s[k]);
+    s[k] = fmaf(s[k], exp2m1_small<DEG>(fmaf(rc, p.cs, q[k].d)), s[k]);
     aux[k] += s[k];
     if (n_use > 1) {
-      s[k] = fmaf(s[k], exp2m1_small(fmaf(rc, p.sn, q[k].d)), s[k]);
+      s[k] = fmaf(s[k], exp2m1_small<DEG>(fmaf(rc, p.sn, q[k].d)), s[k]);
       aux[k] += s[k];
     }
   }
@@ -269,7 +271,7 @@ __device__ __forceinline__ float path_payoff(float l, float aux, const Coef& q, 
 
 // One CTA's share of one option: paths_per_thread paths per thread, payoffs accumulated in FP32 per thread.
 // SMALL selects the multiplicative arithmetic-Asian update (state = S_t/S_0 instead of log2 of it).
-template <int KIND, int NS, bool SMALL, int UNROLL>
+template <int KIND, int NS, bool SMALL, int UNROLL, int DEG = 5>
 __device__ __forceinline__ void simulate_tile(const SimArgs& a, const Coef (&q)[NS], uint32_t stream, uint64_t tile_first, float (&acc)[2 * NS]) {
   for (uint32_t j = 0; j < a.paths_per_thread; ++j) {
     const uint64_t local = tile_first + (uint64_t)j * kBlock + threadIdx.x;
@@ -278,7 +280,7 @@ __device__ __forceinline__ void simulate_tile(const SimArgs& a, const Coef (&q)[
 #pragma unroll
     for (int k = 0; k < NS; ++k) l[k] = SMALL ? 1.0f : 0.0f, aux[k] = 0.0f;
     for_each_pair<UNROLL>(a.path_begin + local, a.n_steps, stream, a.rk, [&](const NormalPair& p, int n_use) {
-      if (SMALL) advance_pair_small<NS>(p, n_use, q, l, aux);
+      if (SMALL) advance_pair_small<NS, DEG>(p, n_use, q, l, aux);
       else advance_pair<KIND, NS>(p, n_use, q, l, aux);
     });
 #pragma unroll
@@ -290,7 +292,7 @@ __device__ __forceinline__ void simulate_tile(const SimArgs& a, const Coef (&q)[
   }
 }
 
-template <int KIND, int NS, int MINB, int UNROLL = 1>
+template <int KIND, int NS, int MINB, int UNROLL = 1, int DEG = 5>
 __global__ void __launch_bounds__(kBlock, MINB) pathdep_kernel(const SimArgs a) {
   __shared__ Coef coef_s[NS];
   const uint32_t opt = blockIdx.x / a.tiles;
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(kBlock, MINB) pathdep_kernel(const SimArgs a) 
 #pragma unroll
     for (int k = 0; k < NS; ++k) small = small && (fabsf(q[k].d) + fabsf(q[k].c) * kRadMax <= kSmallMove);  // NaN -> false
   }
-  if (small) simulate_tile<B200MC_ASIAN_ARITH, NS, true, UNROLL>(a, q, stream, tile_first, acc);  // CTA-uniform branch
+  if (small) simulate_tile<B200MC_ASIAN_ARITH, NS, true, UNROLL, DEG>(a, q, stream, tile_first, acc);  // CTA-uniform branch
   else simulate_tile<KIND, NS, false, UNROLL>(a, q, stream, tile_first, acc);
   block_reduce_store<2 * NS>(acc, a.partials + (size_t)blockIdx.x * (2 * NS));
 }
