@@ -46,6 +46,8 @@ typedef enum {
 /* ASIAN_ARITH: always evaluate S_t = S_0 * 2^(l_t) with MUFU.EX2 instead of the multiplicative
  * small-move update the kernel picks per option when |log2 increment| <= 0.25 (mc_kernels.cuh). */
 #define B200MC_FLAG_EXACT_EX2 1u
+/* FP64 parity mode, EUROPEAN: use the plain-load kernel even when the bulk-async staged one applies (A/B). */
+#define B200MC_FLAG_NO_BULK_COPY 2u
 
 typedef struct {
   int32_t kind;           /* b200mc_kind */

@@ -22,6 +22,7 @@ MAX_SCENARIOS = 16
 
 EUROPEAN, ASIAN_ARITH, ASIAN_GEOM, BARRIER, LOOKBACK = range(5)
 FLAG_EXACT_EX2 = 1
+FLAG_NO_BULK_COPY = 2
 
 
 class Spec(C.Structure):
@@ -114,9 +115,9 @@ def load_library():
 
 
 def make_spec(kind: int, n_steps: int, *, is_put=False, antithetic=False, barrier_down=False, barrier_in=False,
-              lookback_fixed=False, exact_ex2=False) -> Spec:
+              lookback_fixed=False, exact_ex2=False, no_bulk_copy=False) -> Spec:
     return Spec(int(kind), int(bool(is_put)), int(bool(antithetic)), int(bool(barrier_down)), int(bool(barrier_in)),
-                int(bool(lookback_fixed)), int(n_steps), FLAG_EXACT_EX2 if exact_ex2 else 0)
+                int(bool(lookback_fixed)), int(n_steps), (FLAG_EXACT_EX2 if exact_ex2 else 0) | (FLAG_NO_BULK_COPY if no_bulk_copy else 0))
 
 
 def make_params(S, K, T, r, sigma, q=0.0, barrier=0.0) -> np.ndarray:

@@ -277,7 +277,16 @@ int enqueue_from_normals(b200mc_engine* e, const b200mc_spec_t* spec, const b200
   const int slot = (int)(e->timed % b200mc_engine::kRing);
   if (time_it) CU_TRY(e, cudaEventRecord(e->ring0[slot], stream));
   switch (spec->kind) {
-    case B200MC_EUROPEAN: from_normals_kernel<B200MC_EUROPEAN><<<grid, kF64Block, 0, stream>>>(a); break;
+    case B200MC_EUROPEAN:
+      // bulk-async staged kernel when the rows can be copied in 16-byte units, else the plain-load kernel
+      if ((spec->n_steps & 1u) == 0 && ((uintptr_t)Z_dev & 15u) == 0 && !(spec->flags & B200MC_FLAG_NO_BULK_COPY)) {
+        static_assert(kTmaSmemBytes <= 227 * 1024, "tile ring exceeds shared memory");
+        CU_TRY(e, cudaFuncSetAttribute(european_from_normals_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
+        european_from_normals_tma_kernel<<<grid, kF64Block, kTmaSmemBytes, stream>>>(a);
+      } else {
+        from_normals_kernel<B200MC_EUROPEAN><<<grid, kF64Block, 0, stream>>>(a);
+      }
+      break;
     case B200MC_ASIAN_ARITH: from_normals_kernel<B200MC_ASIAN_ARITH><<<grid, kF64Block, 0, stream>>>(a); break;
     case B200MC_ASIAN_GEOM: from_normals_kernel<B200MC_ASIAN_GEOM><<<grid, kF64Block, 0, stream>>>(a); break;
     case B200MC_BARRIER: from_normals_kernel<B200MC_BARRIER><<<grid, kF64Block, 0, stream>>>(a); break;

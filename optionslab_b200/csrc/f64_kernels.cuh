@@ -137,4 +137,143 @@ __global__ void __launch_bounds__(kF64Block) from_normals_kernel(const F64Args a
   }
 }
 
+
+// ---- European parity mode with bulk-async (TMA engine) staging ---------------------------------------------------
+// The kernel above keeps at most 8 x 256 B per warp in flight and alternates load and compute phases; this one keeps
+// the copy engine busy all the time.  Each warp owns 32 consecutive rows of Z and a private ring of kTmaStages
+// shared-memory tiles; every lane issues ONE cp.async.bulk per chunk for its own row segment (kF64Chunk steps =
+// 256 B, global -> shared, completion counted in bytes on the stage's mbarrier), so nothing passes through
+// registers and kTmaStages x 8 KB per warp are in flight while the warp adds up the previous chunk.  Rows are parked at a
+// pitch of 17 x 16 B, which makes the per-lane LDS.128 row walk bank-conflict free.  Requirements (checked by the
+// host, which otherwise launches from_normals_kernel): n_steps even (16-byte row pitch in HBM) and Z 16-byte aligned.
+// The arithmetic is the same statement sequence as from_normals_kernel<B200MC_EUROPEAN>.
+constexpr int kTmaStages = 3;
+constexpr int kTmaPitch = kF64Chunk * 8 + 16;                                   // bytes per parked row segment
+constexpr int kTmaWarpBytes = kTmaStages * 32 * kTmaPitch;                      // 26112 B per warp
+constexpr int kTmaSmemBytes = kF64Warps * kTmaWarpBytes;                        // 104448 B per CTA -> 2 CTAs per SM
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kF64Block) european_from_normals_tma_kernel(const F64Args a) {
+  extern __shared__ __align__(128) unsigned char tma_tiles[];
+  __shared__ __align__(8) unsigned long long bars[kF64Warps][kTmaStages];
+  __shared__ double red[kF64Warps][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t warp_first = ((uint64_t)blockIdx.x * kF64Warps + warp) * 32;
+  const uint64_t path = warp_first + lane;
+  const bool live = path < a.n_paths;
+  const uint32_t live_rows = warp_first < a.n_paths ? (uint32_t)min((uint64_t)32, a.n_paths - warp_first) : 0u;
+  const bool is_put = a.is_put != 0;
+  const uint32_t n = a.n_steps;
+  const uint32_t n_chunks = (n + kF64Chunk - 1) / kF64Chunk;
+
+  const double dt = __ddiv_rn(a.T, (double)n);
+  const double drift = __dmul_rn(__dsub_rn(__dsub_rn(a.r, a.q), __dmul_rn(__dmul_rn(0.5, a.sigma), a.sigma)), dt);
+  const double vol = __dmul_rn(a.sigma, sqrt(dt));
+  const double log_S0 = log(a.S);
+
+  unsigned char* my_tiles = tma_tiles + (size_t)warp * kTmaWarpBytes;
+  const uint32_t tiles_u32 = smem_u32(my_tiles);
+  const uint32_t bar0 = smem_u32(&bars[warp][0]);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(bar0 + 8u * s, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const double* my_row = a.Z + path * n;  // only dereferenced (by the copy engine) when live
+  auto issue = [&](uint32_t c) {
+    const uint32_t stage = c % kTmaStages;
+    const uint32_t bytes = min((uint32_t)kF64Chunk, n - c * kF64Chunk) * 8u;
+    if (lane == 0) mbar_expect_tx(bar0 + 8u * stage, live_rows * bytes);
+    __syncwarp();
+    if (live) bulk_g2s(tiles_u32 + (stage * 32u + (uint32_t)lane) * kTmaPitch, my_row + (size_t)c * kF64Chunk, bytes, bar0 + 8u * stage);
+  };
+
+  double acc_pos = 0.0, acc_neg = 0.0;
+  if (live_rows > 0) {
+    for (uint32_t c = 0; c < (uint32_t)kTmaStages && c < n_chunks; ++c) issue(c);
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+      const uint32_t stage = c % kTmaStages;
+      const uint32_t width = min((uint32_t)kF64Chunk, n - c * kF64Chunk);
+      mbar_wait(bar0 + 8u * stage, (c / kTmaStages) & 1u);
+      if (live) {
+        const double2* row = reinterpret_cast<const double2*>(my_tiles + (size_t)(stage * 32 + lane) * kTmaPitch);
+        for (uint32_t j = 0; j < width / 2; ++j) {
+          const double2 zz = row[j];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const double z = h ? zz.y : zz.x;
+            if (!a.accumulate) {
+              acc_pos = __dadd_rn(acc_pos, z);
+            } else {
+              acc_pos = __dadd_rn(acc_pos, __dadd_rn(drift, __dmul_rn(vol, z)));
+              if (a.antithetic) acc_neg = __dadd_rn(acc_neg, __dsub_rn(drift, __dmul_rn(vol, z)));
+            }
+          }
+        }
+      }
+      __syncwarp();  // every lane has consumed this stage (in-order issue: its LDS results were used) before it is refilled
+      if (c + kTmaStages < n_chunks) issue(c + kTmaStages);
+    }
+  }
+
+  double p0 = 0.0, p1 = 0.0;
+  if (live) {
+    double up, down;
+    if (!a.accumulate) {  // gbm_numpy.py:46,50
+      const double base = __dadd_rn(log_S0, __dmul_rn(drift, (double)n));
+      up = __dadd_rn(base, __dmul_rn(vol, acc_pos));
+      down = __dsub_rn(base, __dmul_rn(vol, acc_pos));
+    } else {              // monte_carlo_unified.py:333-341
+      up = __dadd_rn(log_S0, acc_pos);
+      down = __dadd_rn(log_S0, acc_neg);
+    }
+    p0 = vanilla64(exp(up), a.K, is_put);
+    if (a.antithetic) p1 = vanilla64(exp(down), a.K, is_put);
+    if (a.payoffs) {
+      a.payoffs[path] = p0;
+      if (a.antithetic) a.payoffs[a.n_paths + path] = p1;
+    }
+  }
+  double s1 = p0 + p1, s2 = p0 * p0 + p1 * p1;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+  }
+  if (lane == 0) red[warp][0] = s1, red[warp][1] = s2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+    for (int w = 0; w < kF64Warps; ++w) t1 += red[w][0], t2 += red[w][1];
+    a.partials[2 * (size_t)blockIdx.x] = t1;
+    a.partials[2 * (size_t)blockIdx.x + 1] = t2;
+  }
+}
+
 }  // namespace b200mc

@@ -117,8 +117,10 @@ def main():
         mom = torch.empty(3, dtype=torch.float64, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-        for kind, name, anti in ((_ffi.EUROPEAN, "european", True), (_ffi.ASIAN_ARITH, "asian", False), (_ffi.BARRIER, "barrier", False)):
-            spec = _ffi.make_spec(kind, n_steps, antithetic=anti)
+        for kind, name, anti, plain in ((_ffi.EUROPEAN, "european (bulk-async staged)", True, False),
+                                        (_ffi.EUROPEAN, "european (plain loads, flag NO_BULK_COPY)", True, True),
+                                        (_ffi.ASIAN_ARITH, "asian", False, False), (_ffi.BARRIER, "barrier", False, False)):
+            spec = _ffi.make_spec(kind, n_steps, antithetic=anti, no_bulk_copy=plain)
             eng.set_kernel_timing(True)
             for _ in range(4):
                 eng.payoffs_from_normals_device(spec, _ffi.make_params(**P, barrier=120.0), Z.data_ptr(), n_paths, pay.data_ptr(), mom.data_ptr(), stream)
