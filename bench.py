@@ -41,7 +41,7 @@ WORKLOAD = (f"C5: {N_OPT}-option European call grid ({N_STRIKES} strikes 60..140
 # with cuobjdump — profiles/r01_sass_european.txt): 88 issued instructions per Philox call = 8 path-steps, of which
 # 16 MUFU, 16 IMAD.WIDE (fmaheavy pipe), 18 LOP3 + 8 LEA.HI + 4 PRMT (ALU pipe).
 INSTR_PER_STEP, MUFU_PER_STEP, IMAD_PER_STEP, LOP_PER_STEP = 87 / 8, 2.0, 2.0, 30 / 8
-ASIAN_INSTR_PER_STEP = 147 / 8  # pathdep_kernel<ASIAN_ARITH,1> small-move loop (tools/sass_loop.py --all): 52 FFMA, 16 MUFU per 8 steps
+ASIAN_INSTR_PER_STEP = 123 / 8  # pathdep_kernel<ASIAN_ARITH,1> small-move loop (tools/sass_loop.py --all): 20 FFMA2 + 4 FMUL2 + 32 FP32, 16 MUFU per 8 steps
 
 
 def grid_params():
@@ -291,7 +291,7 @@ def run_engine_arm(args):
             arate = work_per_step / world / (akt["mean_ms"] * 1e-3)
             asian = {"workload": f"{N_OPT} arithmetic-average Asian calls (same strikes/maturities) x {N_PATHS} paths x {N_STEPS} steps, no mirroring",
                      "value": work_per_step * 2 / float(at.item()), "unit": UNIT, "steps": 2, "ms_per_step": 1e3 * float(at.item()) / 2,
-                     "kernel": "pathdep_kernel<ASIAN_ARITH,NS=1> (small-move multiplicative update)", "kernel_ms": akt["mean_ms"],
+                     "kernel": "pathdep_kernel<ASIAN_ARITH,NS=1> (small-move multiplicative update, packed FFMA2)", "kernel_ms": akt["mean_ms"],
                      "per_path_step": {"instructions": ASIAN_INSTR_PER_STEP, "mufu": 2.0},
                      "xu_frac": arate * 2.0 / peaks["mufu_per_s"], "issue_frac": arate * ASIAN_INSTR_PER_STEP / peaks["issue_per_s"],
                      "all_prices_below_european": None, "moments": am}

@@ -151,6 +151,7 @@ void plan_tiles(const b200mc_engine* e, uint32_t n_opt, uint64_t n_paths, uint32
 // interleaved, which needs ~60-75 registers; squeezing below 48 costs 5-10%.
 constexpr int kMinBlocksSmall = 6;    // European, 1-2 scenarios (40-47 registers)
 constexpr int kMinBlocksPathdep = 6;  // Asian / barrier / lookback, 1-2 scenarios (<= 40 registers)
+constexpr int kMinBlocksAsian = 5;    // arithmetic Asian, 1-2 scenarios: the packed small-move loop wants 43 registers (profiles/r01_variants14*)
 constexpr int kMinBlocksWide = 2;     // 4-16 scenarios (<= 128 registers)
 
 template <int NS>
@@ -168,12 +169,15 @@ cudaError_t launch_european(const SimArgs& a, bool anti, bool cv, dim3 grid, cud
 
 template <int KIND>
 cudaError_t launch_pathdep(const SimArgs& a, uint32_t ns, dim3 grid, cudaStream_t s) {
+  constexpr int kMinB = KIND == B200MC_ASIAN_ARITH ? kMinBlocksAsian : kMinBlocksPathdep;
   switch (ns) {
-    case 1: pathdep_kernel<KIND, 1, kMinBlocksPathdep><<<grid, kBlock, 0, s>>>(a); break;
-    case 2: pathdep_kernel<KIND, 2, kMinBlocksPathdep><<<grid, kBlock, 0, s>>>(a); break;
-    case 4: pathdep_kernel<KIND, 4, kMinBlocksWide><<<grid, kBlock, 0, s>>>(a); break;
-    case 8: pathdep_kernel<KIND, 8, kMinBlocksWide><<<grid, kBlock, 0, s>>>(a); break;
-    default: pathdep_kernel<KIND, 16, kMinBlocksWide><<<grid, kBlock, 0, s>>>(a); break;
+    case 1: pathdep_kernel<KIND, 1, kMinB><<<grid, kBlock, 0, s>>>(a); break;
+    case 2: pathdep_kernel<KIND, 2, kMinB><<<grid, kBlock, 0, s>>>(a); break;
+    // 4+ scenarios: the scalar Horner form (immediates instead of 10 registers of packed coefficients; same roundings,
+    // so a scenario's bits do not depend on which form its launch used)
+    case 4: pathdep_kernel<KIND, 4, kMinBlocksWide, 1, 5><<<grid, kBlock, 0, s>>>(a); break;
+    case 8: pathdep_kernel<KIND, 8, kMinBlocksWide, 1, 5><<<grid, kBlock, 0, s>>>(a); break;
+    default: pathdep_kernel<KIND, 16, kMinBlocksWide, 1, 5><<<grid, kBlock, 0, s>>>(a); break;
   }
   return cudaGetLastError();
 }

@@ -9,6 +9,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "optionslab_b200", "libb200mc.so")
+if "--so" in sys.argv:  # inspect another binary (scratch experiments)
+    SO = sys.argv[sys.argv.index("--so") + 1]
 
 
 def functions():
