@@ -94,6 +94,8 @@ typedef struct {
  *   model = B200MC_JUMP_MERTON : a = mu_j, b = sigma_j           (log-normal jumps)
  *   model = B200MC_JUMP_KOU    : a = p,    b = eta1, c = eta2    (double-exponential jumps) */
 typedef enum { B200MC_JUMP_MERTON = 0, B200MC_JUMP_KOU = 1 } b200mc_jump_model;
+#define B200MC_MODEL_PUT 1
+#define B200MC_MODEL_SHARED_STREAM 2
 typedef struct {
   int32_t model;
   int32_t reserved0;
@@ -191,7 +193,10 @@ int b200mc_sobol_normals(b200mc_engine_t* eng, const uint32_t* x_host, uint64_t 
 /* ---- other Euler Monte Carlo models of the reference -------------------- *
  * Heston, full-truncation Euler: replaces HestonPricer.price_monte_carlo (src/pricing_models/heston.py:184-255).
  * One Box-Muller pair per step (Z1 and the independent part of Z2).  params: [n_opt]; out: [n_opt].
- * Paths / seed / stream conventions as b200mc_simulate (option i uses stream stream_base + i). */
+ * Paths / seed / stream conventions as b200mc_simulate (option i uses stream stream_base + i).
+ * is_put carries B200MC_MODEL_* bits: B200MC_MODEL_PUT prices puts; B200MC_MODEL_SHARED_STREAM makes every entry of
+ * params use stream stream_base, i.e. the option axis becomes a common-random-number scenario axis (the bumped
+ * re-pricings of compute_greeks_unified, src/greeks/unified_greeks.py:295-358, in one launch). */
 int b200mc_simulate_heston(b200mc_engine_t* eng, const b200mc_heston_params_t* params_host, uint32_t n_opt, int is_put,
                            uint32_t n_steps, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
                            b200mc_moments_t* out_host);

@@ -9,7 +9,8 @@ library or the device is missing — there is no CPU fallback.
 
 from .exceptions import AccelerationError, ConvergenceError, GreeksError, InputValidationError, MonteCarloError
 from .exotic_options import AsianOption, BarrierOption, LookbackOption, price_asian, price_barrier, price_lookback
-from .greeks import ExerciseStyle, ExoticAdapter, OptionType, PricerProtocol, compute_greeks_unified
+from .greeks import (ExerciseStyle, ExoticAdapter, HestonAdapter, JumpDiffusionAdapter, OptionType, PricerProtocol,
+                     compute_greeks_unified, greeks_heston, greeks_jump_diffusion)
 from .models import HestonPricer, KouJumpDiffusion, MertonJumpDiffusion
 from .monte_carlo import MCMethod, MCResult, MonteCarloPricer
 from .monte_carlo_unified import MonteCarloPricerUni
@@ -21,6 +22,7 @@ __all__ = [
     "AsianOption", "BarrierOption", "LookbackOption", "price_asian", "price_barrier", "price_lookback",
     "HestonPricer", "MertonJumpDiffusion", "KouJumpDiffusion",
     "monte_carlo_convergence_test",
-    "PricerProtocol", "ExoticAdapter", "compute_greeks_unified", "OptionType", "ExerciseStyle",
+    "PricerProtocol", "ExoticAdapter", "HestonAdapter", "JumpDiffusionAdapter", "compute_greeks_unified", "greeks_heston",
+    "greeks_jump_diffusion", "OptionType", "ExerciseStyle",
     "MonteCarloError", "InputValidationError", "ConvergenceError", "AccelerationError", "GreeksError",
 ]

@@ -53,6 +53,7 @@ HESTON_PARAMS_DTYPE = np.dtype([(n, "f8") for n in ("S", "K", "T", "r", "q", "ka
 JUMP_PARAMS_DTYPE = np.dtype([("model", "i4"), ("reserved0", "i4"), ("lambda_j", "f8"), ("a", "f8"), ("b", "f8"), ("c", "f8"),
                               ("reserved", "f8", (3,))])
 JUMP_MERTON, JUMP_KOU = 0, 1
+MODEL_PUT, MODEL_SHARED_STREAM = 1, 2
 
 # name -> (restype, argtypes); also the list the CPU tests check the .so exports against the header.
 _P = C.c_void_p
@@ -245,25 +246,27 @@ class Engine:
 
     # -- Heston / jump-diffusion models -----------------------------------------------------
     def simulate_heston(self, params: np.ndarray, is_put: bool, n_steps: int, seed: int, n_paths: int, *, stream_base: int = 0,
-                        path_begin: int = 0) -> np.ndarray:
-        """params: HESTON_PARAMS_DTYPE [n_opt] -> MOMENTS_DTYPE [n_opt]."""
+                        path_begin: int = 0, shared_stream: bool = False) -> np.ndarray:
+        """params: HESTON_PARAMS_DTYPE [n_opt] -> MOMENTS_DTYPE [n_opt].  shared_stream: all entries price the same draws (CRN)."""
         params = np.ascontiguousarray(params, dtype=HESTON_PARAMS_DTYPE).reshape(-1)
         out = np.empty(params.shape, dtype=MOMENTS_DTYPE)
-        rc = self._lib.b200mc_simulate_heston(self._h, params.ctypes.data, params.size, int(bool(is_put)), int(n_steps),
+        rc = self._lib.b200mc_simulate_heston(self._h, params.ctypes.data, params.size,
+                                              (MODEL_PUT if is_put else 0) | (MODEL_SHARED_STREAM if shared_stream else 0), int(n_steps),
                                               int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF, int(path_begin), int(n_paths),
                                               out.ctypes.data)
         self._check(rc, "b200mc_simulate_heston")
         return out
 
     def simulate_jump_diffusion(self, params: np.ndarray, jumps: np.ndarray, is_put: bool, n_steps: int, seed: int, n_paths: int, *,
-                                stream_base: int = 0, path_begin: int = 0) -> np.ndarray:
+                                stream_base: int = 0, path_begin: int = 0, shared_stream: bool = False) -> np.ndarray:
         """params: PARAMS_DTYPE [n_opt], jumps: JUMP_PARAMS_DTYPE [n_opt] -> MOMENTS_DTYPE [n_opt]."""
         params = np.ascontiguousarray(params, dtype=PARAMS_DTYPE).reshape(-1)
         jumps = np.ascontiguousarray(jumps, dtype=JUMP_PARAMS_DTYPE).reshape(-1)
         if jumps.size != params.size:
             raise MonteCarloError("one jump parameter set per option")
         out = np.empty(params.shape, dtype=MOMENTS_DTYPE)
-        rc = self._lib.b200mc_simulate_jump_diffusion(self._h, params.ctypes.data, jumps.ctypes.data, params.size, int(bool(is_put)),
+        rc = self._lib.b200mc_simulate_jump_diffusion(self._h, params.ctypes.data, jumps.ctypes.data, params.size,
+                                                      (MODEL_PUT if is_put else 0) | (MODEL_SHARED_STREAM if shared_stream else 0),
                                                       int(n_steps), int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF,
                                                       int(path_begin), int(n_paths), out.ctypes.data)
         self._check(rc, "b200mc_simulate_jump_diffusion")

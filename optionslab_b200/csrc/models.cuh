@@ -25,7 +25,7 @@ struct HestonArgs {
   uint32_t n_opt, tiles, paths_per_thread, n_steps;
   PhiloxKeys rk;
   uint32_t stream_base;
-  int32_t is_put;
+  int32_t is_put;  // B200MC_MODEL_* bits
 };
 
 struct HestonCoef {
@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(kBlock, 4) heston_kernel(const HestonArgs a) {
   __syncthreads();
   const HestonCoef c = coef_s;
   float acc[2] = {0.0f, 0.0f};
-  const uint32_t stream = a.stream_base + opt;
-  const bool is_put = a.is_put != 0;
+  const uint32_t stream = a.stream_base + ((a.is_put & B200MC_MODEL_SHARED_STREAM) ? 0u : opt);  // shared: CRN across the option axis
+  const bool is_put = (a.is_put & B200MC_MODEL_PUT) != 0;
   const uint64_t tile_first = (uint64_t)tile * (uint64_t)(kBlock * a.paths_per_thread);
   for (uint32_t j = 0; j < a.paths_per_thread; ++j) {
     const uint64_t local = tile_first + (uint64_t)j * kBlock + threadIdx.x;
@@ -123,7 +123,7 @@ struct JumpArgs {
   uint32_t n_opt, tiles, paths_per_thread, n_steps;
   PhiloxKeys rk;
   uint32_t stream_base;
-  int32_t is_put;
+  int32_t is_put;  // B200MC_MODEL_* bits
 };
 
 struct JumpCoef {
@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(kBlock, 4) jump_kernel(const JumpArgs a) {
   __syncthreads();
   const JumpCoef c = coef_s;
   float acc[2] = {0.0f, 0.0f};
-  const uint32_t stream = a.stream_base + opt;
-  const bool is_put = a.is_put != 0;
+  const uint32_t stream = a.stream_base + ((a.is_put & B200MC_MODEL_SHARED_STREAM) ? 0u : opt);  // shared: CRN across the option axis
+  const bool is_put = (a.is_put & B200MC_MODEL_PUT) != 0;
   const uint64_t tile_first = (uint64_t)tile * (uint64_t)(kBlock * a.paths_per_thread);
   for (uint32_t j = 0; j < a.paths_per_thread; ++j) {
     const uint64_t local = tile_first + (uint64_t)j * kBlock + threadIdx.x;

@@ -16,8 +16,8 @@ from typing import Dict, List, Literal, Protocol, Tuple, runtime_checkable
 
 from .exceptions import GreeksError
 
-__all__ = ["PricerProtocol", "ExoticAdapter", "compute_greeks_unified", "greek_scenarios", "greeks_from_prices",
-           "OptionType", "ExerciseStyle"]
+__all__ = ["PricerProtocol", "ExoticAdapter", "HestonAdapter", "JumpDiffusionAdapter", "compute_greeks_unified",
+           "greeks_heston", "greeks_jump_diffusion", "greek_scenarios", "greeks_from_prices", "OptionType", "ExerciseStyle"]
 
 
 class OptionType(IntEnum):
@@ -128,6 +128,47 @@ class ExoticAdapter:
         return fused(scenarios, n_paths=self.n_paths, n_steps=self.n_steps, **self._kwargs(option_type, kwargs))
 
 
+class HestonAdapter:
+    """src/greeks/unified_greeks.py:74-104: PricerProtocol face of a HestonPricer, ``sigma`` mapped to v0 = sigma^2.
+    The reference's adapter calls the semi-analytic ``price_european``; this package accelerates the Monte Carlo path,
+    so the adapter prices with ``price_monte_carlo`` on a FIXED seed (common random numbers across the bumps) and offers
+    the fused ``price_scenarios`` route: all 8-14 bumped re-pricings of compute_greeks_unified in one launch."""
+
+    def __init__(self, heston_pricer, n_paths: int = 100000, n_steps: int = 252, seed: int = 0):
+        self.heston = heston_pricer
+        self.n_paths, self.n_steps, self.seed = n_paths, n_steps, seed
+        self._original_v0 = heston_pricer.v0
+
+    def price(self, S, K, T, r, sigma, option_type, q=0.0, **kwargs) -> float:
+        self.heston.v0 = sigma**2
+        try:
+            return self.heston.price_monte_carlo(S, K, T, r, q, option_type, self.n_paths, self.n_steps, seed=self.seed)
+        finally:
+            self.heston.v0 = self._original_v0
+
+    def price_scenarios(self, scenarios, option_type, **kwargs):
+        sc = [(s[0], s[1], s[2], s[3], s[4] ** 2, s[5]) for s in scenarios]
+        return self.heston.price_scenarios(sc, option_type, self.n_paths, self.n_steps, self.seed)
+
+    def __repr__(self):
+        return f"HestonAdapter({self.heston})"
+
+
+class JumpDiffusionAdapter:
+    """src/greeks/unified_greeks.py:155-174 for MertonJumpDiffusion / KouJumpDiffusion, Monte Carlo backed (fixed seed =
+    common random numbers; fused single-launch route as HestonAdapter)."""
+
+    def __init__(self, jd_model, n_paths: int = 100000, n_steps: int = 252, seed: int = 0):
+        self.jd = jd_model
+        self.n_paths, self.n_steps, self.seed = n_paths, n_steps, seed
+
+    def price(self, S, K, T, r, sigma, option_type, q=0.0, **kwargs) -> float:
+        return self.jd.price_monte_carlo(S, K, T, r, sigma, option_type, q, self.n_paths, self.n_steps, seed=self.seed)
+
+    def price_scenarios(self, scenarios, option_type, **kwargs):
+        return self.jd.price_scenarios(scenarios, option_type, self.n_paths, self.n_steps, self.seed)
+
+
 def compute_greeks_unified(pricer: PricerProtocol, S: float, K: float, T: float, r: float, sigma: float,
                            option_type: Literal["call", "put"] = "call", q: float = 0.0,
                            include_second_order: bool = True, **pricer_kwargs) -> "OrderedDict[str, float]":
@@ -142,3 +183,12 @@ def compute_greeks_unified(pricer: PricerProtocol, S: float, K: float, T: float,
         return greeks_from_prices(dict(zip(pts, prices)), S, K, T, r, sigma, q, include_second_order)
     except Exception as e:
         raise GreeksError(f"Failed to compute unified Greeks: {str(e)}") from e
+
+
+def greeks_heston(heston_pricer, S, K, T, r, sigma, option_type: str = "call", q: float = 0.0, **adapter_kwargs):
+    """unified_greeks.py:375-388 (Monte Carlo backed; ``adapter_kwargs`` = n_paths / n_steps / seed)."""
+    return compute_greeks_unified(HestonAdapter(heston_pricer, **adapter_kwargs), S, K, T, r, sigma, option_type, q)
+
+
+def greeks_jump_diffusion(jd_model, S, K, T, r, sigma, option_type: str = "call", q: float = 0.0, **adapter_kwargs):
+    return compute_greeks_unified(JumpDiffusionAdapter(jd_model, **adapter_kwargs), S, K, T, r, sigma, option_type, q)

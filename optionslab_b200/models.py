@@ -19,13 +19,13 @@ from . import _ffi, distributed, runtime
 __all__ = ["HestonPricer", "MertonJumpDiffusion", "KouJumpDiffusion"]
 
 
-def _sharded(run, n_paths: int) -> np.ndarray:
+def _sharded(run, n_paths: int, n_out: int = 1) -> np.ndarray:
     """Run ``run(path_begin, count)`` on this rank's slice of the global paths and all-reduce the moments."""
     ctx = distributed.current()
     if ctx is None or ctx.world_size == 1:
         return run(0, n_paths)
     begin, count = distributed.partition_paths(n_paths, ctx.rank, ctx.world_size)
-    local = run(begin, count) if count > 0 else np.zeros(1, dtype=_ffi.MOMENTS_DTYPE)
+    local = run(begin, count) if count > 0 else np.zeros(n_out, dtype=_ffi.MOMENTS_DTYPE)
     return distributed.allreduce_moments(local, ctx)
 
 
@@ -72,6 +72,29 @@ class HestonPricer:
             return price, float(runtime.discounted_std_error(m, r, T))
         return price
 
+    def price_scenarios(self, scenarios, option_type: str = "call", n_paths: int = 100000, n_steps: int = 252, seed: int = 0):
+        """Common-random-number re-pricings in ONE launch: ``scenarios`` = (S, K, T, r, v0, q) tuples, all simulated on the
+        same draws (the bumped prices compute_greeks_unified asks a Heston adapter for, unified_greeks.py:295-358)."""
+        sc = np.asarray(scenarios, dtype=np.float64).reshape(-1, 6)
+        params = np.zeros(len(sc), dtype=_ffi.HESTON_PARAMS_DTYPE)
+        params["S"], params["K"], params["T"], params["r"], params["v0"], params["q"] = sc.T
+        params["kappa"], params["theta"], params["sigma_v"], params["rho"] = self.kappa, self.theta, self.sigma_v, self.rho
+        eng = _ffi.get_engine()
+        m = _sharded(lambda b, c: eng.simulate_heston(params, option_type != "call", n_steps, int(seed), c, path_begin=b,
+                                                      shared_stream=True), int(n_paths), len(sc))
+        return [float(x) for x in runtime.discounted_price(m, sc[:, 3], sc[:, 2])]
+
+
+def _jump_scenarios(model: int, lambda_j: float, a: float, b: float, c: float, scenarios, option_type, n_paths, n_steps, seed):
+    sc = np.asarray(scenarios, dtype=np.float64).reshape(-1, 6)  # (S, K, T, r, sigma, q)
+    params = _ffi.make_params(sc[:, 0], sc[:, 1], sc[:, 2], sc[:, 3], sc[:, 4], sc[:, 5])
+    jumps = np.zeros(len(sc), dtype=_ffi.JUMP_PARAMS_DTYPE)
+    jumps["model"], jumps["lambda_j"], jumps["a"], jumps["b"], jumps["c"] = model, lambda_j, a, b, c
+    eng = _ffi.get_engine()
+    m = _sharded(lambda b_, c_: eng.simulate_jump_diffusion(params, jumps, option_type != "call", n_steps, int(seed), c_, path_begin=b_,
+                                                            shared_stream=True), int(n_paths), len(sc))
+    return [float(x) for x in runtime.discounted_price(m, sc[:, 3], sc[:, 2])]
+
 
 def _jump_price(model: int, lambda_j: float, a: float, b: float, c: float, S, K, T, r, sigma, option_type, q, n_paths, n_steps,
                 seed, return_error):
@@ -113,6 +136,10 @@ class MertonJumpDiffusion:
         return _jump_price(_ffi.JUMP_MERTON, self.lambda_j, self.mu_j, self.sigma_j, 0.0, S, K, T, r, sigma, option_type, q,
                            n_paths, n_steps, seed, return_error)
 
+    def price_scenarios(self, scenarios, option_type: str = "call", n_paths: int = 100000, n_steps: int = 252, seed: int = 0):
+        """(S, K, T, r, sigma, q) scenarios on common random numbers, one launch."""
+        return _jump_scenarios(_ffi.JUMP_MERTON, self.lambda_j, self.mu_j, self.sigma_j, 0.0, scenarios, option_type, n_paths, n_steps, seed)
+
 
 @dataclass
 class KouJumpDiffusion:
@@ -141,3 +168,7 @@ class KouJumpDiffusion:
                           n_steps: int = 252, seed: Optional[int] = None, return_error: bool = False):
         return _jump_price(_ffi.JUMP_KOU, self.lambda_j, self.p, self.eta1, self.eta2, S, K, T, r, sigma, option_type, q,
                            n_paths, n_steps, seed, return_error)
+
+    def price_scenarios(self, scenarios, option_type: str = "call", n_paths: int = 100000, n_steps: int = 252, seed: int = 0):
+        """(S, K, T, r, sigma, q) scenarios on common random numbers, one launch."""
+        return _jump_scenarios(_ffi.JUMP_KOU, self.lambda_j, self.p, self.eta1, self.eta2, scenarios, option_type, n_paths, n_steps, seed)

@@ -164,3 +164,56 @@ def test_model_constructors_validate_like_the_reference():
         ob.MertonJumpDiffusion(-1.0, 0.0, 0.1)
     with pytest.raises(ValueError):
         ob.KouJumpDiffusion(1.0, 0.4, 1.0, 5.0)
+
+
+# ---------------- bump-and-revalue Greeks of the model pricers: adapters + single-launch CRN scenarios ----------
+
+def test_model_scenarios_share_draws_and_match_separate_repricings():
+    """price_scenarios (one launch, option axis = CRN scenario axis) == the same re-pricings issued call by call
+    with the same seed; only the tile plan (hence the FP64 summation order) may differ."""
+    hes = ob.HestonPricer(kappa=2.0, theta=0.04, sigma_v=0.3, rho=-0.7, v0=0.04)
+    sc = [(100.0, 100.0, 1.0, 0.05, 0.04, 0.01), (101.0, 100.0, 1.0, 0.05, 0.04, 0.01), (100.0, 95.0, 0.5, 0.03, 0.0441, 0.0)]
+    fused = hes.price_scenarios(sc, "put", n_paths=200_000, n_steps=50, seed=9)
+    for (S, K, T, r, v0, q), got in zip(sc, fused):
+        one = ob.HestonPricer(kappa=2.0, theta=0.04, sigma_v=0.3, rho=-0.7, v0=v0).price_monte_carlo(S, K, T, r, q, "put", 200_000, 50, seed=9)
+        assert got == pytest.approx(one, rel=1e-9)
+    for pricer in (ob.MertonJumpDiffusion(**MER), ob.KouJumpDiffusion(**KOU)):
+        sj = [(100.0, 100.0, 1.0, 0.05, 0.2, 0.01), (99.0, 100.0, 1.0, 0.05, 0.21, 0.01)]
+        fused = pricer.price_scenarios(sj, "call", n_paths=200_000, n_steps=40, seed=5)
+        for (S, K, T, r, sig, q), got in zip(sj, fused):
+            assert got == pytest.approx(pricer.price_monte_carlo(S, K, T, r, sig, "call", q, 200_000, 40, seed=5), rel=1e-9)
+
+
+def test_adapter_greeks_fused_equal_call_by_call_and_approach_black_scholes():
+    """compute_greeks_unified through HestonAdapter / JumpDiffusionAdapter: the fused single-launch route equals the
+    reference's call-by-call route (same seed => same draws), and in the Black-Scholes limits of the models
+    (vol-of-vol -> 0 with v0 = theta; lambda_j = 0) delta / gamma / rho approach the closed form."""
+    bs = orc.black_scholes  # noqa: F841  (closed-form anchors below are its derivatives at S=K=100, T=1, r=5%, sigma=20%)
+    BS_DELTA, BS_GAMMA, BS_VEGA, BS_RHO = 0.6368306511756191, 0.018762017345846895, 37.52403469169379, 53.232481545376345
+
+    class CallByCall:
+        def __init__(self, inner):
+            self.inner = inner
+
+        def price(self, *a, **k):
+            return self.inner.price(*a, **k)
+
+    hes = ob.HestonPricer(kappa=1.0, theta=0.04, sigma_v=1e-3, rho=0.0, v0=0.04)
+    ad = ob.HestonAdapter(hes, n_paths=400_000, n_steps=64, seed=21)
+    g = ob.compute_greeks_unified(ad, 100.0, 100.0, 1.0, 0.05, 0.2, "call")
+    g2 = ob.compute_greeks_unified(CallByCall(ad), 100.0, 100.0, 1.0, 0.05, 0.2, "call")
+    assert list(g) == list(g2) == ["price", "delta", "gamma", "vega", "theta", "rho", "vanna", "charm", "vomma"]
+    assert g["price"] == pytest.approx(g2["price"], rel=1e-9) and g["delta"] == pytest.approx(g2["delta"], rel=1e-6)
+    assert hes.v0 == 0.04  # the adapter restores the pricer's state
+    assert g["delta"] == pytest.approx(BS_DELTA, abs=0.01) and g["gamma"] == pytest.approx(BS_GAMMA, rel=0.1)
+    assert g["rho"] == pytest.approx(BS_RHO, rel=0.03)
+    assert 0 < g["vega"] < BS_VEGA  # sigma only moves v0, which mean-reverts to theta: less than the flat-vol vega
+
+    jd = ob.JumpDiffusionAdapter(ob.MertonJumpDiffusion(0.0, -0.1, 0.15), n_paths=400_000, n_steps=32, seed=4)
+    gj = ob.greeks_jump_diffusion(ob.MertonJumpDiffusion(0.0, -0.1, 0.15), 100.0, 100.0, 1.0, 0.05, 0.2, "call", n_paths=400_000, n_steps=32, seed=4)
+    assert dict(gj) == dict(ob.compute_greeks_unified(jd, 100.0, 100.0, 1.0, 0.05, 0.2, "call"))
+    assert gj["delta"] == pytest.approx(BS_DELTA, abs=0.01) and gj["vega"] == pytest.approx(BS_VEGA, rel=0.03)
+    assert gj["rho"] == pytest.approx(BS_RHO, rel=0.03)
+    # jumps add convexity: with lambda_j > 0 the at-the-money call is worth more, its delta stays in (0, 1)
+    gm = ob.greeks_jump_diffusion(ob.MertonJumpDiffusion(**MER), 100.0, 100.0, 1.0, 0.05, 0.2, "call", n_paths=400_000, n_steps=32, seed=4)
+    assert gm["price"] > gj["price"] and 0 < gm["delta"] < 1

@@ -153,3 +153,35 @@ def test_closed_form_geometric_asian_matches_reference():
     assert ob.AsianOption(**P).price_geometric_closed_form("call") == pytest.approx(orc.asian_geometric_closed_form(**P), rel=1e-12)
     assert ob.AsianOption(**P, q=0.01).price_geometric_closed_form("put") == pytest.approx(
         orc.asian_geometric_closed_form(**P, q=0.01, option_type="put"), rel=1e-12)
+
+
+def test_model_adapters_map_arguments_like_the_reference():
+    """HestonAdapter: sigma -> v0 = sigma^2 for the call and restored afterwards (unified_greeks.py:96-101);
+    JumpDiffusionAdapter forwards (S, K, T, r, sigma, option_type, q) (unified_greeks.py:163-174).  No GPU: fake pricers."""
+    calls = []
+
+    class FakeHeston:
+        v0 = 0.09
+
+        def price_monte_carlo(self, S, K, T, r, q, option_type, n_paths, n_steps, seed=None):
+            calls.append(("mc", S, K, T, r, q, option_type, n_paths, n_steps, seed, self.v0))
+            return 1.0
+
+        def price_scenarios(self, sc, option_type, n_paths, n_steps, seed):
+            calls.append(("sc", sc, option_type, n_paths, n_steps, seed))
+            return [float(i) for i in range(len(sc))]
+
+    h = FakeHeston()
+    ad = ob.HestonAdapter(h, n_paths=123, n_steps=7, seed=5)
+    assert ad.price(100.0, 90.0, 0.5, 0.01, 0.2, "put", q=0.03) == 1.0
+    assert calls[-1] == ("mc", 100.0, 90.0, 0.5, 0.01, 0.03, "put", 123, 7, 5, pytest.approx(0.04)) and h.v0 == 0.09
+    out = ad.price_scenarios([(100.0, 90.0, 0.5, 0.01, 0.2, 0.03), (101.0, 90.0, 0.5, 0.01, 0.3, 0.03)], "call")
+    assert out == [0.0, 1.0] and calls[-1][1][1] == (101.0, 90.0, 0.5, 0.01, pytest.approx(0.09), 0.03)
+    g = ob.compute_greeks_unified(ad, 100.0, 100.0, 1.0, 0.05, 0.2, "call")  # takes the fused route: 14 scenarios, one call
+    assert calls[-1][0] == "sc" and len(calls[-1][1]) == 14 and list(g)[:3] == ["price", "delta", "gamma"]
+
+    class FakeJD:
+        def price_monte_carlo(self, S, K, T, r, sigma, option_type, q, n_paths, n_steps, seed=None):
+            return S - K + sigma + q + n_paths + n_steps + seed
+
+    assert ob.JumpDiffusionAdapter(FakeJD(), 10, 2, 1).price(100.0, 90.0, 1.0, 0.0, 0.25, "call", q=0.5) == 10 + 0.25 + 0.5 + 10 + 2 + 1
