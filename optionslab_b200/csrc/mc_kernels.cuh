@@ -199,18 +199,41 @@ __device__ __forceinline__ void step_update(float l, float& aux) {
   else aux = fmaxf(aux, l);  // BARRIER / LOOKBACK: running max of sgn*l, seeded with l_0 = 0
 }
 
-// Two consecutive steps from one pair.  The same expression shape for every NS (rc_k = rad*c_k,
-// then fma(rc_k, cos|sin, l_k + d_k)), so a scenario's result does not depend on how many other
-// scenarios share the launch: fused Greeks == separate re-pricings, bit for bit.
+// Packed FP32 pairs (Blackwell fma.rn.f32x2 / mul.rn.f32x2 -> FFMA2 / FMUL2): the two steps of a Box-Muller pair run
+// their polynomials in one instruction stream.  Same roundings as the scalar fmaf sequence, half the issue slots.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// Two consecutive steps from one pair.  Both increments come from ONE packed FFMA2, (rc*cos + d, rc*sin + d), and are
+// then added to the running log2-price in step order.  The same expression shape for every NS, so a scenario's
+// result does not depend on how many other scenarios share the launch: fused Greeks == separate re-pricings, bit for bit.
 template <int KIND, int NS>
 __device__ __forceinline__ void advance_pair(const NormalPair& p, int n_use, const Coef (&q)[NS], float (&l)[NS], float (&aux)[NS]) {
+  const f32x2 cssn = pack2(p.cs, p.sn);
 #pragma unroll
   for (int k = 0; k < NS; ++k) {
     const float rc = p.rad * q[k].c;
-    l[k] = fmaf(rc, p.cs, l[k] + q[k].d);
+    float inc0, inc1;
+    unpack2(fma2(pack2(rc, rc), cssn, pack2(q[k].d, q[k].d)), inc0, inc1);
+    l[k] += inc0;
     step_update<KIND>(l[k], aux[k]);
     if (n_use > 1) {
-      l[k] = fmaf(rc, p.sn, l[k] + q[k].d);
+      l[k] += inc1;
       step_update<KIND>(l[k], aux[k]);
     }
   }
@@ -236,26 +259,6 @@ __device__ __forceinline__ float exp2m1_small(float x) {
   t = fmaf(x, t, 2.4022650696e-1f);                                                       // ln2^2/2
   t = fmaf(x, t, 6.9314718056e-1f);                                                       // ln2
   return x * t;
-}
-
-// Packed FP32 pairs (Blackwell fma.rn.f32x2 / mul.rn.f32x2 -> FFMA2 / FMUL2): the two steps of a Box-Muller pair run
-// their polynomials in one instruction stream.  Same roundings as the scalar fmaf sequence, half the issue slots.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
 }
 
 // DEG = kSmallPacked5 (shipped): packed degree 5.  DEG = 3..5: scalar Horner forms kept for scratch/variants14.cu.

@@ -53,28 +53,47 @@ struct SobolArgs {
 //   A piecewise central/tail form (Giles) is more accurate in relative terms near z = 0 but its tail branch
 //   diverges in 19% of the warps: measured 25% slower (profiles/r01_variants13_inverse_normal.txt).
 // x in [0, 2^bits): the Sobol integer.  u = x * 2^-bits clipped to [1e-10, 1 - 1e-10] (gbm_qmc.py:36).
-__device__ __forceinline__ float inverse_normal_from_sobol(uint32_t x, uint32_t one, float scale) {
+// y = sqrt(-2 ln min(u, 1-u)) and the half u falls in.
+__device__ __forceinline__ float inverse_normal_radius(uint32_t x, uint32_t one, float scale, bool& lower) {
   const uint32_t xr = one - x;
-  const bool lower = x < xr;                                  // u < 1/2
+  lower = x < xr;                                             // u < 1/2
   const float t = fmaxf((float)(lower ? x : xr) * scale, 1e-10f);
-  const float y = mufu_sqrt(mufu_lg2(t) * -1.38629436111989061883f);  // sqrt(-2 ln t)
+  return mufu_sqrt(mufu_lg2(t) * -1.38629436111989061883f);   // sqrt(-2 ln t)
+}
+
+#define B200MC_NDTRI_HORNER(FMA, C)                                                                   \
+  p = FMA(p, v, C(3.917148571e-03f));  p = FMA(p, v, C(5.165553951e-03f));  p = FMA(p, v, C(-5.742339453e-03f)); \
+  p = FMA(p, v, C(-8.094970152e-03f)); p = FMA(p, v, C(9.645064409e-03f));  p = FMA(p, v, C(-2.167277874e-03f)); \
+  p = FMA(p, v, C(5.823089048e-03f));  p = FMA(p, v, C(-1.531743127e-02f)); p = FMA(p, v, C(2.503921833e-02f));  \
+  p = FMA(p, v, C(-4.184841491e-02f)); p = FMA(p, v, C(7.395411314e-02f));  p = FMA(p, v, C(-1.353623019e-01f)); \
+  p = FMA(p, v, C(3.068033996e+00f));  p = FMA(p, v, C(3.381260124e+00f));
+
+__device__ __forceinline__ float inverse_normal_from_sobol(uint32_t x, uint32_t one, float scale) {
+  bool lower;
+  const float y = inverse_normal_radius(x, one, scale, lower);
   const float v = fmaf(y, 3.565869380e-01f, -1.419849035e+00f);
   float p = -2.964769098e-03f;
-  p = fmaf(p, v, 3.917148571e-03f);
-  p = fmaf(p, v, 5.165553951e-03f);
-  p = fmaf(p, v, -5.742339453e-03f);
-  p = fmaf(p, v, -8.094970152e-03f);
-  p = fmaf(p, v, 9.645064409e-03f);
-  p = fmaf(p, v, -2.167277874e-03f);
-  p = fmaf(p, v, 5.823089048e-03f);
-  p = fmaf(p, v, -1.531743127e-02f);
-  p = fmaf(p, v, 2.503921833e-02f);
-  p = fmaf(p, v, -4.184841491e-02f);
-  p = fmaf(p, v, 7.395411314e-02f);
-  p = fmaf(p, v, -1.353623019e-01f);
-  p = fmaf(p, v, 3.068033996e+00f);
-  p = fmaf(p, v, 3.381260124e+00f);
+#define B200MC_ID(c) (c)
+  B200MC_NDTRI_HORNER(fmaf, B200MC_ID)
+#undef B200MC_ID
   return lower ? -p : p;
+}
+
+// Two points at once: the polynomial runs as packed FFMA2 (coefficients are FFMA2 immediates), 16 issue slots
+// for two normals instead of 30; the roundings are those of the scalar form, so both give the same bits.
+__device__ __forceinline__ void inverse_normal_from_sobol2(uint32_t x0, uint32_t x1, uint32_t one, float scale, float& z0, float& z1) {
+  bool lower0, lower1;
+  const float y0 = inverse_normal_radius(x0, one, scale, lower0);
+  const float y1 = inverse_normal_radius(x1, one, scale, lower1);
+#define B200MC_BOTH(c) pack2((c), (c))
+  const f32x2 v = fma2(pack2(y0, y1), B200MC_BOTH(3.565869380e-01f), B200MC_BOTH(-1.419849035e+00f));
+  f32x2 p = B200MC_BOTH(-2.964769098e-03f);
+  B200MC_NDTRI_HORNER(fma2, B200MC_BOTH)
+#undef B200MC_BOTH
+  float p0, p1;
+  unpack2(p, p0, p1);
+  z0 = lower0 ? -p0 : p0;
+  z1 = lower1 ? -p1 : p1;
 }
 
 struct QmcCoef {
@@ -138,10 +157,19 @@ __global__ void __launch_bounds__(kBlock, NS <= 2 ? 4 : 2) qmc_european_kernel(c
       uint32_t x = xcta_s[j];
 #pragma unroll
       for (int b = 0; b < kSobolTidBits; ++b) x ^= word[PB + b] & tid_mask[b];
+      if (kPoints == 1) {
+        W[0] += inverse_normal_from_sobol(x, one, scale);
+      } else {
 #pragma unroll
-      for (int g = 0; g < kPoints; ++g) {  // local point bits visited in Gray order: one XOR per point
-        if (g > 0) x ^= word[(g & 1) ? 0 : (g & 2) ? 1 : (g & 4) ? 2 : 3];  // lowest set bit of g
-        W[g ^ (g >> 1)] += inverse_normal_from_sobol(x, one, scale);
+        for (int g = 0; g < kPoints; g += 2) {  // local point bits visited in Gray order: one XOR per point, two points per polynomial
+          if (g > 0) x ^= word[(g & 2) ? 1 : (g & 4) ? 2 : 3];  // lowest set bit of the even g
+          const uint32_t x0 = x;
+          x ^= word[0];                                         // g + 1: lowest set bit 0
+          float z0, z1;
+          inverse_normal_from_sobol2(x0, x, one, scale, z0, z1);
+          W[g ^ (g >> 1)] += z0;
+          W[(g + 1) ^ ((g + 1) >> 1)] += z1;
+        }
       }
     }
   }
