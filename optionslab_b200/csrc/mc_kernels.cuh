@@ -134,8 +134,30 @@ __device__ __forceinline__ void for_each_pair(uint64_t path, uint32_t n_steps, u
   }
 }
 
+// Packed FP32 pairs (Blackwell fma.rn.f32x2 / mul.rn.f32x2 -> FFMA2 / FMUL2): the two steps of a Box-Muller pair run
+// their polynomials in one instruction stream.  Same roundings as the scalar fmaf sequence, half the issue slots.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // ================================ European (terminal payoff) ====================================
 // W' = sum over steps of rad*cos / rad*sin (log2-radius units); everything else happens once per path.
+// (Accumulating the two branches in the halves of one packed FFMA2 register saves 4 issue slots per 8 steps and
+// measures 0.6% slower: the European loop is not issue-bound.  profiles/r01_variants16_ffma2.txt)
 template <int UNROLL = 1>
 __device__ __forceinline__ float terminal_sum(uint64_t path, uint32_t n_steps, uint32_t stream, const PhiloxKeys& rk) {
   float W = 0.0f;
@@ -197,26 +219,6 @@ __device__ __forceinline__ void step_update(float l, float& aux) {
   if (KIND == B200MC_ASIAN_ARITH) aux += mufu_ex2(l);
   else if (KIND == B200MC_ASIAN_GEOM) aux += l;
   else aux = fmaxf(aux, l);  // BARRIER / LOOKBACK: running max of sgn*l, seeded with l_0 = 0
-}
-
-// Packed FP32 pairs (Blackwell fma.rn.f32x2 / mul.rn.f32x2 -> FFMA2 / FMUL2): the two steps of a Box-Muller pair run
-// their polynomials in one instruction stream.  Same roundings as the scalar fmaf sequence, half the issue slots.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
 }
 
 // Two consecutive steps from one pair.  Both increments come from ONE packed FFMA2, (rc*cos + d, rc*sin + d), and are
@@ -288,16 +290,16 @@ __device__ __forceinline__ void advance_pair_small(const NormalPair& p, int n_us
         aux[k] += s[k];
       }
     }
-    return;
-  }
+  } else {
 #pragma unroll
-  for (int k = 0; k < NS; ++k) {
-    const float rc = p.rad * q[k].c;
-    s[k] = fmaf(s[k], exp2m1_small<DEG>(fmaf(rc, p.cs, q[k].d)), s[k]);
-    aux[k] += s[k];
-    if (n_use > 1) {
-      s[k] = fmaf(s[k], exp2m1_small<DEG>(fmaf(rc, p.sn, q[k].d)), s[k]);
+    for (int k = 0; k < NS; ++k) {
+      const float rc = p.rad * q[k].c;
+      s[k] = fmaf(s[k], exp2m1_small<DEG>(fmaf(rc, p.cs, q[k].d)), s[k]);
       aux[k] += s[k];
+      if (n_use > 1) {
+        s[k] = fmaf(s[k], exp2m1_small<DEG>(fmaf(rc, p.sn, q[k].d)), s[k]);
+        aux[k] += s[k];
+      }
     }
   }
 }
