@@ -102,15 +102,16 @@ __device__ __forceinline__ u32x4 draw4(uint64_t path, uint32_t call, uint32_t st
 // trailing odd step.  One Philox call = 4 words = 4 pairs = 8 steps (layout documented in normal.cuh).
 // UNROLL calls are drawn before any is consumed, so their multiply chains interleave on the fmaheavy
 // pipe; which UNROLL wins depends on the consumer's register appetite (profiles/r01_variants.txt).
-template <class F>
+template <bool SQUARED, class F>
 __device__ __forceinline__ void consume_call(const u32x4& x, F&& f) {
-  f(box_muller(x.x), 2);
-  f(box_muller(x.y), 2);
-  f(box_muller(x.z), 2);
-  f(box_muller(x.w), 2);
+  f(box_muller<SQUARED>(x.x), 2);
+  f(box_muller<SQUARED>(x.y), 2);
+  f(box_muller<SQUARED>(x.z), 2);
+  f(box_muller<SQUARED>(x.w), 2);
 }
 
-template <int UNROLL = 1, class F>
+// SQUARED: the pairs carry rad^2 = -log2(u) instead of rad (see box_muller).
+template <int UNROLL = 1, bool SQUARED = false, class F>
 __device__ __forceinline__ void for_each_pair(uint64_t path, uint32_t n_steps, uint32_t stream, const PhiloxKeys& rk, F&& f) {
   const uint32_t full = n_steps >> 3;
   uint32_t j = 0;
@@ -120,22 +121,22 @@ __device__ __forceinline__ void for_each_pair(uint64_t path, uint32_t n_steps, u
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) x[u] = draw4(path, j + u, stream, rk);
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) consume_call(x[u], f);
+      for (int u = 0; u < UNROLL; ++u) consume_call<SQUARED>(x[u], f);
     }
   }
-  for (; j < full; ++j) consume_call(draw4(path, j, stream, rk), f);
+  for (; j < full; ++j) consume_call<SQUARED>(draw4(path, j, stream, rk), f);
   const int rem = (int)(n_steps & 7u);
   if (rem) {  // 1..7 trailing steps: same word layout, only the pairs that are needed
     const u32x4 x = draw4(path, full, stream, rk);
-    f(box_muller(x.x), rem >= 2 ? 2 : 1);
-    if (rem > 2) f(box_muller(x.y), rem >= 4 ? 2 : 1);
-    if (rem > 4) f(box_muller(x.z), rem >= 6 ? 2 : 1);
-    if (rem > 6) f(box_muller(x.w), 1);
+    f(box_muller<SQUARED>(x.x), rem >= 2 ? 2 : 1);
+    if (rem > 2) f(box_muller<SQUARED>(x.y), rem >= 4 ? 2 : 1);
+    if (rem > 4) f(box_muller<SQUARED>(x.z), rem >= 6 ? 2 : 1);
+    if (rem > 6) f(box_muller<SQUARED>(x.w), 1);
   }
 }
 
-// Packed FP32 pairs (Blackwell fma.rn.f32x2 / mul.rn.f32x2 -> FFMA2 / FMUL2): the two steps of a Box-Muller pair run
-// their polynomials in one instruction stream.  Same roundings as the scalar fmaf sequence, half the issue slots.
+// Packed FP32 pairs (Blackwell fma.rn.f32x2 / mul.rn.f32x2 -> FFMA2 / FMUL2): two FP32 FMAs per issue slot, with the
+// roundings of the scalar fmaf sequence.  Operands whose halves are equal compile to FFMA2 immediates / broadcasts.
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
   f32x2 r;

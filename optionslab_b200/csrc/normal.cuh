@@ -70,10 +70,13 @@ struct NormalPair {
   float rad, cs, sn;
 };
 
+// SQUARED = true leaves rad = -log2(u), the squared radius, for callers that fold another factor under the same
+// square root (Heston: sqrt(v) * rad = sqrt(v * rad^2) is one MUFU.SQRT instead of two).
+template <bool SQUARED = false>
 __device__ __forceinline__ NormalPair box_muller(uint32_t w) {
   NormalPair p;
   const float u = 2.0f - __uint_as_float((w >> 9) | 0x3f800000u);
-  p.rad = mufu_sqrt(-mufu_lg2(u));
+  p.rad = SQUARED ? -mufu_lg2(u) : mufu_sqrt(-mufu_lg2(u));
   const float turns = __uint_as_float((__byte_perm(w, 0u, 0x0123) >> 9) | 0x3f800000u);
   const float theta = fmaf(turns, kTwoPi, kMinusThreePi);
   p.cs = mufu_cos(theta);
