@@ -58,3 +58,61 @@ def test_unsharded_allreduce_is_identity():
     distributed.shutdown()
     m = _moments_for_range(0, 100)
     assert distributed.allreduce_moments(m) is m
+
+
+# ---- the pricer classes themselves under world_size 2 (host logic of the N > 1 path, no GPU) ---------------------
+class _OracleEngine:
+    """Stands in for _ffi.Engine on the CPU: same simulate() contract (global path range in, MOMENTS out), computed
+    by the FP64 oracle evaluation of the engine's own Philox stream.  Test infrastructure only."""
+
+    def simulate(self, spec, params, seed, n_paths, *, stream_base=0, path_begin=0, control_variate=False):
+        params = np.asarray(params)
+        out = np.zeros(params.shape, dtype=_ffi.MOMENTS_DTYPE)
+        for opt in range(params.shape[0]):
+            Z = philox_oracle.normals(seed, n_paths, spec.n_steps, stream=stream_base + opt, path_begin=path_begin)
+            for k in range(params.shape[1]):
+                p = params[opt, k]
+                ot = "put" if spec.is_put else "call"
+                if spec.kind == _ffi.EUROPEAN:
+                    st = orc.gbm_terminal_from_normals(p["S"], p["T"], p["r"], p["sigma"], p["q"], Z)  # antithetic: 2N terminals
+                    pay = orc.vanilla_payoffs(st if spec.antithetic else st[: len(Z)], p["K"], ot)
+                else:
+                    paths = orc.exotic_paths_from_normals(p["S"], p["T"], p["r"], p["sigma"], p["q"], Z)
+                    pay = orc.asian_payoffs(paths, p["K"], "arithmetic", ot)
+                out[opt, k] = (pay.sum(), (pay**2).sum(), len(pay))
+        return out
+
+
+def _price_everything():
+    import optionslab_b200 as ob
+
+    pr = ob.MonteCarloPricer(N_PATHS, N_STEPS, seed=SEED)
+    res = pr.price(**P, option_type="put", return_error=True)
+    greeks = pr.greeks(**P, option_type="call", include_second_order=False)
+    grid = ob.MonteCarloPricerUni(N_PATHS, N_STEPS, seed=SEED).price_batch([100.0, 101.0], [105.0, 95.0], 0.5, 0.03, 0.25, "call")
+    asian = ob.AsianOption(**P, seed=SEED).price(n_paths=N_PATHS, n_steps=N_STEPS, return_error=True)
+    return np.array([res.price, res.std_error, res.n_paths, greeks["delta"], greeks["vega"], grid[0], grid[1], asian.price, asian.n_paths])
+
+
+def _pricer_worker(rank, world, port, out_dir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    _ffi.get_engine = lambda device=None: _OracleEngine()
+    distributed.init(backend="gloo")
+    np.save(os.path.join(out_dir, f"pricers{rank}.npy"), _price_everything())
+    distributed.shutdown()
+
+
+def test_pricer_classes_shard_paths_and_allreduce(tmp_path, monkeypatch):
+    """MonteCarloPricer / MonteCarloPricerUni.price_batch / AsianOption on 2 ranks == 1 process: every rank simulates
+    its slice of the global path range (runtime.simulate) and the all-reduced moments give identical prices, Greeks,
+    standard errors and sample counts on all ranks."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_pricer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    distributed.shutdown()
+    monkeypatch.setattr(_ffi, "get_engine", lambda device=None: _OracleEngine())
+    whole = _price_everything()
+    for rank in range(2):
+        np.testing.assert_allclose(np.load(os.path.join(tmp_path, f"pricers{rank}.npy")), whole, rtol=1e-12)
+    assert whole[2] == 2 * N_PATHS and whole[8] == N_PATHS  # antithetic European counts 2N samples, the Asian N
