@@ -345,9 +345,10 @@ def run_engine_arm(args):
             "imad_frac": kernel_rate * IMAD_PER_STEP / peaks["imad_wide_per_s"],
             "alu_frac": kernel_rate * LOP_PER_STEP / peaks["lop3_per_s"],
             "vs_rng_only_probe": kernel_rate / peaks["normals_per_s"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size from the ncu --set full capture
-            # (profiles/r01_ncu_european.txt: 2.59 MB read + 20.81 MB written); algorithmic: 262 KB in + 8.06 MB partials out
-            "traffic": 23.4e6 / world if world >= 1 else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size (N=1) from the ncu --set full capture
+            # (profiles/r01_ncu_european.txt: 369 KB read, 0 B written - the 8 MB of tile partials are still in the 126 MB
+            # L2 when the launch ends and are consumed there by fold_kernel); algorithmic: 262 KB in + 98 KB moments out
+            "traffic": 368640.0 if world == 1 else None,
             "hbm": {"achieved_gbs": hbm_bytes / kernel_s / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
                     "frac": hbm_bytes / kernel_s / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": hbm_bytes},
             "pipe_peaks": peaks,

@@ -94,6 +94,10 @@ def main():
            lambda: prq.price(**P, option_type="call"),
            lambda: orc.european_price_qmc(**P, option_type="call", num_simulations=1 << 16, num_steps=252, seed=42).price, (1 << 16) * 252,
            note="CPU oracle (scipy Sobol + norm.ppf) at 2^16 points; api_ms includes building scipy's direction table on the host")
+    # the same at 2^24 points: enough CTAs (4096) to fill the machine; the reference's (N, d) arrays would take 2 x 34 GB
+    prq24 = ob.MonteCarloPricer(1 << 24, 252, seed=42, method=ob.MCMethod.QMC)
+    record("QMC European call 2^24 Sobol points x 252", "qmc", (1 << 24) * 252, (1 << 24) * 252,
+           lambda: prq24.price(**P, option_type="call"), lambda: None, 1, note="no CPU leg at this size")
     # Heston full-truncation Euler and Merton jump diffusion, 4M paths x 252 steps
     hes = ob.HestonPricer(kappa=2.0, theta=0.04, sigma_v=0.3, rho=-0.7, v0=0.04)
     record("Heston European call 4M x 252", "heston", 4_000_000 * 252, 4_000_000 * 252,
