@@ -173,3 +173,23 @@ def test_parity_mode_argument_errors(engine):
         engine.payoffs_from_normals(spec, _ffi.make_params(**P), np.zeros((8, 4)))
     with pytest.raises(MonteCarloError):
         engine.payoffs_from_normals(_ffi.make_spec(_ffi.EUROPEAN, 4), _ffi.make_params(**P), np.zeros((8, 5)))
+
+
+@pytest.mark.parametrize("n_steps", [2, 30, 32, 34, 64, 96, 250])
+@pytest.mark.parametrize("n_paths", [1, 31, 129, 4097, 50_000])
+def test_bulk_async_staged_kernel_equals_plain_load_kernel_bitwise(engine, n_paths, n_steps):
+    """european_from_normals_tma_kernel (cp.async.bulk + mbarrier ring, taken for even n_steps) and from_normals_kernel
+    (flag NO_BULK_COPY) run the same FP64 statement sequence: identical payoffs and moments, bit for bit — partial
+    warps, partial last chunks (n_steps % 32 != 0), fewer chunks than ring stages, both summation forms."""
+    Z = orc.normals_generator(7, (n_paths, n_steps))
+    p = _ffi.make_params(**P, q=0.02)
+    for accumulate in (False, True):
+        for anti in (True, False):
+            a_pay, a_mom = engine.payoffs_from_normals(_ffi.make_spec(_ffi.EUROPEAN, n_steps, antithetic=anti), p, Z, accumulate=accumulate)
+            b_pay, b_mom = engine.payoffs_from_normals(_ffi.make_spec(_ffi.EUROPEAN, n_steps, antithetic=anti, no_bulk_copy=True), p, Z,
+                                                       accumulate=accumulate)
+            assert np.array_equal(a_pay, b_pay)
+            assert a_mom["sum"] == b_mom["sum"] and a_mom["sum_sq"] == b_mom["sum_sq"] and a_mom["n"] == b_mom["n"] == n_paths * (2 if anti else 1)
+    terminal = orc.gbm_terminal_from_normals(P["S"], P["T"], P["r"], P["sigma"], 0.02, Z)
+    got, _ = engine.payoffs_from_normals(_ffi.make_spec(_ffi.EUROPEAN, n_steps, antithetic=True), p, Z)
+    _check(got, orc.vanilla_payoffs(terminal, P["K"], "call"), np.maximum(terminal, P["K"]))
