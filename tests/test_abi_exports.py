@@ -74,3 +74,28 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "oracle/" not in text or f.endswith((".cuh", ".cu")), f
+
+
+def test_header_is_plain_c_and_a_c_client_links():
+    """include/b200mc.h must be consumable from C (the boundary is extern "C", plain pointers and sizes): compile it as
+    strict C99 and link a tiny C client against libb200mc.so that only calls b200mc_abi_version() (no device needed)."""
+    import shutil
+    import subprocess
+    import tempfile
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    header = os.path.join(ROOT, "include", "b200mc.h")
+    subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", header], check=True)
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "client.c")
+        with open(src, "w") as f:
+            f.write('#include "b200mc.h"\n#include <stdio.h>\nint main(void) { b200mc_spec_t s = {0}; s.flags = B200MC_FLAG_EXACT_EX2;\n'
+                    '  printf("%d %u\\n", b200mc_abi_version(), (unsigned)sizeof(b200mc_params_t) + s.flags); return 0; }\n')
+        exe = os.path.join(d, "client")
+        libdir = os.path.dirname(_ffi.LIB_PATH)
+        subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", libdir, "-l:libb200mc.so",
+                        f"-Wl,-rpath,{libdir}"], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+        assert out == [str(_ffi.ABI_VERSION), "65"]
