@@ -187,7 +187,11 @@ def run_engine_arm(args):
     torch.cuda.set_device(local)
     import torch.distributed as dist
 
-    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    # rank 0 prints ONE JSON line on stdout: while the job runs, file descriptor 1 points at stderr, so that library
+    # chatter written straight to fd 1 (NCCL's version banner) cannot land in front of the JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ctx = distributed.init(backend="nccl") if world > 1 else None
     eng = _ffi.get_engine(local)
     dev = torch.device("cuda", local)
@@ -388,9 +392,13 @@ def run_engine_arm(args):
                                    "argmax_all": {"K": float(g["K"][i_max]), "T": float(g["T"][i_max]), "price": float(dev_prices[i_max]),
                                                   "bs": float(bs[i_max]), "se": float(se[i_max])}},
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if ctx is not None:
         distributed.shutdown()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
     return 0
 
 
