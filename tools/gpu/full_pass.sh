@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU pass: parity tests, smoke, bench, per-config numbers, ncu launch list + full captures.
+# Full GPU pass (tools/gpu/full_pass.sh): parity tests, smoke, bench, per-config numbers, ncu launch list + full captures.
 # ncu reports are summarised ON the box (tools/ncu_summary.py) and only the European one travels back:
 # gpurun refuses to copy more than 64 MiB of gpurun_out/.
 mkdir -p gpurun_out
