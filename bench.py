@@ -41,7 +41,7 @@ WORKLOAD = (f"C5: {N_OPT}-option European call grid ({N_STRIKES} strikes 60..140
 # with cuobjdump — profiles/r01_sass_european.txt): 88 issued instructions per Philox call = 8 path-steps, of which
 # 16 MUFU, 16 IMAD.WIDE (fmaheavy pipe), 18 LOP3 + 8 LEA.HI + 4 PRMT (ALU pipe).
 INSTR_PER_STEP, MUFU_PER_STEP, IMAD_PER_STEP, LOP_PER_STEP = 87 / 8, 2.0, 2.0, 30 / 8
-IMAD_WIDE_DISPATCH_CYCLES = 4.36  # scratch/variants15.cu: 16 IMAD.WIDE (+ their XORs) per warp take 69.7 SMSP cycles
+IMAD_WIDE_DISPATCH_CYCLES = 4.0  # scratch/variants15.cu: 16 IMAD.WIDE / IMAD.HI (+ XORs, loop) per warp take 69.7 / 66.0 SMSP cycles; charged 4
 ASIAN_INSTR_PER_STEP = 123 / 8  # pathdep_kernel<ASIAN_ARITH,1> small-move loop (tools/sass_loop.py --all): 20 FFMA2 + 4 FMUL2 + 32 FP32, 16 MUFU per 8 steps
 
 
@@ -351,7 +351,7 @@ def run_engine_arm(args):
             "alu_frac": kernel_rate * LOP_PER_STEP / peaks["lop3_per_s"],
             "vs_rng_only_probe": kernel_rate / peaks["normals_per_s"],
             # dispatch-port view (profiles/r01_variants15_fma_pipe_model.txt): an IMAD.WIDE holds an SMSP's dispatch port for
-            # 4.36 cycles (measured), every other instruction for 1; fraction of the measured issue peak under that weighting
+            # ~4 cycles (measured 4.1-4.4 including loop overhead), every other instruction for 1; fraction of the measured issue peak under that weighting
             "dispatch_frac": kernel_rate * (INSTR_PER_STEP + IMAD_PER_STEP * (IMAD_WIDE_DISPATCH_CYCLES - 1.0)) / peaks["issue_per_s"],
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size (N=1) from the ncu --set full capture
             # (profiles/r01_ncu_european.txt: 369 KB read, 0 B written - the 8 MB of tile partials are still in the 126 MB
