@@ -52,3 +52,33 @@ def test_device_normals_ks_and_pair_independence(engine):
     assert abs(np.corrcoef(zz[:, 0] ** 2, zz[:, 1] ** 2)[0, 1]) < 4 / np.sqrt(n)
     assert abs(np.corrcoef(zz[:, 1], zz[:, 2])[0, 1]) < 4 / np.sqrt(n)
     assert abs(np.corrcoef(zz[:-1, 7], zz[1:, 0])[0, 1]) < 4 / np.sqrt(n)
+
+
+def test_streams_and_neighbouring_paths_are_uncorrelated(engine):
+    """Disjoint Philox counters must give independent draws: the same (path, step) cells of streams s and s+1 (two
+    options of a batch), of path blocks one apart (two GPUs of a sharded run) and of seeds differing in one bit are
+    uncorrelated, in the values and in their squares; lagged steps within a path likewise (lags 1..9 cross the
+    cosine/sine branch of a pair, the 4 pairs of a Philox call and the call boundary)."""
+    n_paths, n_steps, seed = 1 << 18, 32, 99
+    n = n_paths * n_steps
+    lim = 4.5 / np.sqrt(n)
+    base = engine.generate_normals(seed, n_paths, n_steps, stream=3).astype(np.float64)
+    others = {
+        "next stream": engine.generate_normals(seed, n_paths, n_steps, stream=4),
+        "next path block": engine.generate_normals(seed, n_paths, n_steps, stream=3, path_begin=n_paths),
+        "seed ^ 1": engine.generate_normals(seed ^ 1, n_paths, n_steps, stream=3),
+        "seed ^ 2^32": engine.generate_normals(seed ^ (1 << 32), n_paths, n_steps, stream=3),
+    }
+    a = base.ravel()
+    for name, other in others.items():
+        b = other.astype(np.float64).ravel()
+        assert abs(np.mean(a * b)) < lim, name
+        assert abs(np.mean((a * a - 1) * (b * b - 1))) < 2 * lim, name  # var of (z^2-1)(z'^2-1) is 4
+        assert np.max(np.abs(a - b)) > 1.0, name
+    for lag in range(1, 10):
+        x, y = base[:, :-lag].ravel(), base[:, lag:].ravel()
+        assert abs(np.mean(x * y)) < 4.5 / np.sqrt(x.size), lag
+        assert abs(np.mean((x * x - 1) * (y * y - 1))) < 9.0 / np.sqrt(x.size), lag
+    # neighbouring paths of one stream (adjacent threads of a warp)
+    x, y = base[:-1].ravel(), base[1:].ravel()
+    assert abs(np.mean(x * y)) < 4.5 / np.sqrt(x.size)

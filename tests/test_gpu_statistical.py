@@ -287,3 +287,26 @@ def test_config5_grid_z_scores_are_standard_normal_where_the_clt_applies(engine)
     assert abs(z.mean()) < 4.0 / np.sqrt(z.size), z.mean()
     assert 0.5 < z.std() < 1.08, z.std()
     assert np.max(np.abs(z)) < 4.75, np.max(np.abs(z))
+
+
+def test_martingale_and_variance_of_the_terminal_spot_over_maturities_and_step_counts(engine):
+    """E[S_T] = S e^{(r-q)T} and Var[ln S_T] = sigma^2 T for every maturity and for step counts that are not multiples of the
+    8-step Philox block: a call struck at ~0 prices the discounted forward (first moment), and the control-variate
+    moments give Var[S_T] = F^2 (e^{sigma^2 T} - 1) (second moment) - both within 4 standard errors, 40 cases."""
+    n = 2_000_000
+    for n_steps in (1, 7, 12, 252, 365):
+        T = np.linspace(0.25, 2.0, 8)
+        S, r, q, sigma = 100.0, 0.05, 0.015, 0.3
+        params = _ffi.make_params(S, 1e-9, T, r, sigma, q).reshape(len(T), 1)
+        m = engine.simulate(_ffi.make_spec(_ffi.EUROPEAN, n_steps, antithetic=False), params, 77, n, control_variate=True)[:, 0]
+        fwd = S * np.exp((r - q) * T)
+        mean = m["sum_terminal"] / m["n"]
+        var = m["sum_terminal_sq"] / m["n"] - mean**2
+        se = np.sqrt(var / m["n"])
+        assert np.all(np.abs(mean - fwd) < 4 * se), (n_steps, (mean - fwd) / se)
+        want_var = fwd**2 * (np.exp(sigma**2 * T) - 1)
+        # std error of a sample variance of a lognormal: sqrt((mu4 - var^2)/n); bound mu4 by the lognormal's fourth central moment
+        w = np.exp(sigma**2 * T)
+        mu4 = fwd**4 * (w - 1) ** 2 * (w**4 + 2 * w**3 + 3 * w**2 - 3)
+        assert np.all(np.abs(var - want_var) < 4.5 * np.sqrt((mu4 - want_var**2) / m["n"])), (n_steps, var / want_var)
+        assert np.allclose(m["sum_payoff"], m["sum_terminal"], rtol=1e-6)  # K ~ 0: the payoff is the terminal spot
