@@ -305,9 +305,56 @@ def lookback_payoffs(paths, K, lookback_type="floating", option_type="call") -> 
     return np.maximum(K - S_min, 0)
 
 
+def autocallable_payoffs(paths, S, T, r, autocall_barrier=1.0, coupon_barrier=0.8, coupon_rate=0.10, ki_barrier=0.6,
+                         observation_freq=21) -> np.ndarray:
+    """ALREADY DISCOUNTED per-path payoffs (fraction of notional) of AutocallableOption.price,
+    src/pricing_models/exotic_options.py:438-488: early redemption at the first observation with S_t/S >= autocall
+    barrier pays (1 + coupon_rate * (i+1)/n_obs * T) * exp(-r t dt); otherwise 1 (+ coupon_rate*T above the coupon
+    barrier) at maturity, replaced by S_T/S when the path minimum (t = 0 included) touched the knock-in barrier and
+    S_T < S; discounted with exp(-rT).  The price is the plain mean of these."""
+    n_paths, n_cols = paths.shape
+    n_steps = n_cols - 1
+    dt = T / n_steps
+    obs_times = list(range(observation_freq, n_steps + 1, observation_freq))
+    n_obs = len(obs_times)
+    payoffs = np.zeros(n_paths)
+    redeemed = np.zeros(n_paths, dtype=bool)
+    knocked_in = np.min(paths / S, axis=1) <= ki_barrier
+    for i, t in enumerate(obs_times):
+        active = ~redeemed
+        S_rel = paths[active, t] / S
+        idx = np.where(active)[0][S_rel >= autocall_barrier]
+        coupon = coupon_rate * ((i + 1) / n_obs) * T
+        payoffs[idx] = (1 + coupon) * np.exp(-r * t * dt)
+        redeemed[idx] = True
+    still = ~redeemed
+    S_rel_final = paths[still, -1] / S
+    final = np.ones(int(np.sum(still)))
+    final[S_rel_final >= coupon_barrier] += coupon_rate * T
+    loss = knocked_in[still] & (S_rel_final < 1.0)
+    final[loss] = S_rel_final[loss]
+    payoffs[still] = final * np.exp(-r * T)
+    return payoffs
+
+
+def cliquet_payoffs(paths, S, local_cap=0.05, local_floor=-0.05, global_cap=0.30, global_floor=0.0, n_periods=12) -> np.ndarray:
+    """UNDISCOUNTED per-path payoffs of CliquetOption.price, src/pricing_models/exotic_options.py:525-552: sum over
+    n_periods reset periods of n_steps // n_periods steps of the locally clipped simple returns, clipped globally,
+    floored at 0, times S.  (Steps beyond n_periods * (n_steps // n_periods) are simulated and ignored.)"""
+    n_paths, n_cols = paths.shape
+    n_steps = n_cols - 1
+    spp = n_steps // n_periods
+    total = np.zeros(n_paths)
+    for p in range(n_periods):
+        S_start, S_end = paths[:, p * spp], paths[:, (p + 1) * spp]
+        total += np.clip((S_end - S_start) / S_start, local_floor, local_cap)
+    total = np.clip(total, global_floor, global_cap)
+    return np.maximum(total, 0) * S
+
+
 def exotic_price(kind, S, K, T, r, sigma, q=0.0, *, seed, n_paths, n_steps, option_type="call",
                  avg_type="arithmetic", barrier=0.0, barrier_type="up-and-out",
-                 lookback_type="floating", return_payoffs=False):
+                 lookback_type="floating", return_payoffs=False, **product):
     """``AsianOption/BarrierOption/LookbackOption(...).price(n_paths, n_steps, ...)``.
 
     src/pricing_models/exotic_options.py:97-131, :174-224, :368-401.  Chunk-free:
@@ -323,6 +370,12 @@ def exotic_price(kind, S, K, T, r, sigma, q=0.0, *, seed, n_paths, n_steps, opti
         pay = barrier_payoffs(paths, K, barrier, barrier_type, option_type)
     elif kind == "lookback":
         pay = lookback_payoffs(paths, K, lookback_type, option_type)
+    elif kind == "cliquet":
+        pay = cliquet_payoffs(paths, S, **product)
+    elif kind == "autocallable":  # discounting happens per path, inside the payoffs (exotic_options.py:466,486-488)
+        pay = autocallable_payoffs(paths, S, T, r, **product)
+        price = np.mean(pay)
+        return (price, pay) if return_payoffs else price
     else:
         raise ValueError(kind)
     price = np.exp(-r * T) * np.mean(pay)

@@ -38,7 +38,7 @@ def import_reference():
         sys.path.insert(0, REFERENCE_ROOT)
     from src.greeks.unified_greeks import ExoticAdapter, compute_greeks_unified
     from src.pricing_models.black_scholes import black_scholes
-    from src.pricing_models.exotic_options import AsianOption, BarrierOption, LookbackOption
+    from src.pricing_models.exotic_options import AsianOption, AutocallableOption, BarrierOption, CliquetOption, LookbackOption
     from src.pricing_models.heston import HestonPricer
     from src.pricing_models.jump_diffusion import KouJumpDiffusion, MertonJumpDiffusion
     from src.pricing_models.monte_carlo import MCMethod, MonteCarloPricer
@@ -46,6 +46,7 @@ def import_reference():
 
     return dict(HestonPricer=HestonPricer, MertonJumpDiffusion=MertonJumpDiffusion, KouJumpDiffusion=KouJumpDiffusion, MCMethod=MCMethod, MonteCarloPricer=MonteCarloPricer, MonteCarloPricerUni=MonteCarloPricerUni,
                 AsianOption=AsianOption, BarrierOption=BarrierOption, LookbackOption=LookbackOption,
+                AutocallableOption=AutocallableOption, CliquetOption=CliquetOption,
                 compute_greeks_unified=compute_greeks_unified, ExoticAdapter=ExoticAdapter,
                 black_scholes=black_scholes)
 
@@ -155,6 +156,22 @@ def main():
     out = ref["compute_greeks_unified"](ad, **P, option_type="call")
     ex["asian_adapter_greeks_20000x32"] = {k: float(v) for k, v in out.items()}
     g["exotics"] = ex
+
+    # --- structured products of the same file (exotic_options.py:404-552): autocallable and cliquet ----------------
+    sp = {}
+    for n_paths, n_steps, freq, nper in [(100000, 252, 21, 12), (5000, 12, 3, 4), (20000, 100, 7, 9), (4097, 37, 37, 37)]:
+        tag = f"{n_paths}x{n_steps}"
+        sp[f"autocallable_default_{tag}_f{freq}"] = float(ref["AutocallableOption"](**P, seed=42).price(n_paths, n_steps, freq))
+        sp[f"autocallable_tight_{tag}_f{freq}"] = float(ref["AutocallableOption"](
+            **P, seed=42, autocall_barrier=1.05, coupon_barrier=0.9, coupon_rate=0.08, ki_barrier=0.75).price(n_paths, n_steps, freq))
+        sp[f"cliquet_default_{tag}_p{nper}"] = float(ref["CliquetOption"](**P, seed=42).price(n_paths, n_steps, nper))
+        sp[f"cliquet_wide_{tag}_p{nper}"] = float(ref["CliquetOption"](
+            **P, seed=42, local_cap=0.08, local_floor=-0.03, global_cap=0.5, global_floor=-0.1).price(n_paths, n_steps, nper))
+    sp["autocallable_q_sigma_20000x64_f8"] = float(ref["AutocallableOption"](105.0, 100.0, 1.5, 0.03, 0.35, 0.02, seed=7).price(20000, 64, 8))
+    sp["cliquet_q_sigma_20000x64_p8"] = float(ref["CliquetOption"](105.0, 100.0, 1.5, 0.03, 0.35, 0.02, seed=7).price(20000, 64, 8))
+    ad = ref["ExoticAdapter"](ref["CliquetOption"](**P, seed=42), n_paths=20000, n_steps=36)
+    sp["cliquet_adapter_greeks_20000x36"] = {k: float(v) for k, v in ref["compute_greeks_unified"](ad, **P, option_type="call", n_periods=6).items()}
+    g["structured"] = sp
 
     # --- Heston / Merton / Kou Monte Carlo (heston.py:184-255, jump_diffusion.py:160-225, :325-377) ------------
     import warnings

@@ -215,3 +215,39 @@ def test_jump_diffusion_mc_matches_reference(goldens, n_paths, n_steps, ot):
     assert got == pytest.approx(goldens["models"][f"merton_{ot}_{n_paths}x{n_steps}"], rel=REL)
     got = orc.kou_price_mc(100.0, 100.0, 1.0, 0.05, 0.2, ot, 0.01, **KOU, **kw)
     assert got == pytest.approx(goldens["models"][f"kou_{ot}_{n_paths}x{n_steps}"], rel=REL)
+
+
+TIGHT_AUTOCALL = dict(autocall_barrier=1.05, coupon_barrier=0.9, coupon_rate=0.08, ki_barrier=0.75)
+WIDE_CLIQUET = dict(local_cap=0.08, local_floor=-0.03, global_cap=0.5, global_floor=-0.1)
+STRUCTURED_CASES = [(100000, 252, 21, 12), (5000, 12, 3, 4), (20000, 100, 7, 9), (4097, 37, 37, 37)]
+
+
+@pytest.mark.parametrize("n_paths,n_steps,freq,nper", STRUCTURED_CASES)
+def test_autocallable_and_cliquet_match_reference(goldens, n_paths, n_steps, freq, nper):
+    """exotic_options.py:404-552 restated (autocallable_payoffs / cliquet_payoffs) vs the real classes."""
+    if not _same_numpy(goldens):
+        pytest.skip("goldens recorded with another NumPy build")
+    sp, tag = goldens["structured"], f"{n_paths}x{n_steps}"
+    kw = dict(seed=42, n_paths=n_paths, n_steps=n_steps)
+    assert orc.exotic_price("autocallable", **P, **kw, observation_freq=freq) == pytest.approx(sp[f"autocallable_default_{tag}_f{freq}"], rel=REL)
+    assert orc.exotic_price("autocallable", **P, **kw, observation_freq=freq, **TIGHT_AUTOCALL) == pytest.approx(
+        sp[f"autocallable_tight_{tag}_f{freq}"], rel=REL)
+    assert orc.exotic_price("cliquet", **P, **kw, n_periods=nper) == pytest.approx(sp[f"cliquet_default_{tag}_p{nper}"], rel=REL)
+    assert orc.exotic_price("cliquet", **P, **kw, n_periods=nper, **WIDE_CLIQUET) == pytest.approx(sp[f"cliquet_wide_{tag}_p{nper}"], rel=REL)
+
+
+def test_structured_products_with_dividend_and_adapter_greeks(goldens):
+    if not _same_numpy(goldens):
+        pytest.skip("goldens recorded with another NumPy build")
+    sp = goldens["structured"]
+    kw = dict(seed=7, n_paths=20000, n_steps=64)
+    assert orc.exotic_price("autocallable", 105.0, 100.0, 1.5, 0.03, 0.35, 0.02, **kw, observation_freq=8) == pytest.approx(
+        sp["autocallable_q_sigma_20000x64_f8"], rel=REL)
+    assert orc.exotic_price("cliquet", 105.0, 100.0, 1.5, 0.03, 0.35, 0.02, **kw, n_periods=8) == pytest.approx(sp["cliquet_q_sigma_20000x64_p8"], rel=REL)
+
+    def fn(S, K, T, r, sigma, q):
+        return orc.exotic_price("cliquet", S, K, T, r, sigma, q, seed=42, n_paths=20000, n_steps=36, n_periods=6)
+
+    out = orc.greeks_bump_and_revalue(fn, **P)
+    for k, v in sp["cliquet_adapter_greeks_20000x36"].items():
+        assert out[k] == pytest.approx(v, rel=1e-8, abs=1e-8), k
