@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200MC_ABI_VERSION 3
+#define B200MC_ABI_VERSION 4
 #define B200MC_MAX_SCENARIOS 16
 
 typedef struct b200mc_engine b200mc_engine_t;
@@ -40,7 +40,10 @@ typedef enum {
   B200MC_ASIAN_ARITH = 1, /* mean of S_t, t=1..n;  src/pricing_models/exotic_options.py:119-120 */
   B200MC_ASIAN_GEOM = 2,  /* exp(mean(log S_t));   src/pricing_models/exotic_options.py:121-122 */
   B200MC_BARRIER = 3,     /* any(S_t >= B) / any(S_t <= B), t=0..n;  exotic_options.py:201-212 */
-  B200MC_LOOKBACK = 4     /* running max / min, t=0..n;  exotic_options.py:382-399 */
+  B200MC_LOOKBACK = 4,    /* running max / min, t=0..n;  exotic_options.py:382-399 */
+  /* structured products of the same file; only b200mc_simulate_structured / b200mc_structured_from_normals take them */
+  B200MC_CLIQUET = 5,     /* sum of locally clipped period returns, clipped globally;  exotic_options.py:525-552 */
+  B200MC_AUTOCALLABLE = 6 /* early redemption on observation dates, coupon, knock-in put;  exotic_options.py:438-488 */
 } b200mc_kind;
 
 /* ASIAN_ARITH: always evaluate S_t = S_0 * 2^(l_t) with MUFU.EX2 instead of the multiplicative
@@ -68,6 +71,18 @@ typedef struct {
   double barrier; /* BARRIER only */
   double reserved;
 } b200mc_params_t;
+
+/* Terms of a structured product (dataclass fields of CliquetOption / AutocallableOption plus the schedule argument of
+ * their price methods, exotic_options.py:416-427, :502-513).  One product per launch, shared by all options / scenarios.
+ *   B200MC_CLIQUET      : a = local_cap, b = local_floor, c = global_cap, d = global_floor, period = n_periods
+ *                         (each period spans n_steps / n_periods steps, integer division; later steps are ignored)
+ *   B200MC_AUTOCALLABLE : a = autocall_barrier, b = coupon_barrier, c = coupon_rate, d = ki_barrier (all relative to S),
+ *                         period = observation_freq (an observation every `period` steps, the first at step `period`) */
+typedef struct {
+  double a, b, c, d;
+  uint32_t period;
+  uint32_t reserved;
+} b200mc_product_t;
 
 /* Raw FP64 payoff moments of one (option, scenario): sum over samples of the UNDISCOUNTED payoff,
  * of its square, and the sample count (2x paths when antithetic).  The host applies exp(-rT), the
@@ -217,6 +232,25 @@ int b200mc_heston_from_normals(b200mc_engine_t* eng, const b200mc_heston_params_
 int b200mc_jump_diffusion_from_draws(b200mc_engine_t* eng, const b200mc_params_t* p, double lambda_kappa, int is_put,
                                      uint32_t n_steps, const double* dW_host, const double* J_host, uint64_t n_paths,
                                      double* payoffs_host, b200mc_moments_t* out_host);
+
+/* ---- structured products (exotic_options.py:404-552) ------------------------------------------------------------- *
+ * Same fused path as b200mc_simulate (Philox normals in registers, log-Euler steps, payoff, FP64 moments, scenarios on
+ * common random numbers), with the period / observation schedule counted down in registers.
+ *   B200MC_CLIQUET      : out = moments of the UNDISCOUNTED payoff max(clip(sum_p clip(R_p)), 0) * S; the host applies
+ *                         exp(-rT) (exotic_options.py:552).
+ *   B200MC_AUTOCALLABLE : out = moments of the DISCOUNTED payoff per unit notional - redemption at observation i pays
+ *                         (1 + c*(i/n_obs)*T) * exp(-r t_i), maturity pays exp(-rT) * {1 (+ c*T above the coupon barrier),
+ *                         or S_T/S after a knock-in with S_T < S}; the price is sum / n (exotic_options.py:466,486-488).
+ * spec: kind = B200MC_CLIQUET or B200MC_AUTOCALLABLE, n_steps; the other fields are ignored.  K is unused. */
+int b200mc_simulate_structured(b200mc_engine_t* eng, const b200mc_spec_t* spec, const b200mc_product_t* product,
+                               const b200mc_params_t* params_host, uint32_t n_opt, uint32_t n_scen, uint64_t seed,
+                               uint32_t stream_base, uint64_t path_begin, uint64_t n_paths, b200mc_moments_t* out_host);
+/* The same two products in FP64 on caller-supplied draws Z [n_paths][n_steps] (the reference's own normals,
+ * exotic_options.py:59), statement by statement as the reference evaluates them.  payoffs (may be NULL) and out follow
+ * the conventions above. */
+int b200mc_structured_from_normals(b200mc_engine_t* eng, const b200mc_spec_t* spec, const b200mc_product_t* product,
+                                   const b200mc_params_t* p, const double* Z_host, uint64_t n_paths, double* payoffs_host,
+                                   b200mc_moments_t* out_host);
 
 /* ---- FP64 parity mode: price from caller-supplied normal draws ------------------------------- *
  * Z is row-major [n_paths][spec->n_steps] FP64 — exactly the array the reference draws at

@@ -8,7 +8,8 @@ library or the device is missing — there is no CPU fallback.
 """
 
 from .exceptions import AccelerationError, ConvergenceError, GreeksError, InputValidationError, MonteCarloError
-from .exotic_options import AsianOption, BarrierOption, LookbackOption, price_asian, price_barrier, price_lookback
+from .exotic_options import (AsianOption, AutocallableOption, BarrierOption, CliquetOption, LookbackOption, price_asian,
+                             price_barrier, price_lookback)
 from .greeks import (ExerciseStyle, ExoticAdapter, HestonAdapter, JumpDiffusionAdapter, OptionType, PricerProtocol,
                      compute_greeks_unified, greeks_heston, greeks_jump_diffusion)
 from .models import HestonPricer, KouJumpDiffusion, MertonJumpDiffusion
@@ -19,7 +20,8 @@ from .validation import monte_carlo_convergence_test
 __version__ = "0.1.0"
 __all__ = [
     "MonteCarloPricer", "MCMethod", "MCResult", "MonteCarloPricerUni",
-    "AsianOption", "BarrierOption", "LookbackOption", "price_asian", "price_barrier", "price_lookback",
+    "AsianOption", "BarrierOption", "LookbackOption", "AutocallableOption", "CliquetOption", "price_asian", "price_barrier",
+    "price_lookback",
     "HestonPricer", "MertonJumpDiffusion", "KouJumpDiffusion",
     "monte_carlo_convergence_test",
     "PricerProtocol", "ExoticAdapter", "HestonAdapter", "JumpDiffusionAdapter", "compute_greeks_unified", "greeks_heston",

@@ -17,10 +17,10 @@ from .exceptions import AccelerationError, MonteCarloError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200mc.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_SCENARIOS = 16
 
-EUROPEAN, ASIAN_ARITH, ASIAN_GEOM, BARRIER, LOOKBACK = range(5)
+EUROPEAN, ASIAN_ARITH, ASIAN_GEOM, BARRIER, LOOKBACK, CLIQUET, AUTOCALLABLE = range(7)
 FLAG_EXACT_EX2 = 1
 FLAG_NO_BULK_COPY = 2
 
@@ -29,6 +29,12 @@ class Spec(C.Structure):
     _fields_ = [("kind", C.c_int32), ("is_put", C.c_int32), ("antithetic", C.c_int32),
                 ("barrier_down", C.c_int32), ("barrier_in", C.c_int32), ("lookback_fixed", C.c_int32),
                 ("n_steps", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class Product(C.Structure):
+    """b200mc_product_t: CLIQUET (local_cap, local_floor, global_cap, global_floor, n_periods) /
+    AUTOCALLABLE (autocall_barrier, coupon_barrier, coupon_rate, ki_barrier, observation_freq)."""
+    _fields_ = [("a", C.c_double), ("b", C.c_double), ("c", C.c_double), ("d", C.c_double), ("period", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Info(C.Structure):
@@ -69,6 +75,9 @@ SIGNATURES = {
                                          C.c_uint64, C.c_uint64, _P, _P]),
     "b200mc_simulate_control_variate": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
                                                   C.c_uint64, C.c_uint64, _P]),
+    "b200mc_simulate_structured": (C.c_int, [_P, C.POINTER(Spec), C.POINTER(Product), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
+                                             C.c_uint64, C.c_uint64, _P]),
+    "b200mc_structured_from_normals": (C.c_int, [_P, C.POINTER(Spec), C.POINTER(Product), _P, _P, C.c_uint64, _P, _P]),
     "b200mc_simulate_sobol": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_uint32, C.c_uint32, _P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P]),
     "b200mc_sobol_points": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, _P]),
     "b200mc_sobol_normals": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P]),
@@ -210,6 +219,36 @@ class Engine:
                                               int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF,
                                               int(path_begin), int(n_paths), out_ptr, cuda_stream)
         self._check(rc, "b200mc_simulate_device")
+
+    # -- structured products (cliquet / autocallable) ------------------------------------------
+    def simulate_structured(self, spec: Spec, product: Product, params: np.ndarray, seed: int, n_paths: int, *, stream_base: int = 0,
+                            path_begin: int = 0) -> np.ndarray:
+        """params [n_opt, n_scen] -> MOMENTS_DTYPE [n_opt, n_scen] (CLIQUET: undiscounted currency payoff;
+        AUTOCALLABLE: discounted payoff per unit notional)."""
+        params = np.ascontiguousarray(params, dtype=PARAMS_DTYPE)
+        if params.ndim != 2:
+            raise MonteCarloError("params must have shape [n_opt, n_scen]")
+        out = np.empty(params.shape, dtype=MOMENTS_DTYPE)
+        rc = self._lib.b200mc_simulate_structured(self._h, C.byref(spec), C.byref(product), params.ctypes.data, params.shape[0], params.shape[1],
+                                                  int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF, int(path_begin), int(n_paths),
+                                                  out.ctypes.data)
+        self._check(rc, "b200mc_simulate_structured")
+        return out
+
+    def structured_from_normals(self, spec: Spec, product: Product, params: np.ndarray, Z: np.ndarray):
+        """FP64 on the caller's draws Z [n_paths, n_steps] -> (payoffs [n_paths], moments)."""
+        Z = np.ascontiguousarray(Z, dtype=np.float64)
+        if Z.ndim != 2 or Z.shape[1] != spec.n_steps:
+            raise MonteCarloError("Z must have shape [n_paths, n_steps]")
+        p = np.ascontiguousarray(params, dtype=PARAMS_DTYPE).reshape(-1)
+        if p.size != 1:
+            raise MonteCarloError("parity mode prices one parameter set per call")
+        pay = np.empty(Z.shape[0], dtype=np.float64)
+        mom = np.empty(1, dtype=MOMENTS_DTYPE)
+        rc = self._lib.b200mc_structured_from_normals(self._h, C.byref(spec), C.byref(product), p.ctypes.data, Z.ctypes.data, Z.shape[0],
+                                                      pay.ctypes.data, mom.ctypes.data)
+        self._check(rc, "b200mc_structured_from_normals")
+        return pay, mom[0]
 
     # -- quasi-Monte Carlo ------------------------------------------------------------------
     def simulate_sobol(self, spec: Spec, params: np.ndarray, dirnums: np.ndarray, shift: np.ndarray, bits: int, n_points: int,

@@ -20,6 +20,7 @@
 #include "models.cuh"
 #include "peaks.cuh"
 #include "sobol.cuh"
+#include "structured.cuh"
 
 using namespace b200mc;
 
@@ -101,6 +102,8 @@ int reserve_pinned(b200mc_engine* e, size_t bytes) {
 
 int check_spec(b200mc_engine* e, const b200mc_spec_t* s) {
   if (!s) return fail(e, B200MC_ERR_INVALID, "spec is null");
+  if (s->kind == B200MC_CLIQUET || s->kind == B200MC_AUTOCALLABLE)
+    return fail(e, B200MC_ERR_INVALID, "structured products (kind %d) go through b200mc_simulate_structured", s->kind);
   if (s->kind < B200MC_EUROPEAN || s->kind > B200MC_LOOKBACK) return fail(e, B200MC_ERR_INVALID, "unknown payoff kind %d", s->kind);
   if (s->n_steps == 0) return fail(e, B200MC_ERR_INVALID, "n_steps must be >= 1");
   if (s->antithetic && s->kind != B200MC_EUROPEAN)
@@ -178,6 +181,39 @@ cudaError_t launch_pathdep(const SimArgs& a, uint32_t ns, dim3 grid, cudaStream_
     case 4: pathdep_kernel<KIND, 4, kMinBlocksWide, 1, 5><<<grid, kBlock, 0, s>>>(a); break;
     case 8: pathdep_kernel<KIND, 8, kMinBlocksWide, 1, 5><<<grid, kBlock, 0, s>>>(a); break;
     default: pathdep_kernel<KIND, 16, kMinBlocksWide, 1, 5><<<grid, kBlock, 0, s>>>(a); break;
+  }
+  return cudaGetLastError();
+}
+
+// ---- structured products: argument checks and launch dispatch ---------------------------------------------------
+int check_structured(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc_product_t* product, uint32_t* period, uint32_t* n_events,
+                     uint32_t* sim_steps) {
+  if (!spec || !product) return fail(e, B200MC_ERR_INVALID, "spec / product is null");
+  if (spec->kind != B200MC_CLIQUET && spec->kind != B200MC_AUTOCALLABLE)
+    return fail(e, B200MC_ERR_INVALID, "kind %d is not a structured product", spec->kind);
+  if (spec->n_steps == 0) return fail(e, B200MC_ERR_INVALID, "n_steps must be >= 1");
+  if (product->period == 0) return fail(e, B200MC_ERR_INVALID, "n_periods / observation_freq must be >= 1");
+  if (spec->kind == B200MC_CLIQUET) {
+    *n_events = product->period;                 // n_periods
+    *period = spec->n_steps / product->period;   // steps per period (exotic_options.py:532)
+    if (*period == 0) return fail(e, B200MC_ERR_INVALID, "more cliquet periods (%u) than steps (%u): every return is 0", product->period, spec->n_steps);
+    *sim_steps = *period * *n_events;
+  } else {
+    *period = product->period;                   // observation_freq
+    *n_events = spec->n_steps / product->period; // len(range(freq, n_steps + 1, freq))
+    *sim_steps = spec->n_steps;
+  }
+  return 0;
+}
+
+template <int KIND>
+cudaError_t launch_structured(const StructuredArgs& g, uint32_t ns, dim3 grid, cudaStream_t s) {
+  switch (ns) {
+    case 1: structured_kernel<KIND, 1, kMinBlocksAsian><<<grid, kBlock, 0, s>>>(g); break;
+    case 2: structured_kernel<KIND, 2, kMinBlocksAsian><<<grid, kBlock, 0, s>>>(g); break;
+    case 4: structured_kernel<KIND, 4, kMinBlocksWide><<<grid, kBlock, 0, s>>>(g); break;
+    case 8: structured_kernel<KIND, 8, kMinBlocksWide><<<grid, kBlock, 0, s>>>(g); break;
+    default: structured_kernel<KIND, 16, kMinBlocksWide><<<grid, kBlock, 0, s>>>(g); break;
   }
   return cudaGetLastError();
 }
@@ -432,6 +468,99 @@ int b200mc_simulate_control_variate(b200mc_engine_t* e, const b200mc_spec_t* spe
                                     uint32_t n_opt, uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin,
                                     uint64_t n_paths, b200mc_cv_moments_t* out_host) {
   return simulate_host(e, spec, params_host, n_opt, n_scen, seed, stream_base, path_begin, n_paths, out_host, true);
+}
+
+// ---- structured products ---------------------------------------------------------------------------------------
+int b200mc_simulate_structured(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_product_t* product,
+                               const b200mc_params_t* params_host, uint32_t n_opt, uint32_t n_scen, uint64_t seed, uint32_t stream_base,
+                               uint64_t path_begin, uint64_t n_paths, b200mc_moments_t* out_host) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  uint32_t period, n_events, sim_steps;
+  if (int rc = check_structured(e, spec, product, &period, &n_events, &sim_steps)) return rc;
+  if (!params_host || !out_host) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
+  if (n_opt == 0 || n_paths == 0 || n_scen == 0 || n_scen > B200MC_MAX_SCENARIOS) return fail(e, B200MC_ERR_INVALID, "bad n_opt / n_scen / n_paths");
+  CU_TRY(e, cudaSetDevice(e->device));
+  const size_t n = (size_t)n_opt * n_scen;
+  const size_t in_bytes = n * sizeof(b200mc_params_t), out_bytes = n * sizeof(b200mc_moments_t);
+  if (int rc = reserve(e, e->params_dev, in_bytes)) return rc;
+  if (int rc = reserve(e, e->moments_dev, out_bytes)) return rc;
+  if (int rc = reserve_pinned(e, in_bytes + out_bytes)) return rc;
+  char* pin_in = (char*)e->pinned;
+  char* pin_out = pin_in + in_bytes;
+  memcpy(pin_in, params_host, in_bytes);
+  CU_TRY(e, cudaMemcpyAsync(e->params_dev.ptr, pin_in, in_bytes, cudaMemcpyHostToDevice, e->stream));
+
+  const uint32_t ns = pad_scenarios(n_scen);
+  uint32_t tiles, ppt;
+  plan_tiles(e, n_opt, n_paths, sim_steps, ns, true, tiles, ppt);
+  const uint64_t ctas = (uint64_t)tiles * n_opt;
+  if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
+  if (int rc = reserve(e, e->partials, ctas * 2 * ns * sizeof(double))) return rc;
+  StructuredArgs a{};
+  a.sim.params = (const b200mc_params_t*)e->params_dev.ptr;
+  a.sim.partials = (double*)e->partials.ptr;
+  a.sim.path_begin = path_begin, a.sim.n_paths = n_paths;
+  a.sim.n_opt = n_opt, a.sim.n_scen = n_scen, a.sim.tiles = tiles, a.sim.paths_per_thread = ppt, a.sim.n_steps = spec->n_steps;
+  a.sim.rk = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32));
+  a.sim.stream_base = stream_base;
+  a.a = product->a, a.b = product->b, a.c = product->c, a.d = product->d;
+  a.period = period, a.n_events = n_events, a.sim_steps = sim_steps;
+  const dim3 grid((unsigned)ctas);
+  const int slot = (int)(e->timed % b200mc_engine::kRing);
+  if (e->timing) CU_TRY(e, cudaEventRecord(e->ring0[slot], e->stream));
+  const cudaError_t err = spec->kind == B200MC_CLIQUET ? launch_structured<B200MC_CLIQUET>(a, ns, grid, e->stream)
+                                                      : launch_structured<B200MC_AUTOCALLABLE>(a, ns, grid, e->stream);
+  if (err != cudaSuccess) return fail(e, B200MC_ERR_CUDA, "structured kernel launch failed: %s", cudaGetErrorString(err));
+  if (e->timing) {
+    CU_TRY(e, cudaEventRecord(e->ring1[slot], e->stream));
+    e->timed += 1;
+  }
+  // CLIQUET payoffs are per unit spot (scaled by S in the fold); AUTOCALLABLE payoffs are per unit notional
+  fold_kernel<<<n_opt * n_scen, 32, 0, e->stream>>>((const double*)e->partials.ptr, spec->kind == B200MC_CLIQUET ? a.sim.params : nullptr,
+                                                   (b200mc_moments_t*)e->moments_dev.ptr, n_scen, ns, tiles, (double)n_paths);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 2;
+  CU_TRY(e, cudaMemcpyAsync(pin_out, e->moments_dev.ptr, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  memcpy(out_host, pin_out, out_bytes);
+  return 0;
+}
+
+int b200mc_structured_from_normals(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_product_t* product, const b200mc_params_t* p,
+                                   const double* Z_host, uint64_t n_paths, double* payoffs_host, b200mc_moments_t* out_host) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  uint32_t period, n_events, sim_steps;
+  if (int rc = check_structured(e, spec, product, &period, &n_events, &sim_steps)) return rc;
+  if (!p || !Z_host || !out_host) return fail(e, B200MC_ERR_INVALID, "null pointer argument");
+  if (n_paths == 0) return fail(e, B200MC_ERR_INVALID, "n_paths must be >= 1");
+  CU_TRY(e, cudaSetDevice(e->device));
+  const size_t z_bytes = (size_t)n_paths * spec->n_steps * sizeof(double);
+  const uint64_t ctas = (n_paths + 127) / 128;
+  if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "too many paths for one launch");
+  if (int rc = reserve(e, e->scratch_a, z_bytes)) return rc;
+  if (int rc = reserve(e, e->scratch_b, n_paths * sizeof(double))) return rc;
+  if (int rc = reserve(e, e->partials, ctas * 2 * sizeof(double))) return rc;
+  if (int rc = reserve(e, e->moments_dev, sizeof(b200mc_moments_t))) return rc;
+  CU_TRY(e, cudaMemcpyAsync(e->scratch_a.ptr, Z_host, z_bytes, cudaMemcpyHostToDevice, e->stream));
+  StructuredF64Args a{};
+  a.Z = (const double*)e->scratch_a.ptr;
+  a.payoffs = payoffs_host ? (double*)e->scratch_b.ptr : nullptr;
+  a.partials = (double*)e->partials.ptr;
+  a.n_paths = n_paths, a.n_steps = spec->n_steps, a.period = period, a.n_events = n_events;
+  a.S = p->S, a.T = p->T, a.r = p->r, a.sigma = p->sigma, a.q = p->q;
+  a.a = product->a, a.b = product->b, a.c = product->c, a.d = product->d;
+  if (spec->kind == B200MC_CLIQUET) structured_from_normals_kernel<B200MC_CLIQUET><<<(unsigned)ctas, 128, 0, e->stream>>>(a);
+  else structured_from_normals_kernel<B200MC_AUTOCALLABLE><<<(unsigned)ctas, 128, 0, e->stream>>>(a);
+  CU_TRY(e, cudaGetLastError());
+  fold_kernel<<<1, 32, 0, e->stream>>>((const double*)e->partials.ptr, nullptr, (b200mc_moments_t*)e->moments_dev.ptr, 1, 1, (uint32_t)ctas, (double)n_paths);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 2;
+  if (payoffs_host) CU_TRY(e, cudaMemcpyAsync(payoffs_host, e->scratch_b.ptr, n_paths * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaMemcpyAsync(out_host, e->moments_dev.ptr, sizeof(b200mc_moments_t), cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  return 0;
 }
 
 int b200mc_payoffs_from_normals_device(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* p, int accumulate,

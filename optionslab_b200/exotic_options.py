@@ -18,8 +18,8 @@ import numpy as np
 from . import _ffi, runtime
 from .monte_carlo import MCResult
 
-__all__ = ["ExoticOptionBase", "AsianOption", "BarrierOption", "LookbackOption", "price_asian", "price_barrier",
-           "price_lookback"]
+__all__ = ["ExoticOptionBase", "AsianOption", "BarrierOption", "LookbackOption", "AutocallableOption", "CliquetOption",
+           "price_asian", "price_barrier", "price_lookback"]
 
 
 @dataclass
@@ -131,6 +131,94 @@ class LookbackOption(ExoticOptionBase):
     def price_scenarios(self, scenarios, n_paths: int = 100000, n_steps: int = 252, lookback_type="floating",
                         option_type="call"):
         m, sc = self._run(self._spec(n_steps, lookback_type, option_type), scenarios, n_paths)
+        return [float(p) for p in self._finish(m, sc, False)]
+
+
+def _run_structured(opt: ExoticOptionBase, spec, product, scenarios: Sequence, n_paths: int):
+    """Moments of every (S, K, T, r, sigma, q) scenario on common random numbers, sharded over ranks like runtime.simulate."""
+    from . import distributed
+
+    sc = np.asarray(scenarios, dtype=np.float64).reshape(-1, 6)
+    seed = opt._seed()
+    eng = _ffi.get_engine()
+    ctx = distributed.current()
+    out = []
+    for lo in range(0, len(sc), _ffi.MAX_SCENARIOS):
+        blk = sc[lo:lo + _ffi.MAX_SCENARIOS]
+        params = _ffi.make_params(blk[:, 0], blk[:, 1], blk[:, 2], blk[:, 3], blk[:, 4], blk[:, 5])[None, :]
+        if ctx is None or ctx.world_size == 1:
+            m = eng.simulate_structured(spec, product, params, seed, n_paths)
+        else:
+            begin, count = distributed.partition_paths(n_paths, ctx.rank, ctx.world_size)
+            local = (eng.simulate_structured(spec, product, params, seed, count, path_begin=begin) if count > 0
+                     else np.zeros(params.shape, dtype=_ffi.MOMENTS_DTYPE))
+            m = distributed.allreduce_moments(local, ctx)
+        out.append(m[0])
+    return np.concatenate(out), sc
+
+
+@dataclass
+class AutocallableOption(ExoticOptionBase):
+    """exotic_options.py:404-488.  Barriers are relative to the spot; the price is a fraction of the notional.  The
+    redemption / coupon / knock-in logic runs per path in registers; discounting happens per path, as in the reference."""
+
+    autocall_barrier: float = 1.0
+    coupon_barrier: float = 0.8
+    coupon_rate: float = 0.10
+    ki_barrier: float = 0.6
+
+    def _launch(self, scenarios, n_paths, n_steps, observation_freq):
+        if observation_freq == 0:
+            raise ValueError("range() arg 3 must not be zero")  # what the reference's range(freq, n_steps + 1, freq) raises
+        freq = int(observation_freq) if observation_freq > 0 else int(n_steps) + 1  # a negative step gives no observation dates
+        product = _ffi.Product(self.autocall_barrier, self.coupon_barrier, self.coupon_rate, self.ki_barrier, min(freq, 0xFFFFFFFF), 0)
+        return _run_structured(self, _ffi.make_spec(_ffi.AUTOCALLABLE, n_steps), product, scenarios, n_paths)
+
+    def price(self, n_paths: int = 100000, n_steps: int = 252, observation_freq: int = 21, return_error: bool = False, **kwargs):
+        m, _ = self._launch(self._self_scenario(), n_paths, n_steps, observation_freq)
+        mean = m["sum"][0] / m["n"][0]  # payoffs are already discounted (exotic_options.py:466,486-488)
+        if return_error:
+            var = max(m["sum_sq"][0] / m["n"][0] - mean * mean, 0.0)
+            return MCResult(float(mean), float(np.sqrt(var / m["n"][0])), int(m["n"][0]))
+        return np.float64(mean)
+
+    def price_scenarios(self, scenarios, n_paths: int = 100000, n_steps: int = 252, observation_freq: int = 21, **kwargs):
+        m, _ = self._launch(scenarios, n_paths, n_steps, observation_freq)
+        return [float(x) for x in m["sum"] / m["n"]]
+
+
+@dataclass
+class CliquetOption(ExoticOptionBase):
+    """exotic_options.py:491-552: sum over n_periods reset periods of the locally capped / floored simple returns,
+    capped / floored globally, floored at 0, times S, discounted."""
+
+    local_cap: float = 0.05
+    local_floor: float = -0.05
+    global_cap: float = 0.30
+    global_floor: float = 0.0
+
+    def _launch(self, scenarios, n_paths, n_steps, n_periods):
+        if n_periods == 0:
+            raise ZeroDivisionError("integer division or modulo by zero")  # n_steps // n_periods in the reference
+        product = _ffi.Product(self.local_cap, self.local_floor, self.global_cap, self.global_floor, int(n_periods), 0)
+        return _run_structured(self, _ffi.make_spec(_ffi.CLIQUET, n_steps), product, scenarios, n_paths)
+
+    def _degenerate(self, scenarios, n_steps, n_periods):
+        """More periods than steps: every period starts and ends at column 0, every return is 0 (exotic_options.py:532-546)."""
+        total = float(np.clip(sum(float(np.clip(0.0, self.local_floor, self.local_cap)) for _ in range(n_periods)), self.global_floor, self.global_cap))
+        return [float(np.exp(-s[3] * s[2]) * max(total, 0.0) * s[0]) for s in scenarios]
+
+    def price(self, n_paths: int = 100000, n_steps: int = 252, n_periods: int = 12, return_error: bool = False, **kwargs):
+        if 0 < n_steps < n_periods:
+            p = self._degenerate(self._self_scenario(), n_steps, n_periods)[0]
+            return MCResult(p, 0.0, int(n_paths)) if return_error else np.float64(p)
+        m, sc = self._launch(self._self_scenario(), n_paths, n_steps, n_periods)
+        return self._finish(m, sc, return_error)[0]
+
+    def price_scenarios(self, scenarios, n_paths: int = 100000, n_steps: int = 252, n_periods: int = 12, **kwargs):
+        if 0 < n_steps < n_periods:
+            return self._degenerate(scenarios, n_steps, n_periods)
+        m, sc = self._launch(scenarios, n_paths, n_steps, n_periods)
         return [float(p) for p in self._finish(m, sc, False)]
 
 

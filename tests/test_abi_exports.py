@@ -34,6 +34,7 @@ def test_struct_layouts_match_header():
     assert _ffi.PARAMS_DTYPE.itemsize == 64 and _ffi.MOMENTS_DTYPE.itemsize == 24
     assert C.sizeof(_ffi.Info) == 4 * 6 + 8 + 4 * 2 + 64
     assert C.sizeof(_ffi.Peaks) == 12 * 8
+    assert C.sizeof(_ffi.Product) == 4 * 8 + 2 * 4 and _ffi.Product.period.offset == 32
     p = _ffi.make_params(100.0, [90.0, 110.0], 1.0, 0.05, 0.2, 0.0, 120.0)
     assert p.shape == (2,) and p["K"].tolist() == [90.0, 110.0] and p["barrier"].tolist() == [120.0, 120.0]
 

@@ -20,7 +20,7 @@ from oracle import reference_mc as orc  # noqa: E402  (CPU baseline / checker on
 P = dict(S=100.0, K=100.0, T=1.0, r=0.05, sigma=0.2)
 # per path-step (instructions, MUFU) of each kernel family, from the shipped SASS (profiles/r01_sass_*.txt)
 BUDGET = {"european": (87 / 8, 2.0), "asian": (123 / 8, 2.0), "asian_ex2": (111 / 8, 3.0), "barrier": (99 / 8, 2.0), "qmc": (330 / 16, 2.0),
-          "heston": (112 / 4, 4.0), "jump": (88 / 8, 2.0)}  # tools/sass_loop.py (Heston: one Box-Muller pair + sqrt(v) per step)
+          "heston": (112 / 4, 4.0), "jump": (88 / 8, 2.0), "structured": (130 / 8, 2.0)}  # tools/sass_loop.py (Heston: one Box-Muller pair + sqrt(v) per step)
 
 
 def timed(fn, reps=5):
@@ -86,6 +86,17 @@ def main():
            lambda: float(bar.price(16_000_000, 365, "up-and-out")),
            lambda: float(orc.exotic_price("barrier", **P, seed=42, n_paths=100_000, n_steps=365, barrier=120.0)), 100_000 * 365,
            note="CPU oracle at 100k paths (16M x 366 doubles = 46.8 GB per array does not fit)")
+    # structured products of the same file (exotic_options.py:404-552): autocallable (monthly observations) and cliquet (12 periods)
+    auto = ob.AutocallableOption(**P, seed=42)
+    record("Autocallable 4M x 252, 12 observation dates", "structured", 4_000_000 * 252, 4_000_000 * 252,
+           lambda: float(auto.price(4_000_000, 252, 21)),
+           lambda: float(orc.exotic_price("autocallable", **P, seed=42, n_paths=100_000, n_steps=252, observation_freq=21)), 100_000 * 252,
+           note="CPU oracle at 100k paths")
+    cliq = ob.CliquetOption(**P, seed=42)
+    record("Cliquet 4M x 252, 12 reset periods", "structured", 4_000_000 * 252, 4_000_000 * 252,
+           lambda: float(cliq.price(4_000_000, 252, 12)),
+           lambda: float(orc.exotic_price("cliquet", **P, seed=42, n_paths=100_000, n_steps=252, n_periods=12)), 100_000 * 252,
+           note="CPU oracle at 100k paths")
     # QMC: scrambled Sobol, 2^20 points x 252 dimensions (MCMethod.QMC; N samples, no mirroring)
     import warnings
     warnings.simplefilter("ignore")  # scipy: N not a power of two (CPU sample below)
