@@ -25,6 +25,14 @@ def _prices():
     uni = ob.MonteCarloPricerUni(100_001, 16, seed=3)
     out["batch"] = uni.price_batch([100.0, 90.0, 110.0], [100.0, 95.0, 105.0], [1.0, 0.5, 2.0], [0.05] * 3, [0.2, 0.3, 0.1], "put").tolist()
     out["greeks"] = dict(ob.MonteCarloPricer(100_001, 12, seed=2).greeks(**P, option_type="call"))
+    out["autocall"] = float(ob.AutocallableOption(**P, seed=8).price(200_003, 24, 6))
+    out["cliquet"] = ob.CliquetOption(**P, seed=8).price_scenarios([(100.0, 100.0, 1.0, 0.05, 0.2, 0.0), (101.0, 100.0, 1.0, 0.05, 0.21, 0.01)],
+                                                                  n_paths=200_003, n_steps=24, n_periods=6)
+    hes = ob.HestonPricer(kappa=2.0, theta=0.04, sigma_v=0.3, rho=-0.7, v0=0.04)
+    out["heston"] = [hes.price_monte_carlo(100.0, 100.0, 1.0, 0.05, 0.01, "call", 200_003, 20, seed=4)] + \
+        hes.price_scenarios([(100.0, 100.0, 1.0, 0.05, 0.04, 0.01), (101.0, 100.0, 1.0, 0.05, 0.0441, 0.01)], "put", 200_003, 20, seed=4)
+    out["kou"] = ob.KouJumpDiffusion(2.0, 0.4, 10.0, 5.0).price_monte_carlo(100.0, 100.0, 1.0, 0.05, 0.2, "call", 0.01, 200_003, 20, seed=4)
+    out["qmc"] = ob.MonteCarloPricer(1 << 16, 16, seed=42, method=ob.MCMethod.QMC).price(**P, option_type="call")
     return out
 
 
@@ -60,6 +68,11 @@ def test_two_ranks_reproduce_single_process_prices(tmp_path):
         np.testing.assert_allclose(got["batch"], whole["batch"], rtol=1e-6)
         for k, v in whole["greeks"].items():
             assert got["greeks"][k] == pytest.approx(v, rel=2e-3, abs=2e-3), k
+        assert got["autocall"] == pytest.approx(whole["autocall"], rel=1e-6)
+        np.testing.assert_allclose(got["cliquet"], whole["cliquet"], rtol=1e-6)
+        np.testing.assert_allclose(got["heston"], whole["heston"], rtol=1e-6)
+        assert got["kou"] == pytest.approx(whole["kou"], rel=1e-6)
+        assert got["qmc"] == pytest.approx(whole["qmc"], rel=1e-6)
     a = json.load(open(os.path.join(tmp_path, "rank0.json")))
     b = json.load(open(os.path.join(tmp_path, "rank1.json")))
     assert a == b  # every rank holds the identical all-reduced result
