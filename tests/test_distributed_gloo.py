@@ -83,6 +83,22 @@ class _OracleEngine:
         return out
 
 
+    def simulate_structured(self, spec, product, params, seed, n_paths, *, stream_base=0, path_begin=0):
+        params = np.asarray(params)
+        out = np.zeros(params.shape, dtype=_ffi.MOMENTS_DTYPE)
+        for opt in range(params.shape[0]):
+            Z = philox_oracle.normals(seed, n_paths, spec.n_steps, stream=stream_base + opt, path_begin=path_begin)
+            for k in range(params.shape[1]):
+                p = params[opt, k]
+                paths = orc.exotic_paths_from_normals(p["S"], p["T"], p["r"], p["sigma"], p["q"], Z)
+                if spec.kind == _ffi.CLIQUET:
+                    pay = orc.cliquet_payoffs(paths, p["S"], product.a, product.b, product.c, product.d, product.period)
+                else:
+                    pay = orc.autocallable_payoffs(paths, p["S"], p["T"], p["r"], product.a, product.b, product.c, product.d, product.period)
+                out[opt, k] = (pay.sum(), (pay**2).sum(), len(pay))
+        return out
+
+
 def _price_everything():
     import optionslab_b200 as ob
 
@@ -91,7 +107,11 @@ def _price_everything():
     greeks = pr.greeks(**P, option_type="call", include_second_order=False)
     grid = ob.MonteCarloPricerUni(N_PATHS, N_STEPS, seed=SEED).price_batch([100.0, 101.0], [105.0, 95.0], 0.5, 0.03, 0.25, "call")
     asian = ob.AsianOption(**P, seed=SEED).price(n_paths=N_PATHS, n_steps=N_STEPS, return_error=True)
-    return np.array([res.price, res.std_error, res.n_paths, greeks["delta"], greeks["vega"], grid[0], grid[1], asian.price, asian.n_paths])
+    auto = ob.AutocallableOption(**P, seed=SEED).price(N_PATHS, N_STEPS, 4, return_error=True)
+    cliq = ob.CliquetOption(**P, seed=SEED).price_scenarios([(100.0, 105.0, 0.5, 0.03, 0.25, 0.0), (101.0, 105.0, 0.5, 0.03, 0.26, 0.0)],
+                                                            n_paths=N_PATHS, n_steps=N_STEPS, n_periods=3)
+    return np.array([res.price, res.std_error, res.n_paths, greeks["delta"], greeks["vega"], grid[0], grid[1], asian.price, asian.n_paths,
+                     auto.price, auto.std_error, auto.n_paths, cliq[0], cliq[1]])
 
 
 def _pricer_worker(rank, world, port, out_dir):
@@ -103,7 +123,7 @@ def _pricer_worker(rank, world, port, out_dir):
 
 
 def test_pricer_classes_shard_paths_and_allreduce(tmp_path, monkeypatch):
-    """MonteCarloPricer / MonteCarloPricerUni.price_batch / AsianOption on 2 ranks == 1 process: every rank simulates
+    """MonteCarloPricer / MonteCarloPricerUni.price_batch / AsianOption / AutocallableOption / CliquetOption on 2 ranks == 1 process: every rank simulates
     its slice of the global path range (runtime.simulate) and the all-reduced moments give identical prices, Greeks,
     standard errors and sample counts on all ranks."""
     with socket.socket() as s:
