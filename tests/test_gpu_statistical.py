@@ -310,3 +310,27 @@ def test_martingale_and_variance_of_the_terminal_spot_over_maturities_and_step_c
         mu4 = fwd**4 * (w - 1) ** 2 * (w**4 + 2 * w**3 + 3 * w**2 - 3)
         assert np.all(np.abs(var - want_var) < 4.5 * np.sqrt((mu4 - want_var**2) / m["n"])), (n_steps, var / want_var)
         assert np.allclose(m["sum_payoff"], m["sum_terminal"], rtol=1e-6)  # K ~ 0: the payoff is the terminal spot
+
+
+def test_discrete_geometric_asian_matches_its_exact_lognormal_law(engine):
+    """The discrete geometric average of a GBM is exactly lognormal: ln G ~ N(ln S + (r-q-sigma^2/2) T (n+1)/(2n),
+    sigma^2 T (n+1)(2n+1)/(6 n^2)).  The path-dependent kernel (ASIAN_GEOM, running sum of l_t in registers) must price
+    within 4 standard errors of that closed form for calls and puts over strikes, maturities and step counts."""
+    from math import erf, exp, log, sqrt
+
+    cdf = lambda x: 0.5 * (1.0 + erf(x / sqrt(2.0)))
+    n_paths = 4_000_000
+    for n_steps, T, sigma, q in ((252, 1.0, 0.2, 0.0), (12, 0.5, 0.35, 0.02), (37, 2.0, 0.15, 0.01)):
+        S, r = 100.0, 0.05
+        mu = log(S) + (r - q - 0.5 * sigma**2) * T * (n_steps + 1) / (2 * n_steps)
+        var = sigma**2 * T * (n_steps + 1) * (2 * n_steps + 1) / (6 * n_steps**2)
+        for K in (90.0, 100.0, 115.0):
+            d2 = (mu - log(K)) / sqrt(var)
+            d1 = d2 + sqrt(var)
+            call = exp(-r * T) * (exp(mu + 0.5 * var) * cdf(d1) - K * cdf(d2))
+            put = exp(-r * T) * (K * cdf(-d2) - exp(mu + 0.5 * var) * cdf(-d1))
+            for ot, want in (("call", call), ("put", put)):
+                m = engine.simulate(_ffi.make_spec(_ffi.ASIAN_GEOM, n_steps, is_put=ot == "put"), _ffi.make_params(S, K, T, r, sigma, q).reshape(1, 1),
+                                    2024 + n_steps, n_paths)[0, 0]
+                price, se = _price_se(m, r, T)
+                assert abs(price - want) <= 4 * se, (n_steps, K, ot, price, want, se)
