@@ -154,7 +154,8 @@ void plan_tiles(const b200mc_engine* e, uint32_t n_opt, uint64_t n_paths, uint32
 // interleaved, which needs ~60-75 registers; squeezing below 48 costs 5-10%.
 constexpr int kMinBlocksSmall = 6;    // European, 1-2 scenarios (40-47 registers)
 constexpr int kMinBlocksPathdep = 6;  // Asian / barrier / lookback, 1-2 scenarios (<= 40 registers)
-constexpr int kMinBlocksAsian = 5;    // arithmetic Asian, 1-2 scenarios: the packed small-move loop wants 43 registers (profiles/r01_variants14*)
+constexpr int kMinBlocksAsian = 6;    // arithmetic Asian, 1-2 scenarios (profiles/r01_variants14*)
+constexpr int kMinBlocksStructured = 5;  // cliquet / autocallable, 1-2 scenarios (47-48 registers)
 constexpr int kMinBlocksWide = 2;     // 4-16 scenarios (<= 128 registers)
 
 template <int NS>
@@ -178,9 +179,9 @@ cudaError_t launch_pathdep(const SimArgs& a, uint32_t ns, dim3 grid, cudaStream_
     case 2: pathdep_kernel<KIND, 2, kMinB><<<grid, kBlock, 0, s>>>(a); break;
     // 4+ scenarios: the scalar Horner form (immediates instead of 10 registers of packed coefficients; same roundings,
     // so a scenario's bits do not depend on which form its launch used)
-    case 4: pathdep_kernel<KIND, 4, kMinBlocksWide, 1, 5><<<grid, kBlock, 0, s>>>(a); break;
-    case 8: pathdep_kernel<KIND, 8, kMinBlocksWide, 1, 5><<<grid, kBlock, 0, s>>>(a); break;
-    default: pathdep_kernel<KIND, 16, kMinBlocksWide, 1, 5><<<grid, kBlock, 0, s>>>(a); break;
+    case 4: pathdep_kernel<KIND, 4, kMinBlocksWide, 1, 4><<<grid, kBlock, 0, s>>>(a); break;
+    case 8: pathdep_kernel<KIND, 8, kMinBlocksWide, 1, 4><<<grid, kBlock, 0, s>>>(a); break;
+    default: pathdep_kernel<KIND, 16, kMinBlocksWide, 1, 4><<<grid, kBlock, 0, s>>>(a); break;
   }
   return cudaGetLastError();
 }
@@ -209,8 +210,8 @@ int check_structured(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc_p
 template <int KIND>
 cudaError_t launch_structured(const StructuredArgs& g, uint32_t ns, dim3 grid, cudaStream_t s) {
   switch (ns) {
-    case 1: structured_kernel<KIND, 1, kMinBlocksAsian><<<grid, kBlock, 0, s>>>(g); break;
-    case 2: structured_kernel<KIND, 2, kMinBlocksAsian><<<grid, kBlock, 0, s>>>(g); break;
+    case 1: structured_kernel<KIND, 1, kMinBlocksStructured><<<grid, kBlock, 0, s>>>(g); break;
+    case 2: structured_kernel<KIND, 2, kMinBlocksStructured><<<grid, kBlock, 0, s>>>(g); break;
     case 4: structured_kernel<KIND, 4, kMinBlocksWide><<<grid, kBlock, 0, s>>>(g); break;
     case 8: structured_kernel<KIND, 8, kMinBlocksWide><<<grid, kBlock, 0, s>>>(g); break;
     default: structured_kernel<KIND, 16, kMinBlocksWide><<<grid, kBlock, 0, s>>>(g); break;

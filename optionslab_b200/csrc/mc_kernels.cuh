@@ -246,10 +246,12 @@ __device__ __forceinline__ void advance_pair(const NormalPair& p, int n_use, con
 // The arithmetic average needs S_t itself every step, i.e. a third MUFU per path-step on a kernel the XU pipe
 // already bounds.  When every possible log2-increment x = d + c*rad*cos of an option is small
 // (|d| + |c|*kRadMax <= kSmallMove; daily steps up to sigma ~ 0.48) the kernel tracks s_t = S_t/S_0 directly:
-//   s_t = s_{t-1} + s_{t-1} * (2^x - 1),   2^x - 1 = x*ln2 * (1 + x*ln2/2 * (1 + ...)) to degree 5 on the FMA pipe,
-// the two steps of a Box-Muller pair evaluated together with packed FFMA2 (123 instead of 147 issue slots per 8 steps).
-// Truncation: (ln2 x)^6/720 <= 3.8e-8 relative at the bound (a 5.65-sigma draw), ~1e-14 for a typical draw;
-// rounding is half an ulp of s per step, the same order as the additive form's 3e-8 on l_t.
+//   s_t = s_{t-1} + s_{t-1} * (2^x - 1),   2^x - 1 = x*ln2 * (1 + x*ln2/2 * (1 + ...)) to degree 4 on the FMA pipe,
+// the two steps of a Box-Muller pair evaluated together with packed FFMA2 (119 instead of 147 issue slots per 8 steps).
+// Truncation: the dropped (x ln2)^5/120 term is odd in the draw (mean zero; 1.3e-6 relative for a single 5.65-sigma draw
+// at the bound, ~1e-11 for a typical one), the first even - biased - term (x ln2)^6/720 is <= 3.8e-8 at the bound and
+// ~1e-14 typically; rounding is half an ulp of s per step, the same order as the additive form's 3e-8 on l_t.
+// Measured on identical draws at 16M paths: prices of the two forms differ by <= 3e-8 relative (tools/asian_forms_diff.py).
 // The choice is made per CTA (= per option, over all its scenarios) from the coefficients alone.
 constexpr float kRadMax = 4.79583152331271954f;  // sqrt(23): u >= 2^-23 (normal.cuh)
 constexpr float kSmallMove = 0.25f;
@@ -264,12 +266,12 @@ __device__ __forceinline__ float exp2m1_small(float x) {
   return x * t;
 }
 
-// DEG = kSmallPacked5 (shipped): packed degree 5.  DEG = 3..5: scalar Horner forms kept for scratch/variants14.cu.
-constexpr int kSmallPacked5 = -5;
+// DEG = kSmallPacked4 (shipped) / kSmallPacked5: packed degree 4 / 5.  DEG = 3..5: scalar Horner forms (4+ scenarios, scratch/variants14.cu).
+constexpr int kSmallPacked5 = -5, kSmallPacked4 = -4;
 
-template <int NS, int DEG = kSmallPacked5>
+template <int NS, int DEG = kSmallPacked4>
 __device__ __forceinline__ void advance_pair_small(const NormalPair& p, int n_use, const Coef (&q)[NS], float (&s)[NS], float (&aux)[NS]) {
-  if (DEG < 0) {  // packed degree-5 form
+  if (DEG < 0) {  // packed forms: degree -DEG
     const f32x2 cssn = pack2(p.cs, p.sn);
     const f32x2 c5 = pack2(1.3333558146e-3f, 1.3333558146e-3f), c4 = pack2(9.6181291076e-3f, 9.6181291076e-3f),
                 c3 = pack2(5.5504108665e-2f, 5.5504108665e-2f), c2 = pack2(2.4022650696e-1f, 2.4022650696e-1f),
@@ -278,7 +280,7 @@ __device__ __forceinline__ void advance_pair_small(const NormalPair& p, int n_us
     for (int k = 0; k < NS; ++k) {
       const float rc = p.rad * q[k].c;
       const f32x2 x = fma2(pack2(rc, rc), cssn, pack2(q[k].d, q[k].d));
-      f32x2 t = fma2(x, c5, c4);
+      f32x2 t = DEG <= -5 ? fma2(x, c5, c4) : c4;  // degree 4: drop the x^5 term
       t = fma2(x, t, c3);
       t = fma2(x, t, c2);
       t = fma2(x, t, c1);
@@ -325,7 +327,7 @@ __device__ __forceinline__ float path_payoff(float l, float aux, const Coef& q, 
 
 // One CTA's share of one option: paths_per_thread paths per thread, payoffs accumulated in FP32 per thread.
 // SMALL selects the multiplicative arithmetic-Asian update (state = S_t/S_0 instead of log2 of it).
-template <int KIND, int NS, bool SMALL, int UNROLL, int DEG = kSmallPacked5>
+template <int KIND, int NS, bool SMALL, int UNROLL, int DEG = kSmallPacked4>
 __device__ __forceinline__ void simulate_tile(const SimArgs& a, const Coef (&q)[NS], uint32_t stream, uint64_t tile_first, float (&acc)[2 * NS]) {
   for (uint32_t j = 0; j < a.paths_per_thread; ++j) {
     const uint64_t local = tile_first + (uint64_t)j * kBlock + threadIdx.x;
@@ -346,7 +348,7 @@ __device__ __forceinline__ void simulate_tile(const SimArgs& a, const Coef (&q)[
   }
 }
 
-template <int KIND, int NS, int MINB, int UNROLL = 1, int DEG = kSmallPacked5>
+template <int KIND, int NS, int MINB, int UNROLL = 1, int DEG = kSmallPacked4>
 __global__ void __launch_bounds__(kBlock, MINB) pathdep_kernel(const SimArgs a) {
   __shared__ Coef coef_s[NS];
   const uint32_t opt = blockIdx.x / a.tiles;

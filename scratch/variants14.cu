@@ -33,6 +33,7 @@ int main() {
 #define AS(M, U, D, EX) a.force_mufu_ex2 = EX; report("asian minb=" #M " unroll=" #U " deg=" #D " exact_ex2=" #EX, time_ms([&] { pathdep_kernel<B200MC_ASIAN_ARITH, 1, M, U, D><<<grid, 256>>>(a); }))
   AS(6, 1, 5, 1); AS(6, 1, 5, 0);
   AS(6, 1, -5, 0); AS(5, 1, -5, 0); AS(4, 1, -5, 0); AS(3, 1, -5, 0); AS(4, 2, -5, 0);
+  AS(6, 1, -4, 0); AS(5, 1, -4, 0); AS(4, 1, -4, 0);
   AS(8, 1, 5, 0); AS(5, 1, 5, 0); AS(4, 1, 5, 0); AS(3, 1, 5, 0); AS(2, 1, 5, 0);
   AS(6, 2, 5, 0); AS(4, 2, 5, 0); AS(3, 2, 5, 0);
   AS(6, 1, 4, 0); AS(4, 1, 4, 0); AS(6, 1, 3, 0); AS(4, 1, 3, 0);
