@@ -185,3 +185,24 @@ def test_model_adapters_map_arguments_like_the_reference():
             return S - K + sigma + q + n_paths + n_steps + seed
 
     assert ob.JumpDiffusionAdapter(FakeJD(), 10, 2, 1).price(100.0, 90.0, 1.0, 0.0, 0.25, "call", q=0.5) == 10 + 0.25 + 0.5 + 10 + 2 + 1
+
+
+def test_structured_products_host_side_contracts():
+    """No GPU: the cases CliquetOption / AutocallableOption settle on the host, mirroring exotic_options.py:432-552."""
+    P_ = dict(S=100.0, K=100.0, T=1.0, r=0.05, sigma=0.2)
+    # more periods than steps: start and end index of every period are column 0, every return is 0 (:532-546)
+    assert ob.CliquetOption(**P_, seed=1).price(1000, 4, 12) == 0.0
+    assert ob.CliquetOption(**P_, seed=1, global_floor=0.02).price(1000, 4, 12) == pytest.approx(np.exp(-0.05) * 0.02 * 100.0, rel=1e-15)
+    res = ob.CliquetOption(**P_, seed=1, global_floor=0.02).price(1000, 4, 12, return_error=True)
+    assert (res.std_error, res.n_paths) == (0.0, 1000)
+    assert ob.CliquetOption(**P_, seed=1, local_floor=0.01, global_cap=0.05).price_scenarios(
+        [(100.0, 100.0, 1.0, 0.05, 0.2, 0.0), (50.0, 100.0, 2.0, 0.0, 0.2, 0.0)], n_steps=4, n_periods=12) == pytest.approx(
+        [np.exp(-0.05) * 0.05 * 100.0, 0.05 * 50.0])
+    with pytest.raises(ZeroDivisionError):          # n_steps // n_periods
+        ob.CliquetOption(**P_, seed=1).price(1000, 12, 0)
+    with pytest.raises(ValueError, match="range"):  # range(freq, n_steps + 1, freq)
+        ob.AutocallableOption(**P_, seed=1).price(1000, 12, 0)
+    a = ob.AutocallableOption(**P_, seed=1)
+    assert (a.autocall_barrier, a.coupon_barrier, a.coupon_rate, a.ki_barrier) == (1.0, 0.8, 0.10, 0.6)
+    c = ob.CliquetOption(**P_)
+    assert (c.local_cap, c.local_floor, c.global_cap, c.global_floor, c.seed) == (0.05, -0.05, 0.30, 0.0, None)
