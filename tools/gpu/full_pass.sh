@@ -20,7 +20,7 @@ python tools/bench_configs.py > gpurun_out/plain3.log 2>&1 &&
 ncu --set full --clock-control none -k regex:pathdep_kernel -c 8 -f -o /tmp/prof_pathdep_r01 python tools/bench_configs.py > gpurun_out/ncu_full2.log 2>&1
 echo "ncu pathdep exit $?"
 python tools/ncu_summary.py /tmp/prof_pathdep_r01.ncu-rep > gpurun_out/ncu_pathdep_summary.txt 2>&1
-ncu --set full --clock-control none -k "regex:qmc_european_kernel|heston_kernel|jump_kernel|structured_kernel" -c 14 -f -o /tmp/prof_models_r01 python tools/bench_configs.py > gpurun_out/ncu_full3.log 2>&1
+ncu --set full --clock-control none -k "regex:qmc_european_kernel|heston_kernel|jump_kernel|structured_kernel" -c 36 -f -o /tmp/prof_models_r01 python tools/bench_configs.py > gpurun_out/ncu_full3.log 2>&1
 echo "ncu models exit $?"
 python tools/ncu_summary.py /tmp/prof_models_r01.ncu-rep > gpurun_out/ncu_models_summary.txt 2>&1
 ncu --set full --clock-control none -k "regex:european_from_normals_tma_kernel|from_normals_kernel" -c 8 -f -o /tmp/prof_f64_r01 python tools/bench_configs.py > gpurun_out/ncu_full4.log 2>&1
