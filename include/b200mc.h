@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200MC_ABI_VERSION 4
+#define B200MC_ABI_VERSION 5
 #define B200MC_MAX_SCENARIOS 16
 
 typedef struct b200mc_engine b200mc_engine_t;
@@ -251,6 +251,22 @@ int b200mc_simulate_structured(b200mc_engine_t* eng, const b200mc_spec_t* spec, 
 int b200mc_structured_from_normals(b200mc_engine_t* eng, const b200mc_spec_t* spec, const b200mc_product_t* product,
                                    const b200mc_params_t* p, const double* Z_host, uint64_t n_paths, double* payoffs_host,
                                    b200mc_moments_t* out_host);
+
+/* ---- the simulation layer: terminal price arrays ------------------------------------------------------------------- *
+ * The array the reference's simulation backends return (src/simulation/__init__.py: simulate_terminal_prices(S, T, r,
+ * sigma, q, n_paths, n_steps, seed) -> ndarray): simulate_gbm_numpy / _fast / simulate_gbm_numba (gbm_numpy.py:15-83,
+ * gbm_numba.py:100-129) and, for the Sobol variant, simulate_gbm_qmc / _antithetic (gbm_qmc.py:14-76).
+ *   out_host[i]           = S_T of path (path_begin + i) on its draws,            i in [0, n_paths)
+ *   out_host[n_paths + i] = S_T of the mirrored path (-Z) when antithetic != 0    (the reference's concatenate layout)
+ * Values are the fused path's FP32 arithmetic on log2(S_T/S) scaled to FP64; K is unused.  This is the one call that
+ * writes per-path data to HBM (8 or 16 bytes per path, because the caller asks for the array). */
+int b200mc_terminal_prices(b200mc_engine_t* eng, const b200mc_params_t* p, uint32_t n_steps, int antithetic, uint64_t seed,
+                           uint32_t stream, uint64_t path_begin, uint64_t n_paths, double* out_host);
+/* Sobol points [point_begin, point_begin + n_points) of the sequence described by (dirnums, shift, bits) as in
+ * b200mc_simulate_sobol; point_begin must be a multiple of 4096. */
+int b200mc_terminal_prices_sobol(b200mc_engine_t* eng, const b200mc_params_t* p, uint32_t n_steps, int antithetic,
+                                 const uint32_t* dirnums_host, const uint32_t* shift_host, uint32_t bits, uint64_t point_begin,
+                                 uint64_t n_points, double* out_host);
 
 /* ---- FP64 parity mode: price from caller-supplied normal draws ------------------------------- *
  * Z is row-major [n_paths][spec->n_steps] FP64 — exactly the array the reference draws at

@@ -15,6 +15,7 @@ from .greeks import (ExerciseStyle, ExoticAdapter, HestonAdapter, JumpDiffusionA
 from .models import HestonPricer, KouJumpDiffusion, MertonJumpDiffusion
 from .monte_carlo import MCMethod, MCResult, MonteCarloPricer
 from .monte_carlo_unified import MonteCarloPricerUni
+from . import simulation
 from .validation import monte_carlo_convergence_test
 
 __version__ = "0.1.0"
@@ -23,7 +24,7 @@ __all__ = [
     "AsianOption", "BarrierOption", "LookbackOption", "AutocallableOption", "CliquetOption", "price_asian", "price_barrier",
     "price_lookback",
     "HestonPricer", "MertonJumpDiffusion", "KouJumpDiffusion",
-    "monte_carlo_convergence_test",
+    "monte_carlo_convergence_test", "simulation",
     "PricerProtocol", "ExoticAdapter", "HestonAdapter", "JumpDiffusionAdapter", "compute_greeks_unified", "greeks_heston",
     "greeks_jump_diffusion", "OptionType", "ExerciseStyle",
     "MonteCarloError", "InputValidationError", "ConvergenceError", "AccelerationError", "GreeksError",

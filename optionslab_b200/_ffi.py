@@ -17,7 +17,7 @@ from .exceptions import AccelerationError, MonteCarloError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200mc.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_SCENARIOS = 16
 
 EUROPEAN, ASIAN_ARITH, ASIAN_GEOM, BARRIER, LOOKBACK, CLIQUET, AUTOCALLABLE = range(7)
@@ -78,6 +78,8 @@ SIGNATURES = {
     "b200mc_simulate_structured": (C.c_int, [_P, C.POINTER(Spec), C.POINTER(Product), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
                                              C.c_uint64, C.c_uint64, _P]),
     "b200mc_structured_from_normals": (C.c_int, [_P, C.POINTER(Spec), C.POINTER(Product), _P, _P, C.c_uint64, _P, _P]),
+    "b200mc_terminal_prices": (C.c_int, [_P, _P, C.c_uint32, C.c_int, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _P]),
+    "b200mc_terminal_prices_sobol": (C.c_int, [_P, _P, C.c_uint32, C.c_int, _P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P]),
     "b200mc_simulate_sobol": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_uint32, C.c_uint32, _P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P]),
     "b200mc_sobol_points": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, _P]),
     "b200mc_sobol_normals": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P]),
@@ -249,6 +251,34 @@ class Engine:
                                                       pay.ctypes.data, mom.ctypes.data)
         self._check(rc, "b200mc_structured_from_normals")
         return pay, mom[0]
+
+    # -- simulation layer: terminal price arrays ------------------------------------------------
+    def terminal_prices(self, params: np.ndarray, n_steps: int, seed: int, n_paths: int, *, antithetic: bool = True, stream: int = 0,
+                        path_begin: int = 0) -> np.ndarray:
+        """-> float64 [n_paths] (or [2 n_paths]: +Z paths then their -Z mirrors, gbm_numpy.py:51)."""
+        p = np.ascontiguousarray(params, dtype=PARAMS_DTYPE).reshape(-1)
+        if p.size != 1:
+            raise MonteCarloError("terminal_prices takes one parameter set")
+        out = np.empty(int(n_paths) * (2 if antithetic else 1), dtype=np.float64)
+        rc = self._lib.b200mc_terminal_prices(self._h, p.ctypes.data, int(n_steps), int(bool(antithetic)), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                              int(stream) & 0xFFFFFFFF, int(path_begin), int(n_paths), out.ctypes.data)
+        self._check(rc, "b200mc_terminal_prices")
+        return out
+
+    def terminal_prices_sobol(self, params: np.ndarray, n_steps: int, dirnums: np.ndarray, shift: np.ndarray, bits: int, n_points: int, *,
+                              antithetic: bool = False, point_begin: int = 0) -> np.ndarray:
+        p = np.ascontiguousarray(params, dtype=PARAMS_DTYPE).reshape(-1)
+        if p.size != 1:
+            raise MonteCarloError("terminal_prices_sobol takes one parameter set")
+        dirnums = np.ascontiguousarray(dirnums, dtype=np.uint32)
+        shift = np.ascontiguousarray(shift, dtype=np.uint32)
+        if dirnums.shape != (n_steps, 32) or shift.shape != (n_steps,):
+            raise MonteCarloError("Sobol table must have shape [n_steps, 32] and shift [n_steps]")
+        out = np.empty(int(n_points) * (2 if antithetic else 1), dtype=np.float64)
+        rc = self._lib.b200mc_terminal_prices_sobol(self._h, p.ctypes.data, int(n_steps), int(bool(antithetic)), dirnums.ctypes.data,
+                                                    shift.ctypes.data, int(bits), int(point_begin), int(n_points), out.ctypes.data)
+        self._check(rc, "b200mc_terminal_prices_sobol")
+        return out
 
     # -- quasi-Monte Carlo ------------------------------------------------------------------
     def simulate_sobol(self, spec: Spec, params: np.ndarray, dirnums: np.ndarray, shift: np.ndarray, bits: int, n_points: int,

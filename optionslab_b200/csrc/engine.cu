@@ -789,9 +789,10 @@ static int upload_sobol_table(b200mc_engine_t* e, const uint32_t* dirnums_host, 
   return 0;
 }
 
-int b200mc_simulate_sobol(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_host, uint32_t n_opt,
-                          uint32_t n_scen, const uint32_t* dirnums_host, const uint32_t* shift_host, uint32_t bits,
-                          uint64_t point_begin, uint64_t n_points, b200mc_moments_t* out_host) {
+// Shared body of b200mc_simulate_sobol and b200mc_terminal_prices_sobol (terminal_host != null: also return S_T per point).
+static int sobol_run(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_host, uint32_t n_opt,
+                     uint32_t n_scen, const uint32_t* dirnums_host, const uint32_t* shift_host, uint32_t bits,
+                     uint64_t point_begin, uint64_t n_points, b200mc_moments_t* out_host, double* terminal_host, int terminal_anti) {
   if (!e) return B200MC_ERR_INVALID;
   std::lock_guard<std::mutex> g(e->mutex);
   if (int rc = check_spec(e, spec)) return rc;
@@ -841,6 +842,12 @@ int b200mc_simulate_sobol(b200mc_engine_t* e, const b200mc_spec_t* spec, const b
   a.n_points = n_points;
   a.n_opt = n_opt, a.n_scen = n_scen, a.tiles = (uint32_t)tiles, a.n_steps = spec->n_steps, a.bits = bits;
   a.is_put = spec->is_put;
+  const size_t terminal_bytes = terminal_host ? (size_t)n_points * (terminal_anti ? 2 : 1) * sizeof(double) : 0;
+  if (terminal_host) {
+    if (int rc = reserve(e, e->scratch_b, terminal_bytes)) return rc;
+    a.terminal_out = (double*)e->scratch_b.ptr;
+    a.terminal_anti = terminal_anti;
+  }
   const dim3 grid((unsigned)ctas);
   const int slot = (int)(e->timed % b200mc_engine::kRing);
   if (e->timing) CU_TRY(e, cudaEventRecord(e->ring0[slot], e->stream));
@@ -868,8 +875,54 @@ int b200mc_simulate_sobol(b200mc_engine_t* e, const b200mc_spec_t* spec, const b
   CU_TRY(e, cudaGetLastError());
   e->launches += 2;
   CU_TRY(e, cudaMemcpyAsync(pin_out, e->moments_dev.ptr, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+  if (terminal_host) CU_TRY(e, cudaMemcpyAsync(terminal_host, e->scratch_b.ptr, terminal_bytes, cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
   memcpy(out_host, pin_out, out_bytes);
+  return 0;
+}
+
+int b200mc_simulate_sobol(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_host, uint32_t n_opt,
+                          uint32_t n_scen, const uint32_t* dirnums_host, const uint32_t* shift_host, uint32_t bits,
+                          uint64_t point_begin, uint64_t n_points, b200mc_moments_t* out_host) {
+  return sobol_run(e, spec, params_host, n_opt, n_scen, dirnums_host, shift_host, bits, point_begin, n_points, out_host, nullptr, 0);
+}
+
+int b200mc_terminal_prices_sobol(b200mc_engine_t* e, const b200mc_params_t* p, uint32_t n_steps, int antithetic,
+                                 const uint32_t* dirnums_host, const uint32_t* shift_host, uint32_t bits, uint64_t point_begin,
+                                 uint64_t n_points, double* out_host) {
+  if (!e) return B200MC_ERR_INVALID;
+  if (!out_host) return fail(e, B200MC_ERR_INVALID, "out pointer is null");
+  b200mc_spec_t spec{};
+  spec.kind = B200MC_EUROPEAN, spec.n_steps = n_steps;
+  b200mc_moments_t unused;
+  return sobol_run(e, &spec, p, 1, 1, dirnums_host, shift_host, bits, point_begin, n_points, &unused, out_host, antithetic != 0);
+}
+
+int b200mc_terminal_prices(b200mc_engine_t* e, const b200mc_params_t* p, uint32_t n_steps, int antithetic, uint64_t seed, uint32_t stream,
+                           uint64_t path_begin, uint64_t n_paths, double* out_host) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  if (!p || !out_host) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
+  if (n_steps == 0 || n_paths == 0) return fail(e, B200MC_ERR_INVALID, "n_steps and n_paths must be >= 1");
+  CU_TRY(e, cudaSetDevice(e->device));
+  const size_t out_bytes = (size_t)n_paths * (antithetic ? 2 : 1) * sizeof(double);
+  if (int rc = reserve(e, e->params_dev, sizeof(b200mc_params_t))) return rc;
+  if (int rc = reserve(e, e->scratch_b, out_bytes)) return rc;
+  if (int rc = reserve_pinned(e, sizeof(b200mc_params_t))) return rc;
+  memcpy(e->pinned, p, sizeof(b200mc_params_t));
+  CU_TRY(e, cudaMemcpyAsync(e->params_dev.ptr, e->pinned, sizeof(b200mc_params_t), cudaMemcpyHostToDevice, e->stream));
+  SimArgs a{};
+  a.params = (const b200mc_params_t*)e->params_dev.ptr;
+  a.path_begin = path_begin, a.n_paths = n_paths, a.n_opt = 1, a.n_scen = 1, a.n_steps = n_steps;
+  a.rk = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32));
+  a.stream_base = stream;
+  const uint64_t want = (n_paths + kBlock - 1) / kBlock;
+  const unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)e->prop.multiProcessorCount * 48);
+  terminal_prices_kernel<<<grid, kBlock, 0, e->stream>>>(a, antithetic != 0, (double*)e->scratch_b.ptr);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 1;
+  CU_TRY(e, cudaMemcpyAsync(out_host, e->scratch_b.ptr, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
   return 0;
 }
 

@@ -432,6 +432,26 @@ __global__ void __launch_bounds__(32) fold_cv_kernel(const double* __restrict__ 
   }
 }
 
+// ================================ terminal price arrays (simulation layer) =======================
+// out[i] = S_T of path i, out[n_paths + i] = S_T of its mirror (-Z) when anti: what simulate_gbm_numpy returns
+// (gbm_numpy.py:46-51).  One parameter set; grid-stride over the paths.
+__global__ void __launch_bounds__(kBlock) terminal_prices_kernel(const SimArgs a, int anti, double* __restrict__ out) {
+  __shared__ Coef coef;
+  __shared__ double spot;
+  if (threadIdx.x == 0) {
+    coef = make_coef(a.params[0], a.n_steps, 1.0f);
+    spot = a.params[0].S;
+  }
+  __syncthreads();
+  const Coef q = coef;
+  const double S = spot;
+  for (uint64_t local = (uint64_t)blockIdx.x * kBlock + threadIdx.x; local < a.n_paths; local += (uint64_t)gridDim.x * kBlock) {
+    const float W = terminal_sum(a.path_begin + local, a.n_steps, a.stream_base, a.rk);
+    out[local] = S * (double)mufu_ex2(fmaf(q.c, W, q.a));
+    if (anti) out[a.n_paths + local] = S * (double)mufu_ex2(fmaf(-q.c, W, q.a));
+  }
+}
+
 // ================================ stream inspection kernels ====================================
 __global__ void normals_kernel(const PhiloxKeys rk, uint32_t stream, uint64_t path_begin, uint64_t n_paths,
                                uint32_t n_steps, float* __restrict__ out) {

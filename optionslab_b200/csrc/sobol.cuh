@@ -45,6 +45,8 @@ struct SobolArgs {
   uint64_t n_points;
   uint32_t n_opt, n_scen, tiles, n_steps, bits;
   int32_t is_put;
+  double* terminal_out;           // non-null: also write S_T per point ([n_points], then the mirrored [n_points] when terminal_anti)
+  int32_t terminal_anti;
 };
 
 // Phi^-1 in FP32, branch-free.  t = min(u, 1-u) in [1e-10, 1/2], y = sqrt(-2 ln t) in [1.1774, 6.7861]:
@@ -179,6 +181,17 @@ __global__ void __launch_bounds__(kBlock, NS <= 2 ? 4 : 2) qmc_european_kernel(c
   for (int i = 0; i < 2 * NS; ++i) acc[i] = 0.0f;
   const bool is_put = a.is_put != 0;
   const uint64_t first = ((uint64_t)tile * kBlock + threadIdx.x) * kPoints;  // local index of this thread's point 0
+  if (a.terminal_out) {  // simulation layer (gbm_qmc.py:44-46, :70-76): the terminal prices of scenario 0, one option
+    const QmcCoef q = coef[0];
+    const double S = a.params[0].S;
+#pragma unroll
+    for (int k = 0; k < kPoints; ++k) {
+      if (first + k < a.n_points) {
+        a.terminal_out[first + k] = S * (double)mufu_ex2(fmaf(q.c, W[k], q.a));
+        if (a.terminal_anti) a.terminal_out[a.n_points + first + k] = S * (double)mufu_ex2(fmaf(-q.c, W[k], q.a));
+      }
+    }
+  }
 #pragma unroll
   for (int k = 0; k < kPoints; ++k) {
     if (first + k < a.n_points) {
