@@ -139,3 +139,28 @@ def test_monte_carlo_convergence_test_with_fresh_seeds():
     assert out["stds"][-1] < out["stds"][0]
     assert 0.3 < out["stds"][-1] / out["expected_rate"][-1] < 3.0
     assert all(abs(v["mean"] - 10.4506) < 0.15 for v in out["results"].values())
+
+
+def test_pricers_are_thread_safe_on_one_engine():
+    """The engine serialises calls per handle (one mutex), ctypes releases the GIL: pricers used from several Python threads at
+    once must return exactly what they return one after the other (the reference's objects are single-threaded; callers such
+    as a Streamlit server are not)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import optionslab_b200 as ob
+
+    P_ = dict(S=100.0, K=100.0, T=1.0, r=0.05, sigma=0.2)
+
+    def job(i):
+        if i % 4 == 0:
+            return ob.MonteCarloPricer(50_000 + i, 16, seed=i).price(**P_, option_type="call")
+        if i % 4 == 1:
+            return float(ob.AsianOption(**P_, seed=i).price(30_000 + i, 12))
+        if i % 4 == 2:
+            return ob.MonteCarloPricerUni(20_000 + i, 8, seed=i).price_batch([100.0, 95.0], [100.0, 100.0], [1.0, 0.5], [0.05, 0.05], [0.2, 0.3], "put").tolist()
+        return float(ob.CliquetOption(**P_, seed=i).price(20_000 + i, 12, 4))
+
+    sequential = [job(i) for i in range(24)]
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        concurrent = list(pool.map(job, range(24)))
+    assert concurrent == sequential
