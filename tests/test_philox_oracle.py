@@ -20,6 +20,7 @@ def host_header_lib(tmp_path_factory):
     subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(out), os.path.join(ROOT, "tests", "host_philox.cpp")], check=True)
     lib = C.CDLL(str(out))
     lib.host_philox4x32_10.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    lib.host_philox4x32_10_keyed.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     return lib
 
 
@@ -39,6 +40,21 @@ def test_device_header_known_answers_and_matches_oracle(host_header_lib):
     host_header_lib.host_philox4x32_10(ck.ctypes.data, len(ck), out.ctypes.data)
     for i in range(0, len(ck), 97):
         np.testing.assert_array_equal(out[i], po.philox4x32_10(ck[i, :4], ck[i, 4:]))
+
+
+def test_keyed_form_used_by_the_kernels_equals_the_reference_form(host_header_lib):
+    """philox_expand_key + philox4x32_10 (round keys as launch constants, what every simulation kernel calls) against the
+    known answers and, on random counters / keys, against the textbook loop that bumps the key every round."""
+    ck = kat.kat_inputs()
+    out = np.empty((len(ck), 4), dtype=np.uint32)
+    host_header_lib.host_philox4x32_10_keyed(ck.ctypes.data, len(ck), out.ctypes.data)
+    np.testing.assert_array_equal(out, kat.kat_outputs())
+    rng = np.random.default_rng(5)
+    ck = rng.integers(0, 2**32, size=(5000, 6), dtype=np.uint64).astype(np.uint32)
+    a, b = np.empty((len(ck), 4), dtype=np.uint32), np.empty((len(ck), 4), dtype=np.uint32)
+    host_header_lib.host_philox4x32_10(ck.ctypes.data, len(ck), a.ctypes.data)
+    host_header_lib.host_philox4x32_10_keyed(ck.ctypes.data, len(ck), b.ctypes.data)
+    np.testing.assert_array_equal(a, b)
 
 
 def test_stream_layout_is_counter_based():
