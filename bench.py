@@ -10,6 +10,11 @@ CRN scenarios are NOT counted), whole job over all N GPUs.  N > 1: paths are par
 ranks (strong scaling: total work fixed) and the (sum, sum^2, n) moments are combined with ONE
 NCCL all-reduce per step.
 
+The JSON line also carries: `e2e` (MonteCarloPricerUni.price_batch with host arrays in / prices out), `roofline` (XU and
+dispatch fractions of the peaks measured live by b200mc_measure_peaks, HBM figure, ncu DRAM traffic), `cpu_baseline`
+(the NumPy restatement of the reference on one core, bounded sample), `asian_grid` (the same grid as arithmetic-average
+Asian calls, 2 passes), `z_vs_black_scholes` (z-scores of the timed prices) and `clocks` (nvidia-smi during the run).
+
   python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA engine
   python bench.py --impl reference [...]                        # the reference's NumPy algorithm on host cores
 """
