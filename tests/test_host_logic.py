@@ -206,3 +206,22 @@ def test_structured_products_host_side_contracts():
     assert (a.autocall_barrier, a.coupon_barrier, a.coupon_rate, a.ki_barrier) == (1.0, 0.8, 0.10, 0.6)
     c = ob.CliquetOption(**P_)
     assert (c.local_cap, c.local_floor, c.global_cap, c.global_floor, c.seed) == (0.05, -0.05, 0.30, 0.0, None)
+
+
+def test_monte_carlo_convergence_study_contract():
+    """validation.py:202-239: sizes 1x/2x/4x/10x, population std per size, 1/sqrt(n) law anchored at the first size,
+    `converging` = no size's spread exceeds 1.5x the previous one."""
+    rng = np.random.default_rng(3)
+    calls = []
+
+    def noisy(n):
+        calls.append(n)
+        return 10.0 + rng.standard_normal() / np.sqrt(n)
+
+    out = ob.monte_carlo_convergence_test(noisy, n_trials=9, base_sims=100)
+    assert list(out["results"]) == [100, 200, 400, 1000] and calls == [100] * 9 + [200] * 9 + [400] * 9 + [1000] * 9
+    assert set(out["results"][100]) == {"mean", "std", "min", "max"} and len(out["stds"]) == 4
+    assert out["expected_rate"] == pytest.approx([out["stds"][0] * np.sqrt(100 / n) for n in (100, 200, 400, 1000)])
+    grow = iter([0.0, 1.0] * 2 + [0.0, 10.0] * 6)
+    assert ob.monte_carlo_convergence_test(lambda n: next(grow), n_trials=4, base_sims=10)["converging"] is False
+    assert ob.monte_carlo_convergence_test(lambda n: 1.0, n_trials=3, base_sims=10)["converging"] is True
