@@ -1,6 +1,10 @@
 """Multi-GPU sharding of the Monte Carlo path: one process per GPU, paths partitioned by global
 index, ONE all-reduce of the per-(option, scenario) moments.
 
+Two ways to use several GPUs: one PROCESS per GPU (``init()`` under torchrun; what bench.py measures), or one process
+driving several devices from threads (``with local_devices(n):`` — each device has its own engine handle and stream,
+ctypes releases the GIL, the partial moments are summed on the host).  Both split the same global path range.
+
 Every (option, path) is independent: rank g of G simulates global paths
 [g*N/G, (g+1)*N/G) of every option — the Philox counter carries the global path index, so the
 draws are disjoint by construction and independent of G — and the only exchanged data are the
@@ -16,7 +20,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-__all__ = ["ShardContext", "init", "shutdown", "current", "partition_paths", "allreduce_moments"]
+__all__ = ["ShardContext", "init", "shutdown", "current", "partition_paths", "allreduce_moments", "run_sharded", "local_devices"]
 
 
 @dataclass
@@ -95,3 +99,58 @@ def allreduce_moments(moments: np.ndarray, ctx: Optional[ShardContext] = None) -
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     out = t.cpu().numpy().view(moments.dtype).reshape(moments.shape)
     return out
+
+
+# ---- one process, several devices --------------------------------------------------------------------------------
+_local: Optional[Tuple[int, ...]] = None
+
+
+class local_devices:
+    """``with local_devices(4): pricer.price(...)`` — split every simulation over CUDA devices 0..3 of THIS process (or over
+    an explicit list of device indices).  Not combinable with the process-group mode."""
+
+    def __init__(self, devices):
+        self.devices = tuple(range(devices)) if isinstance(devices, int) else tuple(int(d) for d in devices)
+        if not self.devices:
+            raise ValueError("at least one device")
+
+    def __enter__(self):
+        global _local
+        if _ctx is not None and _ctx.world_size > 1:
+            raise RuntimeError("local_devices cannot be nested inside a multi-process shard context")
+        self._previous, _local = _local, self.devices
+        return self
+
+    def __exit__(self, *exc):
+        global _local
+        _local = self._previous
+        return False
+
+
+def run_sharded(fn, n_units: int, empty, partition=partition_paths) -> np.ndarray:
+    """Run ``fn(engine, begin, count) -> moments`` over this process's share of ``n_units`` global paths (or Sobol points)
+    and return the moments of ALL units: plain call when unsharded, threads + host sum under ``local_devices``, partition +
+    all-reduce under a process group.  ``empty()`` builds the zero moments of a shard that received no unit."""
+    from . import _ffi
+
+    ctx = _ctx
+    if _local is not None and len(_local) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+
+        def one(i):
+            begin, count = partition(n_units, i, len(_local))
+            return fn(_ffi.get_engine(_local[i]), begin, count) if count > 0 else empty()
+
+        with ThreadPoolExecutor(max_workers=len(_local)) as pool:
+            parts = list(pool.map(one, range(len(_local))))
+        total = np.ascontiguousarray(parts[0]).copy()
+        flat = total.view(np.float64)
+        for part in parts[1:]:
+            flat += np.ascontiguousarray(part).view(np.float64)
+        return total
+    eng = _ffi.get_engine(_local[0]) if _local else _ffi.get_engine()
+    if ctx is None or ctx.world_size == 1:
+        return fn(eng, 0, n_units)
+    begin, count = partition(n_units, ctx.rank, ctx.world_size)
+    local = fn(eng, begin, count) if count > 0 else empty()
+    return allreduce_moments(local, ctx)

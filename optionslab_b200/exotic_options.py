@@ -140,19 +140,12 @@ def _run_structured(opt: ExoticOptionBase, spec, product, scenarios: Sequence, n
 
     sc = np.asarray(scenarios, dtype=np.float64).reshape(-1, 6)
     seed = opt._seed()
-    eng = _ffi.get_engine()
-    ctx = distributed.current()
     out = []
     for lo in range(0, len(sc), _ffi.MAX_SCENARIOS):
         blk = sc[lo:lo + _ffi.MAX_SCENARIOS]
         params = _ffi.make_params(blk[:, 0], blk[:, 1], blk[:, 2], blk[:, 3], blk[:, 4], blk[:, 5])[None, :]
-        if ctx is None or ctx.world_size == 1:
-            m = eng.simulate_structured(spec, product, params, seed, n_paths)
-        else:
-            begin, count = distributed.partition_paths(n_paths, ctx.rank, ctx.world_size)
-            local = (eng.simulate_structured(spec, product, params, seed, count, path_begin=begin) if count > 0
-                     else np.zeros(params.shape, dtype=_ffi.MOMENTS_DTYPE))
-            m = distributed.allreduce_moments(local, ctx)
+        m = distributed.run_sharded(lambda eng, begin, count: eng.simulate_structured(spec, product, params, seed, count, path_begin=begin),
+                                    n_paths, lambda: np.zeros(params.shape, dtype=_ffi.MOMENTS_DTYPE))
         out.append(m[0])
     return np.concatenate(out), sc
 

@@ -20,13 +20,8 @@ __all__ = ["HestonPricer", "MertonJumpDiffusion", "KouJumpDiffusion"]
 
 
 def _sharded(run, n_paths: int, n_out: int = 1) -> np.ndarray:
-    """Run ``run(path_begin, count)`` on this rank's slice of the global paths and all-reduce the moments."""
-    ctx = distributed.current()
-    if ctx is None or ctx.world_size == 1:
-        return run(0, n_paths)
-    begin, count = distributed.partition_paths(n_paths, ctx.rank, ctx.world_size)
-    local = run(begin, count) if count > 0 else np.zeros(n_out, dtype=_ffi.MOMENTS_DTYPE)
-    return distributed.allreduce_moments(local, ctx)
+    """``run(engine, path_begin, count)`` over this process's / device's share of the global paths, moments combined."""
+    return distributed.run_sharded(run, n_paths, lambda: np.zeros(n_out, dtype=_ffi.MOMENTS_DTYPE))
 
 
 @dataclass
@@ -65,8 +60,7 @@ class HestonPricer:
                           ("sigma_v", self.sigma_v), ("rho", self.rho), ("v0", self.v0)):
             params[name] = val
         is_put = option_type != "call"  # heston.py:249-252
-        eng = _ffi.get_engine()
-        m = _sharded(lambda b, c: eng.simulate_heston(params, is_put, n_steps, actual_seed, c, path_begin=b), int(n_paths))[0]
+        m = _sharded(lambda eng, b, c: eng.simulate_heston(params, is_put, n_steps, actual_seed, c, path_begin=b), int(n_paths))[0]
         price = float(runtime.discounted_price(m, r, T))
         if return_error:
             return price, float(runtime.discounted_std_error(m, r, T))
@@ -79,9 +73,8 @@ class HestonPricer:
         params = np.zeros(len(sc), dtype=_ffi.HESTON_PARAMS_DTYPE)
         params["S"], params["K"], params["T"], params["r"], params["v0"], params["q"] = sc.T
         params["kappa"], params["theta"], params["sigma_v"], params["rho"] = self.kappa, self.theta, self.sigma_v, self.rho
-        eng = _ffi.get_engine()
-        m = _sharded(lambda b, c: eng.simulate_heston(params, option_type != "call", n_steps, int(seed), c, path_begin=b,
-                                                      shared_stream=True), int(n_paths), len(sc))
+        m = _sharded(lambda eng, b, c: eng.simulate_heston(params, option_type != "call", n_steps, int(seed), c, path_begin=b,
+                                                           shared_stream=True), int(n_paths), len(sc))
         return [float(x) for x in runtime.discounted_price(m, sc[:, 3], sc[:, 2])]
 
 
@@ -90,9 +83,8 @@ def _jump_scenarios(model: int, lambda_j: float, a: float, b: float, c: float, s
     params = _ffi.make_params(sc[:, 0], sc[:, 1], sc[:, 2], sc[:, 3], sc[:, 4], sc[:, 5])
     jumps = np.zeros(len(sc), dtype=_ffi.JUMP_PARAMS_DTYPE)
     jumps["model"], jumps["lambda_j"], jumps["a"], jumps["b"], jumps["c"] = model, lambda_j, a, b, c
-    eng = _ffi.get_engine()
-    m = _sharded(lambda b_, c_: eng.simulate_jump_diffusion(params, jumps, option_type != "call", n_steps, int(seed), c_, path_begin=b_,
-                                                            shared_stream=True), int(n_paths), len(sc))
+    m = _sharded(lambda eng, b_, c_: eng.simulate_jump_diffusion(params, jumps, option_type != "call", n_steps, int(seed), c_, path_begin=b_,
+                                                                 shared_stream=True), int(n_paths), len(sc))
     return [float(x) for x in runtime.discounted_price(m, sc[:, 3], sc[:, 2])]
 
 
@@ -103,8 +95,7 @@ def _jump_price(model: int, lambda_j: float, a: float, b: float, c: float, S, K,
     jumps = np.zeros(1, dtype=_ffi.JUMP_PARAMS_DTYPE)
     jumps["model"], jumps["lambda_j"], jumps["a"], jumps["b"], jumps["c"] = model, lambda_j, a, b, c
     is_put = option_type != "call"
-    eng = _ffi.get_engine()
-    m = _sharded(lambda b_, c_: eng.simulate_jump_diffusion(params, jumps, is_put, n_steps, actual_seed, c_, path_begin=b_), int(n_paths))[0]
+    m = _sharded(lambda eng, b_, c_: eng.simulate_jump_diffusion(params, jumps, is_put, n_steps, actual_seed, c_, path_begin=b_), int(n_paths))[0]
     price = float(runtime.discounted_price(m, r, T))
     if return_error:
         return price, float(runtime.discounted_std_error(m, r, T))

@@ -31,17 +31,11 @@ def simulate(spec: _ffi.Spec, params: np.ndarray, seed: int, n_paths: int, *, st
     combination across ranks is one element-wise all-reduce."""
     if n_paths < 1:
         raise MonteCarloError("n_paths must be >= 1")
-    eng = _ffi.get_engine()
-    ctx = distributed.current()
-    if ctx is None or ctx.world_size == 1:
-        return eng.simulate(spec, params, seed, n_paths, stream_base=stream_base, control_variate=control_variate)
-    begin, count = distributed.partition_paths(n_paths, ctx.rank, ctx.world_size)
-    if count > 0:
-        local = eng.simulate(spec, params, seed, count, stream_base=stream_base, path_begin=begin,
-                             control_variate=control_variate)
-    else:
-        local = np.zeros(np.shape(params), dtype=_ffi.CV_MOMENTS_DTYPE if control_variate else _ffi.MOMENTS_DTYPE)
-    return distributed.allreduce_moments(local, ctx)
+    dtype = _ffi.CV_MOMENTS_DTYPE if control_variate else _ffi.MOMENTS_DTYPE
+    return distributed.run_sharded(
+        lambda eng, begin, count: eng.simulate(spec, params, seed, count, stream_base=stream_base, path_begin=begin,
+                                               control_variate=control_variate),
+        n_paths, lambda: np.zeros(np.shape(params), dtype=dtype))
 
 
 def simulate_sobol(spec: _ffi.Spec, params: np.ndarray, seed, n_points: int) -> np.ndarray:
@@ -52,16 +46,9 @@ def simulate_sobol(spec: _ffi.Spec, params: np.ndarray, seed, n_points: int) -> 
     table, shift, bits = sobol.sobol_table(spec.n_steps, seed)
     if n_points > (1 << bits):
         raise MonteCarloError(f"a {bits}-bit Sobol sequence has 2^{bits} points; asked for {n_points}")
-    eng = _ffi.get_engine()
-    ctx = distributed.current()
-    if ctx is None or ctx.world_size == 1:
-        return eng.simulate_sobol(spec, params, table, shift, bits, n_points)
-    begin, count = sobol.partition_points(n_points, ctx.rank, ctx.world_size)
-    if count > 0:
-        local = eng.simulate_sobol(spec, params, table, shift, bits, count, point_begin=begin)
-    else:
-        local = np.zeros(np.shape(params), dtype=_ffi.MOMENTS_DTYPE)
-    return distributed.allreduce_moments(local, ctx)
+    return distributed.run_sharded(
+        lambda eng, begin, count: eng.simulate_sobol(spec, params, table, shift, bits, count, point_begin=begin),
+        n_points, lambda: np.zeros(np.shape(params), dtype=_ffi.MOMENTS_DTYPE), partition=sobol.partition_points)
 
 
 def control_variate_price(m, S, T, r, q) -> float:

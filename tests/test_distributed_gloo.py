@@ -136,3 +136,34 @@ def test_pricer_classes_shard_paths_and_allreduce(tmp_path, monkeypatch):
     for rank in range(2):
         np.testing.assert_allclose(np.load(os.path.join(tmp_path, f"pricers{rank}.npy")), whole, rtol=1e-12)
     assert whole[2] == 2 * N_PATHS and whole[8] == N_PATHS  # antithetic European counts 2N samples, the Asian N
+
+
+def test_local_devices_mode_splits_paths_over_engines_and_sums(monkeypatch):
+    """One process, several devices: every device's engine gets its slice of the global path range (threads), the partial
+    moments are summed on the host; the prices equal the single-engine ones.  Engines are oracle stand-ins here."""
+    import optionslab_b200 as ob
+
+    seen = []
+
+    class Recording(_OracleEngine):
+        def __init__(self, device):
+            self.device = device
+
+        def simulate(self, spec, params, seed, n_paths, **kw):
+            seen.append((self.device, kw.get("path_begin", 0), n_paths))
+            return super().simulate(spec, params, seed, n_paths, **kw)
+
+    engines = {}
+    monkeypatch.setattr(_ffi, "get_engine", lambda device=None: engines.setdefault(device or 0, Recording(device or 0)))
+    distributed.shutdown()
+    pr = ob.MonteCarloPricer(N_PATHS, N_STEPS, seed=SEED)
+    whole = pr.price(**P, option_type="call", return_error=True)
+    seen.clear()
+    with distributed.local_devices(3):
+        split = pr.price(**P, option_type="call", return_error=True)
+        asian = ob.AsianOption(**P, seed=SEED).price(n_paths=N_PATHS, n_steps=N_STEPS)
+    assert sorted(seen[:3]) == [(0, 0, 3334), (1, 3334, 3334), (2, 6668, 3333)]
+    assert split.n_paths == whole.n_paths and split.price == pytest.approx(whole.price, rel=1e-12) and split.std_error == pytest.approx(whole.std_error, rel=1e-12)
+    assert asian == pytest.approx(ob.AsianOption(**P, seed=SEED).price(n_paths=N_PATHS, n_steps=N_STEPS), rel=1e-12)
+    with distributed.local_devices([0]):  # a single device is the plain path
+        assert pr.price(**P, option_type="call") == pytest.approx(whole.price, rel=1e-15)

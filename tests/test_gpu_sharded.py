@@ -76,3 +76,41 @@ def test_two_ranks_reproduce_single_process_prices(tmp_path):
     a = json.load(open(os.path.join(tmp_path, "rank0.json")))
     b = json.load(open(os.path.join(tmp_path, "rank1.json")))
     assert a == b  # every rank holds the identical all-reduced result
+
+
+def test_local_devices_mode_on_two_gpus():
+    """One process driving two GPUs from threads (distributed.local_devices): same global paths, host-side sum."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in this process")
+    import optionslab_b200 as ob
+    from optionslab_b200 import distributed
+
+    distributed.shutdown()
+    whole = _prices()
+    with distributed.local_devices(2):
+        split = _prices()
+    assert split["euro"][2] == whole["euro"][2]
+    assert split["euro"][0] == pytest.approx(whole["euro"][0], rel=1e-6)
+    for k in ("asian", "barrier", "autocall", "kou", "qmc"):
+        assert split[k] == pytest.approx(whole[k], rel=1e-6), k
+    np.testing.assert_allclose(split["batch"], whole["batch"], rtol=1e-6)
+    np.testing.assert_allclose(split["cliquet"], whole["cliquet"], rtol=1e-6)
+    np.testing.assert_allclose(split["heston"], whole["heston"], rtol=1e-6)
+    # and it scales: 2 devices on a grid large enough to amortise the threads
+    import time
+
+    g = dict(S=np.full(512, 100.0), K=np.linspace(60, 140, 512), T=np.full(512, 1.0), r=np.full(512, 0.05), sigma=np.full(512, 0.2))
+    uni = ob.MonteCarloPricerUni(1_000_000, 252, seed=1)
+    uni.price_batch(g["S"], g["K"], g["T"], g["r"], g["sigma"], "call")
+    t0 = time.perf_counter()
+    one = uni.price_batch(g["S"], g["K"], g["T"], g["r"], g["sigma"], "call")
+    t1 = time.perf_counter()
+    with distributed.local_devices(2):
+        uni.price_batch(g["S"], g["K"], g["T"], g["r"], g["sigma"], "call")
+        t2 = time.perf_counter()
+        two = uni.price_batch(g["S"], g["K"], g["T"], g["r"], g["sigma"], "call")
+        t3 = time.perf_counter()
+    np.testing.assert_allclose(two, one, rtol=1e-6)
+    assert (t3 - t2) < 0.65 * (t1 - t0), (t1 - t0, t3 - t2)
