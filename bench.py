@@ -369,7 +369,7 @@ def run_engine_arm(args):
         cores = os.cpu_count() or 1
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            idx = list(np.linspace(0, N_OPT - 1, 8).astype(int))
+            idx = list(np.linspace(0, N_OPT - 1, 40).astype(int))  # ~12 s of single-core NumPy work
             cpu_sample(idx[:1], 2_000, 1)
             t_cpu, cpu_prices = cpu_sample(idx, 100_000, 1)
             cpu = {"value": len(idx) * 100_000 * N_STEPS / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
