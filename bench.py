@@ -162,12 +162,27 @@ def run_reference_arm(args):
     value = work / total_t
     sample = (f"{per_step} grid options x {n_paths} paths x {N_STEPS} steps per step, NumPy restatement of "
               f"simulate_gbm_numpy+payoff (oracle/reference_mc.py), one process per core over options")
+    # the reference's own multi-core backend (MCMethod.NUMBA, prange over paths) beside it, when numba is present
+    numba_line = None
+    try:
+        from oracle import reference_mc as orc
+        import numba
+
+        orc.numba_backend_terminal(100.0, 1.0, 0.05, 0.2, 0.0, 1000, N_STEPS, SEED)  # JIT
+        t0 = time.perf_counter()
+        term = orc.numba_backend_terminal(100.0, 1.0, 0.05, 0.2, 0.0, 400_000, N_STEPS, SEED)
+        dt_numba = time.perf_counter() - t0
+        numba_line = {"value": 400_000 * N_STEPS / dt_numba, "unit": UNIT, "threads": int(numba.get_num_threads()),
+                      "sample": f"1 option x 400000 paths x {N_STEPS} steps, restatement of _gbm_terminal_parallel (gbm_numba.py:74-97)",
+                      "mean_terminal": float(term.mean())}
+    except Exception as exc:  # numba missing or unusable on this host: the NumPy arm above stands alone
+        numba_line = {"unavailable": repr(exc)}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "numba_prange": numba_line}
     print(json.dumps(line))
     return 0
 

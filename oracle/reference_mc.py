@@ -525,6 +525,41 @@ def cpu_grid_sample(option_indices, num_simulations, num_steps, seed, option_typ
 # --------------------------------------------------------------------------
 
 
+_NUMBA_TERMINAL = None
+
+
+def numba_backend_terminal(S, T, r, sigma, q, n_paths, n_steps, seed):
+    """The reference's multi-core backend, MCMethod.NUMBA -> ``_gbm_terminal_parallel`` (src/simulation/gbm_numba.py:74-97),
+    restated for TIMING on the host cores: a prange over paths, each path re-seeding Numba's per-thread generator with
+    ``seed + i`` and walking its steps with both mirrored log-prices.  Returns 2 * n_paths terminal prices ([i] = +z path,
+    [i + n_paths] = -z path).  Needs numba; raises ImportError otherwise."""
+    global _NUMBA_TERMINAL
+    if _NUMBA_TERMINAL is None:
+        import numba
+
+        @numba.njit(parallel=True, fastmath=True)
+        def kernel(S, T, r, sigma, q, n_paths, n_steps, seed):
+            dt = T / n_steps
+            mu = (r - q - 0.5 * sigma * sigma) * dt
+            vol = sigma * np.sqrt(dt)
+            start = np.log(S)
+            out = np.empty(2 * n_paths)
+            for i in numba.prange(n_paths):
+                np.random.seed(seed + i)
+                up = start
+                down = start
+                for _ in range(n_steps):
+                    z = np.random.randn()
+                    up += mu + vol * z
+                    down += mu - vol * z
+                out[i] = np.exp(up)
+                out[n_paths + i] = np.exp(down)
+            return out
+
+        _NUMBA_TERMINAL = kernel
+    return _NUMBA_TERMINAL(float(S), float(T), float(r), float(sigma), float(q), int(n_paths), int(n_steps), int(seed))
+
+
 def heston_draws(seed: Optional[int], n_paths: int, n_steps: int) -> np.ndarray:
     """The normals ``HestonPricer.price_monte_carlo`` consumes, in its order: per step ``standard_normal(n_paths)``
     for Z1 and again for the independent part of Z2 (src/pricing_models/heston.py:207-229, legacy global

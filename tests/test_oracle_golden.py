@@ -251,3 +251,16 @@ def test_structured_products_with_dividend_and_adapter_greeks(goldens):
     out = orc.greeks_bump_and_revalue(fn, **P)
     for k, v in sp["cliquet_adapter_greeks_20000x36"].items():
         assert out[k] == pytest.approx(v, rel=1e-8, abs=1e-8), k
+
+
+def test_numba_backend_restatement_has_the_reference_layout_and_law():
+    """gbm_numba.py:74-97 restated for the CPU timing arm: 2N values, [i] and [i+N] mirrored (their product is
+    S^2 exp(2 (r-q-sigma^2/2) T) exactly), seeded per path, mean = forward within 4 standard errors."""
+    pytest.importorskip("numba")
+    n, steps = 20000, 16
+    out = orc.numba_backend_terminal(100.0, 1.0, 0.05, 0.2, 0.01, n, steps, 42)
+    assert out.shape == (2 * n,)
+    np.testing.assert_allclose(out[:n] * out[n:], 100.0**2 * np.exp(2 * (0.05 - 0.01 - 0.02) * 1.0), rtol=1e-12)
+    assert abs(out.mean() - 100.0 * np.exp(0.04)) < 4 * out.std() / np.sqrt(2 * n)
+    again = orc.numba_backend_terminal(100.0, 1.0, 0.05, 0.2, 0.01, n, steps, 42)
+    assert np.array_equal(out, again)  # per-path seeding: deterministic for any thread count
