@@ -334,3 +334,33 @@ def test_discrete_geometric_asian_matches_its_exact_lognormal_law(engine):
                                     2024 + n_steps, n_paths)[0, 0]
                 price, se = _price_se(m, r, T)
                 assert abs(price - want) <= 4 * se, (n_steps, K, ot, price, want, se)
+
+
+def test_randomised_cases_against_black_scholes_and_the_fp64_oracle(engine):
+    """60 random (S, K, T, r, sigma, q, n_paths, n_steps) draws over wide ranges: ragged path / step counts exercise the
+    tile planner and the trailing-step code; every price must sit within 4.5 standard errors of the closed form, and on the
+    small cases the FP32 sums must match the FP64 oracle evaluation of the same Philox stream to 3e-4."""
+    rng = np.random.default_rng(20260)
+    worst = 0.0
+    for case in range(60):
+        S = float(rng.uniform(5.0, 500.0))
+        K = S * float(rng.uniform(0.7, 1.4))
+        T = float(rng.uniform(0.02, 3.0))
+        r, q = float(rng.uniform(-0.01, 0.08)), float(rng.uniform(0.0, 0.05))
+        sigma = float(rng.uniform(0.05, 0.8))
+        n_steps = int(rng.integers(1, 400))
+        n_paths = int(rng.integers(1_000, 300_000))
+        ot = "call" if case % 2 == 0 else "put"
+        res = ob.MonteCarloPricer(n_paths, n_steps, seed=case).price(S, K, T, r, sigma, ot, q=q, return_error=True)
+        bs = orc.black_scholes(S, K, T, r, sigma, ot, q)
+        assert res.n_paths == 2 * n_paths
+        z = abs(res.price - bs) / max(res.std_error, 1e-12 * S)
+        worst = max(worst, z)
+        assert z < 4.5 or abs(res.price - bs) < 1e-6 * S, (case, S, K, T, r, sigma, q, n_paths, n_steps, res.price, bs, res.std_error)
+        if n_paths * n_steps < 4_000_000:
+            Z = po.normals(case, n_paths, n_steps)
+            pay = orc.vanilla_payoffs(orc.gbm_terminal_from_normals(S, T, r, sigma, q, Z), K, ot)
+            m = engine.simulate(_ffi.make_spec(_ffi.EUROPEAN, n_steps, is_put=ot == "put", antithetic=True),
+                                _ffi.make_params(S, K, T, r, sigma, q).reshape(1, 1), case, n_paths)[0, 0]
+            assert m["sum"] == pytest.approx(pay.sum(), rel=3e-4, abs=1e-6 * S * n_paths), case
+    assert worst > 0.5  # the test is alive
