@@ -364,3 +364,51 @@ def test_randomised_cases_against_black_scholes_and_the_fp64_oracle(engine):
                                 _ffi.make_params(S, K, T, r, sigma, q).reshape(1, 1), case, n_paths)[0, 0]
             assert m["sum"] == pytest.approx(pay.sum(), rel=3e-4, abs=1e-6 * S * n_paths), case
     assert worst > 0.5  # the test is alive
+
+
+def test_randomised_path_dependent_cases_against_the_fp64_oracle(engine):
+    """40 random path-dependent cases (kind, flags, S, K, T, r, sigma, q, barrier, n_paths, n_steps): the fused FP32 kernels
+    against the FP64 oracle evaluation of the same Philox stream.  Barrier-type payoffs may flip for a path within FP32
+    rounding of the barrier, hence an absolute slack of a few payoffs."""
+    rng = np.random.default_rng(777)
+    for case in range(40):
+        S = float(rng.uniform(20.0, 300.0))
+        K = S * float(rng.uniform(0.8, 1.25))
+        T = float(rng.uniform(0.05, 2.0))
+        r, q = float(rng.uniform(0.0, 0.07)), float(rng.uniform(0.0, 0.04))
+        sigma = float(rng.uniform(0.08, 0.9))  # beyond ~0.5 the arithmetic Asian leaves the small-move form
+        n_steps = int(rng.integers(2, 120))
+        n_paths = int(rng.integers(500, 30_000))
+        is_put = bool(rng.integers(0, 2))
+        ot = "put" if is_put else "call"
+        Z = po.normals(1000 + case, n_paths, n_steps)
+        paths = orc.exotic_paths_from_normals(S, T, r, sigma, q, Z)
+        kind = case % 5
+        B, slack = 0.0, 0.0
+        if kind == 0:
+            spec, want = _ffi.make_spec(_ffi.ASIAN_ARITH, n_steps, is_put=is_put), orc.asian_payoffs(paths, K, "arithmetic", ot)
+        elif kind == 1:
+            spec, want = _ffi.make_spec(_ffi.ASIAN_GEOM, n_steps, is_put=is_put), orc.asian_payoffs(paths, K, "geometric", ot)
+        elif kind == 2:
+            down, knock_in = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+            B = S * (float(rng.uniform(0.7, 0.97)) if down else float(rng.uniform(1.03, 1.4)))
+            bt = ("down" if down else "up") + "-and-" + ("in" if knock_in else "out")
+            spec, want = _ffi.make_spec(_ffi.BARRIER, n_steps, is_put=is_put, barrier_down=down, barrier_in=knock_in), orc.barrier_payoffs(paths, K, B, bt, ot)
+            slack = 3.0 * S
+        elif kind == 3:
+            fixed = bool(rng.integers(0, 2))
+            spec, want = (_ffi.make_spec(_ffi.LOOKBACK, n_steps, is_put=is_put, lookback_fixed=fixed),
+                          orc.lookback_payoffs(paths, K, "fixed" if fixed else "floating", ot))
+        else:
+            nper = int(rng.integers(1, n_steps + 1))
+            terms = dict(local_cap=float(rng.uniform(0.01, 0.1)), local_floor=-float(rng.uniform(0.0, 0.1)),
+                         global_cap=float(rng.uniform(0.1, 0.6)), global_floor=float(rng.uniform(-0.1, 0.05)))
+            want = orc.cliquet_payoffs(paths, S, n_periods=nper, **terms)
+            m = engine.simulate_structured(_ffi.make_spec(_ffi.CLIQUET, n_steps), _ffi.Product(terms["local_cap"], terms["local_floor"], terms["global_cap"],
+                                                                                             terms["global_floor"], nper, 0),
+                                           _ffi.make_params(S, K, T, r, sigma, q).reshape(1, 1), 1000 + case, n_paths)[0, 0]
+            assert m["sum"] == pytest.approx(want.sum(), rel=5e-4, abs=1e-4 * S * n_paths), (case, nper, terms)
+            continue
+        m = engine.simulate(spec, _ffi.make_params(S, K, T, r, sigma, q, B).reshape(1, 1), 1000 + case, n_paths)[0, 0]
+        assert m["n"] == n_paths
+        assert m["sum"] == pytest.approx(want.sum(), rel=5e-4, abs=slack + 1e-6 * S * n_paths), (case, kind, S, K, T, sigma, n_paths, n_steps)
