@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200MC_ABI_VERSION 5
+#define B200MC_ABI_VERSION 6
 #define B200MC_MAX_SCENARIOS 16
 
 typedef struct b200mc_engine b200mc_engine_t;
@@ -298,6 +298,12 @@ int b200mc_philox_raw(b200mc_engine_t* eng, const uint32_t* ctr_key_host, uint32
 int b200mc_measure_peaks(b200mc_engine_t* eng, b200mc_peaks_t* out);
 /* Kernels launched by this engine since creation (the caller's gpu_launches evidence). */
 uint64_t b200mc_kernel_launches(const b200mc_engine_t* eng);
+/* Tuning / tests: pin the tile shape the planner would otherwise choose from the problem size.  split_shift: 2^split_shift
+ * adjacent lanes share each European path (0..3; < 0 = automatic); paths_per_thread: 1..32 (0 = automatic).  Prices do not
+ * depend on the shape beyond FP32 summation order (~1e-7 relative). */
+int b200mc_set_plan(b200mc_engine_t* eng, int split_shift, uint32_t paths_per_thread);
+/* The tile shape of the most recent b200mc_simulate* launch: tiles per option, paths per thread, split shift. */
+int b200mc_last_plan(b200mc_engine_t* eng, uint32_t* tiles, uint32_t* paths_per_thread, uint32_t* split_shift);
 /* When enabled, every simulation / from-normals kernel is bracketed by a CUDA event pair on the
  * stream it is launched on (a ring of 64 pairs; enabling resets it).  b200mc_kernel_timing waits for
  * the recorded kernels and returns their mean and minimum duration and how many were timed. */

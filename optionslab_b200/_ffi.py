@@ -7,6 +7,7 @@ sm_100 device is present, ``AccelerationError`` is raised.  Nothing here imports
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 import threading
 from typing import Optional
@@ -17,7 +18,7 @@ from .exceptions import AccelerationError, MonteCarloError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200mc.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_SCENARIOS = 16
 
 EUROPEAN, ASIAN_ARITH, ASIAN_GEOM, BARRIER, LOOKBACK, CLIQUET, AUTOCALLABLE = range(7)
@@ -94,6 +95,8 @@ SIGNATURES = {
     "b200mc_philox_raw": (C.c_int, [_P, _P, C.c_uint32, _P]),
     "b200mc_measure_peaks": (C.c_int, [_P, C.POINTER(Peaks)]),
     "b200mc_kernel_launches": (C.c_uint64, [_P]),
+    "b200mc_set_plan": (C.c_int, [_P, C.c_int, C.c_uint32]),
+    "b200mc_last_plan": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "b200mc_set_kernel_timing": (C.c_int, [_P, C.c_int]),
     "b200mc_kernel_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
@@ -126,8 +129,10 @@ def load_library():
         return lib
 
 
+@functools.lru_cache(maxsize=512)
 def make_spec(kind: int, n_steps: int, *, is_put=False, antithetic=False, barrier_down=False, barrier_in=False,
               lookback_fixed=False, exact_ex2=False, no_bulk_copy=False) -> Spec:
+    """The launch description.  Cached: callers treat the returned struct as read-only."""
     return Spec(int(kind), int(bool(is_put)), int(bool(antithetic)), int(bool(barrier_down)), int(bool(barrier_in)),
                 int(bool(lookback_fixed)), int(n_steps), (FLAG_EXACT_EX2 if exact_ex2 else 0) | (FLAG_NO_BULK_COPY if no_bulk_copy else 0))
 
@@ -155,6 +160,7 @@ class Engine:
             msg = self._lib.b200mc_last_error(None).decode()
             raise AccelerationError(f"b200mc_create({self.device}) failed: {msg}", backend="cuda")
         self._h = h
+        self._tls = threading.local()  # per-thread staging buffers of simulate_scalars
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -186,6 +192,15 @@ class Engine:
     def kernel_launches(self) -> int:
         return int(self._lib.b200mc_kernel_launches(self._h))
 
+    def set_plan(self, split_shift: int = -1, paths_per_thread: int = 0):
+        """Pin the tile shape (tuning / tests); the defaults restore the automatic plan."""
+        self._check(self._lib.b200mc_set_plan(self._h, int(split_shift), int(paths_per_thread)), "b200mc_set_plan")
+
+    def last_plan(self) -> dict:
+        t, p, sft = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._check(self._lib.b200mc_last_plan(self._h, C.byref(t), C.byref(p), C.byref(sft)), "b200mc_last_plan")
+        return {"tiles": int(t.value), "paths_per_thread": int(p.value), "split_shift": int(sft.value)}
+
     def set_kernel_timing(self, enabled: bool):
         self._check(self._lib.b200mc_set_kernel_timing(self._h, int(enabled)), "b200mc_set_kernel_timing")
 
@@ -213,6 +228,31 @@ class Engine:
                 int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF, int(path_begin), int(n_paths), out.ctypes.data)
         self._check(rc, "b200mc_simulate_control_variate" if control_variate else "b200mc_simulate")
         return out
+
+    def simulate_scalars(self, spec: Spec, scenarios, seed: int, n_paths: int, *, barrier: float = 0.0, stream_base: int = 0,
+                         path_begin: int = 0):
+        """Latency path for ONE option: ``scenarios`` = up to 16 (S, K, T, r, sigma, q) tuples on common random numbers ->
+        list of (sum, sum_sq, n) tuples.  No NumPy on the way: the parameter block is filled into a preallocated ctypes
+        buffer and the C side launches one kernel whose arguments carry the coefficients and whose finishing CTA writes
+        the moments into mapped pinned memory (b200mc_simulate, n_opt == 1)."""
+        n = len(scenarios)
+        if not 1 <= n <= MAX_SCENARIOS:
+            raise MonteCarloError(f"between 1 and {MAX_SCENARIOS} scenarios per launch")
+        tls = self._tls
+        try:
+            buf_in, buf_out = tls.buf_in, tls.buf_out
+        except AttributeError:
+            buf_in = tls.buf_in = (C.c_double * (8 * MAX_SCENARIOS))()
+            buf_out = tls.buf_out = (C.c_double * (3 * MAX_SCENARIOS))()
+        b = float(barrier)
+        for k, sc in enumerate(scenarios):
+            buf_in[8 * k:8 * k + 8] = (sc[0], sc[1], sc[2], sc[3], sc[4], sc[5], b, 0.0)
+        rc = self._lib.b200mc_simulate(self._h, C.byref(spec), buf_in, 1, n, int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF,
+                                       int(path_begin), int(n_paths), buf_out)
+        if rc != 0:
+            self._check(rc, "b200mc_simulate")
+        out = buf_out[0:3 * n]
+        return [(out[3 * k], out[3 * k + 1], out[3 * k + 2]) for k in range(n)]
 
     def simulate_device(self, spec: Spec, params_ptr: int, n_opt: int, n_scen: int, seed: int, n_paths: int, out_ptr: int,
                         cuda_stream: int, *, stream_base: int = 0, path_begin: int = 0):

@@ -42,9 +42,21 @@ struct b200mc_engine {
   cudaDeviceProp prop{};
   std::string error;
   std::mutex mutex;  // one call at a time per engine (the reference's pricer objects are single-threaded too)
-  DeviceBuffer partials, params_dev, moments_dev, scratch_a, scratch_b;
+  DeviceBuffer partials, tickets, params_dev, moments_dev, scratch_a, scratch_b;
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
+  // single-option launches: parameters ride in the kernel arguments, the finishing CTA writes the records straight into
+  // this mapped pinned block and then the sequence word the host is polling (no H2D / D2H copy, no stream synchronise)
+  char* mapped_host = nullptr;
+  char* mapped_dev = nullptr;
+  unsigned long long seq = 0;
+  // launches on caller-supplied streams share partials / tickets: order each enqueue after the previous one
+  cudaStream_t last_stream = nullptr;
+  bool last_valid = false, last_own = true;
+  cudaEvent_t order_ev = nullptr;
+  int plan_split_shift = -1;  // b200mc_set_plan: -1 / 0 = automatic
+  uint32_t plan_ppt = 0;
+  uint32_t last_plan[3] = {0, 0, 0};  // tiles, paths per thread, split shift of the most recent fused launch
   uint64_t launches = 0;
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // scratch pair for the probes
@@ -117,36 +129,94 @@ uint32_t pad_scenarios(uint32_t n) {
   return p;
 }
 
-// Tile shape.  A tile = one CTA = kBlock threads x ppt paths of one option.  Large problems simply take
-// ppt = kMaxPathsPerThread (the per-CTA prologue/reduction is amortised over 32 paths per thread).  Small ones
-// (one option, 1e5..1e6 paths) trade three things: CTA overhead (favours few fat CTAs), SM load balance
-// (ceil(ctas / n_sm) CTAs on the busiest SM) and latency hiding (an SM needs ~kSaturatingCtas resident CTAs to
-// keep the XU pipe fed) plus a drain tail (the last resident CTAs of an SM finish at different times and run
-// under-occupied: ~0.3 of one full residency).  Every ppt in [1, 32] is scored and the cheapest wins; the plan depends
+constexpr size_t kMappedRecordBytes = B200MC_MAX_SCENARIOS * sizeof(b200mc_cv_moments_t);  // the largest single-option result
+constexpr size_t kMappedBytes = 4096;
+
+// Ticket counters start at zero and every launch leaves them at zero (finish_tile).
+// Scratch of the in-kernel fold (finish_tile): tile partials + group totals, and the ticket words.
+int reserve_fold(b200mc_engine* e, uint32_t n_opt, uint32_t tiles, uint32_t values_per_tile) {
+  if (int rc = reserve(e, e->partials, (size_t)n_opt * fold_scratch_doubles(tiles, values_per_tile) * sizeof(double))) return rc;
+  const size_t bytes = (size_t)n_opt * fold_ticket_words(tiles) * sizeof(uint32_t);
+  if (e->tickets.bytes >= bytes) return 0;
+  if (int rc = reserve(e, e->tickets, bytes)) return rc;
+  CU_TRY(e, cudaMemset(e->tickets.ptr, 0, e->tickets.bytes));
+  return 0;
+}
+
+// Kernels of consecutive calls share the partials / ticket scratch.  Calls on the engine's own stream are ordered by the
+// stream; a call on a different stream than the previous one first waits for that previous call.
+int order_before(b200mc_engine* e, cudaStream_t stream) {
+  if (e->last_valid && e->last_stream != stream) {
+    if (e->last_own) CU_TRY(e, cudaEventRecord(e->order_ev, e->stream));  // everything enqueued on our stream so far
+    CU_TRY(e, cudaStreamWaitEvent(stream, e->order_ev, 0));
+  }
+  return 0;
+}
+
+int order_after(b200mc_engine* e, cudaStream_t stream) {
+  e->last_stream = stream;
+  e->last_own = stream == e->stream;
+  e->last_valid = true;
+  if (!e->last_own) CU_TRY(e, cudaEventRecord(e->order_ev, stream));  // a caller's stream may be gone by the next call: record now
+  return 0;
+}
+
+// Tile shape.  A tile = one CTA = kBlock threads; a thread owns ppt paths of one option - or, for European launches
+// too small to fill the chip that way, 2^split_shift adjacent lanes share each path (european_kernel<SPLIT>).  Large
+// problems simply take ppt = kMaxPathsPerThread (the per-CTA prologue/reduction is amortised over 32 paths per thread).
+// Small ones (one option, 1e4..1e6 paths) trade three things: CTA overhead (favours few fat CTAs), SM load balance
+// (ceil(ctas / n_sm) CTAs on the busiest SM) and latency hiding (an SM needs ~kSaturatingCtas resident CTAs to keep
+// the XU pipe fed) plus a drain tail (the last resident CTAs of an SM finish at different times and run
+// under-occupied: ~0.3 of one full residency).  Every (split, ppt) is scored and the cheapest wins; the plan depends
 // only on (n_opt, n_paths, n_steps, n_scen, SM count), so a given call is reproducible bit for bit.
-void plan_tiles(const b200mc_engine* e, uint32_t n_opt, uint64_t n_paths, uint32_t n_steps, uint32_t ns, bool path_dependent,
-                uint32_t& tiles, uint32_t& ppt) {
+struct TilePlan {
+  uint32_t tiles = 1, ppt = 1, split_shift = 0;
+};
+
+TilePlan plan_tiles(const b200mc_engine* e, uint32_t n_opt, uint64_t n_paths, uint32_t n_steps, uint32_t ns, bool path_dependent,
+                    bool may_split = false) {
   const int resident = ns <= 2 ? 6 : ns == 4 ? 3 : 2;    // CTAs per SM the register budgets below allow
   constexpr double kSaturatingCtas = 3.0;
   const double n_sm = (double)e->prop.multiProcessorCount;
   // issued instructions per path: step loop (+ per-scenario state updates of the path-dependent kinds) + payoff epilogue
-  const double per_path = (11.0 + (path_dependent ? 3.5 * ns : 0.0)) * n_steps + 14.0 * ns;
-  const double per_cta = 600.0 + 40.0 * ns;              // coefficient set-up + FP64 block reduction
+  const double per_path_loop = (11.0 + (path_dependent ? 3.5 * ns : 0.0)) * n_steps;
+  const double per_path_payoff = 14.0 * ns;
+  const double per_cta = 500.0 + 60.0 * ns;              // coefficient set-up + FP64 block reduction
+  const uint32_t calls = (n_steps + 7u) >> 3;
   double best = 0.0;
-  uint32_t best_p = 1, best_t = 1;
-  for (uint32_t p = 1; p <= (uint32_t)kMaxPathsPerThread; ++p) {
-    const uint64_t t = (n_paths + (uint64_t)kBlock * p - 1) / ((uint64_t)kBlock * p);
-    const uint64_t p_even = (n_paths + (uint64_t)kBlock * t - 1) / ((uint64_t)kBlock * t);  // spread evenly over t tiles
-    if (p_even != p) continue;                                                               // same tiling as a smaller p
-    const double ctas = (double)t * n_opt;
-    const double per_sm = std::ceil(ctas / n_sm);
-    const double concurrency = std::min(per_sm, (double)resident);
-    const double eff = std::min(1.0, concurrency / kSaturatingCtas);
-    const double cost = (per_sm + 0.3 * resident) * ((double)p * per_path + per_cta) / eff;
-    if (best == 0.0 || cost < best * 0.999) best = cost, best_p = p, best_t = (uint32_t)t;
+  TilePlan plan;
+  // Lane split (european_kernel<SPLIT>): measured on B200 (profiles/r02_plan_sweep.jsonl) it pays only while one thread
+  // per path leaves most SMs without a CTA - 10k paths: 19.5 -> 15.4 us with 2 lanes per path; from 30k paths up the
+  // unsplit launch wins.  So: the smallest split that puts a CTA on at least half of the SMs, none otherwise.
+  uint32_t auto_shift = 0;
+  if (may_split) {
+    const double base_ctas = std::ceil((double)n_paths / kBlock) * n_opt;
+    while ((1u << (auto_shift + 1)) <= (uint32_t)kMaxSplit && calls >= (4u << auto_shift) && base_ctas * (1u << auto_shift) < 0.5 * n_sm)
+      ++auto_shift;
   }
-  tiles = best_t;
-  ppt = best_p;
+  uint32_t max_shift = 0;
+  if (may_split)
+    while ((1u << (max_shift + 1)) <= (uint32_t)kMaxSplit && calls >= (4u << max_shift)) ++max_shift;  // >= 2 calls per lane
+  const uint32_t lo = e->plan_split_shift >= 0 ? std::min<uint32_t>((uint32_t)e->plan_split_shift, max_shift) : auto_shift;
+  const uint32_t hi = lo;
+  for (uint32_t shift = lo; shift <= hi; ++shift) {
+    const uint32_t lanes = 1u << shift;
+    const uint64_t per_pass = (uint64_t)kBlock >> shift;
+    const double per_path = per_path_loop / lanes + per_path_payoff + 8.0 * shift;  // + the butterfly
+    for (uint32_t p = 1; p <= (uint32_t)kMaxPathsPerThread; ++p) {
+      if (e->plan_ppt && p != e->plan_ppt) continue;
+      const uint64_t t = (n_paths + per_pass * p - 1) / (per_pass * p);
+      const uint64_t p_even = (n_paths + per_pass * t - 1) / (per_pass * t);  // spread evenly over t tiles
+      if (p_even != p && !e->plan_ppt) continue;                              // same tiling as a smaller p
+      const double ctas = (double)t * n_opt;
+      const double per_sm = std::ceil(ctas / n_sm);
+      const double concurrency = std::min(per_sm, (double)resident);
+      const double eff = std::min(1.0, concurrency / kSaturatingCtas);
+      const double cost = (per_sm + 0.3 * resident) * ((double)p * per_path + per_cta) / eff;
+      if (best == 0.0 || cost < best * 0.999) best = cost, plan.ppt = p, plan.tiles = (uint32_t)t, plan.split_shift = shift;
+    }
+  }
+  return plan;
 }
 
 // __launch_bounds__ minBlocksPerSM per kernel family, picked from measurements on B200
@@ -164,6 +234,9 @@ cudaError_t launch_european(const SimArgs& a, bool anti, bool cv, dim3 grid, cud
   if (cv) {
     if (anti) european_kernel<NS, true, kMinBlocksWide, true><<<grid, kBlock, 0, s>>>(a);
     else european_kernel<NS, false, kMinBlocksWide, true><<<grid, kBlock, 0, s>>>(a);
+  } else if (a.split_shift) {  // under-filled launches: 2^split_shift lanes per path
+    if (anti) european_kernel<NS, true, kMinBlocks, false, 1, true><<<grid, kBlock, 0, s>>>(a);
+    else european_kernel<NS, false, kMinBlocks, false, 1, true><<<grid, kBlock, 0, s>>>(a);
   } else {
     if (anti) european_kernel<NS, true, kMinBlocks><<<grid, kBlock, 0, s>>>(a);
     else european_kernel<NS, false, kMinBlocks><<<grid, kBlock, 0, s>>>(a);
@@ -219,33 +292,55 @@ cudaError_t launch_structured(const StructuredArgs& g, uint32_t ns, dim3 grid, c
   return cudaGetLastError();
 }
 
-// Enqueue simulation + fold on `stream`; params/out are device pointers.
-int enqueue_simulation(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc_params_t* params_dev, uint32_t n_opt,
-                       uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
+// Enqueue the fused simulation on `stream`.  params_dev != null: parameters and `out` are device pointers.  params_dev ==
+// null (single-option launches from the host entry points): the block rides in the kernel arguments (inline_params) and
+// the finishing CTA writes the records into the mapped pinned block, then publishes `seq` for the polling host.
+int enqueue_simulation(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc_params_t* params_dev, const b200mc_params_t* inline_params,
+                       uint32_t n_opt, uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
                        void* out_dev, cudaStream_t stream, bool time_it, bool cv = false) {
   if (int rc = check_spec(e, spec)) return rc;
-  if (!params_dev || !out_dev) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
+  if ((!params_dev && !inline_params) || !out_dev) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
   if (n_opt == 0 || n_paths == 0) return fail(e, B200MC_ERR_INVALID, "n_opt and n_paths must be >= 1");
   if (n_scen == 0 || n_scen > B200MC_MAX_SCENARIOS)
     return fail(e, B200MC_ERR_INVALID, "n_scen must be in [1, %d]", B200MC_MAX_SCENARIOS);
+  if (inline_params && n_opt != 1) return fail(e, B200MC_ERR_INVALID, "inline parameters carry one option");
 
   if (cv && spec->kind != B200MC_EUROPEAN) return fail(e, B200MC_ERR_INVALID, "the control variate is defined for the European payoff only");
   const uint32_t ns = pad_scenarios(n_scen);
-  uint32_t tiles, ppt;
-  plan_tiles(e, n_opt, n_paths, spec->n_steps, ns, spec->kind != B200MC_EUROPEAN, tiles, ppt);
-  const uint64_t ctas = (uint64_t)tiles * n_opt;
+  const TilePlan plan = plan_tiles(e, n_opt, n_paths, spec->n_steps, ns, spec->kind != B200MC_EUROPEAN, spec->kind == B200MC_EUROPEAN && !cv);
+  const uint64_t ctas = (uint64_t)plan.tiles * n_opt;
   if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
-  if (int rc = reserve(e, e->partials, ctas * (cv ? 5 : 2) * ns * sizeof(double))) return rc;
+  e->last_plan[0] = plan.tiles, e->last_plan[1] = plan.ppt, e->last_plan[2] = plan.split_shift;
+  if (int rc = reserve_fold(e, n_opt, plan.tiles, (cv ? 6 : 3) * ns)) return rc;  // sums + one paid-count per scenario
+  if (int rc = order_before(e, stream)) return rc;
 
   SimArgs a{};
   a.params = params_dev;
-  a.partials = (double*)e->partials.ptr;
+  if (inline_params) {  // the host evaluates what thread k of every CTA's prologue (and the finishing CTA) would
+    const bool negate = (spec->kind == B200MC_BARRIER && spec->barrier_down) ||
+                        (spec->kind == B200MC_LOOKBACK && (spec->lookback_fixed ? spec->is_put : !spec->is_put));
+    for (uint32_t k = 0; k < ns; ++k) {
+      const b200mc_params_t& p = inline_params[k < n_scen ? k : n_scen - 1];
+      const Coef q = make_coef(p, spec->n_steps, negate ? -1.0f : 1.0f);
+      a.inl.c[k] = q.c, a.inl.d[k] = q.d, a.inl.a[k] = q.a, a.inl.kappa[k] = q.kappa, a.inl.beta[k] = q.beta, a.inl.inv_n[k] = q.inv_n;
+      a.inl.spot[k] = p.S, a.inl.kappa64[k] = p.K / p.S;
+    }
+  }
+  a.fold.partials = (double*)e->partials.ptr;
+  a.fold.tickets = (uint32_t*)e->tickets.ptr;
+  a.fold.out = out_dev;
+  a.fold.samples = (double)n_paths * (spec->antithetic ? 2.0 : 1.0);
+  if (inline_params) {
+    a.fold.done = (unsigned long long*)(e->mapped_dev + kMappedRecordBytes);
+    a.fold.seq = ++e->seq;
+  }
   a.path_begin = path_begin;
   a.n_paths = n_paths;
   a.n_opt = n_opt;
   a.n_scen = n_scen;
-  a.tiles = tiles;
-  a.paths_per_thread = ppt;
+  a.tiles = plan.tiles;
+  a.paths_per_thread = plan.ppt;
+  a.split_shift = plan.split_shift;
   a.n_steps = spec->n_steps;
   a.rk = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32));
   a.stream_base = stream_base;
@@ -282,14 +377,23 @@ int enqueue_simulation(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc
     CU_TRY(e, cudaEventRecord(e->ring1[slot], stream));
     e->timed += 1;
   }
-  const double samples = (double)n_paths * (spec->antithetic ? 2.0 : 1.0);
-  if (cv)
-    fold_cv_kernel<<<n_opt * n_scen, 32, 0, stream>>>((const double*)e->partials.ptr, params_dev, (b200mc_cv_moments_t*)out_dev, n_scen, ns, tiles, samples);
-  else
-    fold_kernel<<<n_opt * n_scen, 32, 0, stream>>>((const double*)e->partials.ptr, params_dev, (b200mc_moments_t*)out_dev, n_scen, ns, tiles, samples);
-  CU_TRY(e, cudaGetLastError());
-  e->launches += 2;
-  return 0;
+  e->launches += 1;
+  return order_after(e, stream);
+}
+
+// Wait for the finishing CTA of launch `seq` to publish its records in the mapped block.  Polling host memory sees the
+// result ~1 us after the kernel's last store; a stream synchronise costs several.  Every few thousand polls the stream is
+// queried so that a failed launch surfaces as an error instead of a hang.
+int wait_mapped(b200mc_engine* e, unsigned long long seq) {
+  const volatile unsigned long long* flag = (const volatile unsigned long long*)(e->mapped_host + kMappedRecordBytes);
+  for (uint32_t spin = 0;; ++spin) {
+    if (__atomic_load_n(flag, __ATOMIC_ACQUIRE) == seq) return 0;
+    if ((spin & 0x3fffu) == 0x3fffu) {
+      const cudaError_t q = cudaStreamQuery(e->stream);
+      if (q == cudaSuccess) return __atomic_load_n(flag, __ATOMIC_ACQUIRE) == seq ? 0 : fail(e, B200MC_ERR_CUDA, "kernel finished without publishing its result");
+      if (q != cudaErrorNotReady) return fail(e, B200MC_ERR_CUDA, "simulation kernel failed: %s", cudaGetErrorString(q));
+    }
+  }
 }
 
 int enqueue_from_normals(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc_params_t* p, int accumulate,
@@ -301,6 +405,7 @@ int enqueue_from_normals(b200mc_engine* e, const b200mc_spec_t* spec, const b200
   const uint64_t ctas = (n_paths + kF64Block - 1) / kF64Block;
   if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "too many paths for one launch");
   if (int rc = reserve(e, e->partials, ctas * 2 * sizeof(double))) return rc;
+  if (int rc = order_before(e, stream)) return rc;
   F64Args a{};
   a.Z = Z_dev;
   a.payoffs = payoffs_dev;
@@ -339,10 +444,10 @@ int enqueue_from_normals(b200mc_engine* e, const b200mc_spec_t* spec, const b200
     e->timed += 1;
   }
   const double samples = (double)n_paths * (spec->antithetic ? 2.0 : 1.0);
-  fold_kernel<<<1, 32, 0, stream>>>((const double*)e->partials.ptr, nullptr, out_dev, 1, 1, (uint32_t)ctas, samples);
+  fold_kernel<<<1, 32, 0, stream>>>((const double*)e->partials.ptr, out_dev, (uint32_t)ctas, samples);
   CU_TRY(e, cudaGetLastError());
   e->launches += 2;
-  return 0;
+  return order_after(e, stream);
 }
 
 }  // namespace
@@ -382,6 +487,10 @@ int b200mc_create(b200mc_engine_t** out, int device) {
     if ((err = cudaEventCreate(&e->ring0[i])) != cudaSuccess) return bail(err, "cudaEventCreate");
     if ((err = cudaEventCreate(&e->ring1[i])) != cudaSuccess) return bail(err, "cudaEventCreate");
   }
+  if ((err = cudaEventCreateWithFlags(&e->order_ev, cudaEventDisableTiming)) != cudaSuccess) return bail(err, "cudaEventCreate");
+  if ((err = cudaHostAlloc((void**)&e->mapped_host, kMappedBytes, cudaHostAllocMapped)) != cudaSuccess) return bail(err, "cudaHostAlloc");
+  memset(e->mapped_host, 0, kMappedBytes);
+  if ((err = cudaHostGetDevicePointer((void**)&e->mapped_dev, e->mapped_host, 0)) != cudaSuccess) return bail(err, "cudaHostGetDevicePointer");
   *out = e;
   return 0;
 }
@@ -390,9 +499,11 @@ void b200mc_destroy(b200mc_engine_t* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  for (DeviceBuffer* b : {&e->partials, &e->params_dev, &e->moments_dev, &e->scratch_a, &e->scratch_b})
+  for (DeviceBuffer* b : {&e->partials, &e->tickets, &e->params_dev, &e->moments_dev, &e->scratch_a, &e->scratch_b})
     if (b->ptr) cudaFree(b->ptr);
   if (e->pinned) cudaFreeHost(e->pinned);
+  if (e->mapped_host) cudaFreeHost(e->mapped_host);
+  if (e->order_ev) cudaEventDestroy(e->order_ev);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   for (int i = 0; i < b200mc_engine::kRing; ++i) {
@@ -429,7 +540,8 @@ int b200mc_simulate_device(b200mc_engine_t* e, const b200mc_spec_t* spec, const 
   if (!e) return B200MC_ERR_INVALID;
   std::lock_guard<std::mutex> g(e->mutex);
   CU_TRY(e, cudaSetDevice(e->device));
-  return enqueue_simulation(e, spec, params_dev, n_opt, n_scen, seed, stream_base, path_begin, n_paths, out_dev,
+  if (!params_dev) return fail(e, B200MC_ERR_INVALID, "params pointer is null");
+  return enqueue_simulation(e, spec, params_dev, nullptr, n_opt, n_scen, seed, stream_base, path_begin, n_paths, out_dev,
                             (cudaStream_t)cuda_stream, e->timing);
 }
 
@@ -443,6 +555,14 @@ static int simulate_host(b200mc_engine_t* e, const b200mc_spec_t* spec, const b2
   CU_TRY(e, cudaSetDevice(e->device));
   const size_t n = (size_t)n_opt * n_scen;
   const size_t in_bytes = n * sizeof(b200mc_params_t), out_bytes = n * (cv ? sizeof(b200mc_cv_moments_t) : sizeof(b200mc_moments_t));
+  if (n_opt == 1) {  // one launch, nothing else: parameters in the kernel arguments, records through mapped memory
+    if (int rc = enqueue_simulation(e, spec, nullptr, params_host, 1, n_scen, seed, stream_base, path_begin, n_paths, e->mapped_dev,
+                                    e->stream, e->timing, cv))
+      return rc;
+    if (int rc = wait_mapped(e, e->seq)) return rc;
+    memcpy(out_host, e->mapped_host, out_bytes);
+    return 0;
+  }
   if (int rc = reserve(e, e->params_dev, in_bytes)) return rc;
   if (int rc = reserve(e, e->moments_dev, out_bytes)) return rc;
   if (int rc = reserve_pinned(e, in_bytes + out_bytes)) return rc;
@@ -450,7 +570,7 @@ static int simulate_host(b200mc_engine_t* e, const b200mc_spec_t* spec, const b2
   char* pin_out = pin_in + in_bytes;
   memcpy(pin_in, params_host, in_bytes);
   CU_TRY(e, cudaMemcpyAsync(e->params_dev.ptr, pin_in, in_bytes, cudaMemcpyHostToDevice, e->stream));
-  if (int rc = enqueue_simulation(e, spec, (const b200mc_params_t*)e->params_dev.ptr, n_opt, n_scen, seed, stream_base,
+  if (int rc = enqueue_simulation(e, spec, (const b200mc_params_t*)e->params_dev.ptr, nullptr, n_opt, n_scen, seed, stream_base,
                                   path_begin, n_paths, e->moments_dev.ptr, e->stream, e->timing, cv))
     return rc;
   CU_TRY(e, cudaMemcpyAsync(pin_out, e->moments_dev.ptr, out_bytes, cudaMemcpyDeviceToHost, e->stream));
@@ -493,16 +613,20 @@ int b200mc_simulate_structured(b200mc_engine_t* e, const b200mc_spec_t* spec, co
   CU_TRY(e, cudaMemcpyAsync(e->params_dev.ptr, pin_in, in_bytes, cudaMemcpyHostToDevice, e->stream));
 
   const uint32_t ns = pad_scenarios(n_scen);
-  uint32_t tiles, ppt;
-  plan_tiles(e, n_opt, n_paths, sim_steps, ns, true, tiles, ppt);
+  const TilePlan plan = plan_tiles(e, n_opt, n_paths, sim_steps, ns, true);
+  const uint32_t tiles = plan.tiles;
   const uint64_t ctas = (uint64_t)tiles * n_opt;
   if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
-  if (int rc = reserve(e, e->partials, ctas * 2 * ns * sizeof(double))) return rc;
+  if (int rc = reserve_fold(e, n_opt, tiles, 3 * ns)) return rc;
+  if (int rc = order_before(e, e->stream)) return rc;
   StructuredArgs a{};
   a.sim.params = (const b200mc_params_t*)e->params_dev.ptr;
-  a.sim.partials = (double*)e->partials.ptr;
+  a.sim.fold.partials = (double*)e->partials.ptr;
+  a.sim.fold.tickets = (uint32_t*)e->tickets.ptr;
+  a.sim.fold.out = e->moments_dev.ptr;
+  a.sim.fold.samples = (double)n_paths;
   a.sim.path_begin = path_begin, a.sim.n_paths = n_paths;
-  a.sim.n_opt = n_opt, a.sim.n_scen = n_scen, a.sim.tiles = tiles, a.sim.paths_per_thread = ppt, a.sim.n_steps = spec->n_steps;
+  a.sim.n_opt = n_opt, a.sim.n_scen = n_scen, a.sim.tiles = tiles, a.sim.paths_per_thread = plan.ppt, a.sim.n_steps = spec->n_steps;
   a.sim.rk = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32));
   a.sim.stream_base = stream_base;
   a.a = product->a, a.b = product->b, a.c = product->c, a.d = product->d;
@@ -517,11 +641,8 @@ int b200mc_simulate_structured(b200mc_engine_t* e, const b200mc_spec_t* spec, co
     CU_TRY(e, cudaEventRecord(e->ring1[slot], e->stream));
     e->timed += 1;
   }
-  // CLIQUET payoffs are per unit spot (scaled by S in the fold); AUTOCALLABLE payoffs are per unit notional
-  fold_kernel<<<n_opt * n_scen, 32, 0, e->stream>>>((const double*)e->partials.ptr, spec->kind == B200MC_CLIQUET ? a.sim.params : nullptr,
-                                                   (b200mc_moments_t*)e->moments_dev.ptr, n_scen, ns, tiles, (double)n_paths);
-  CU_TRY(e, cudaGetLastError());
-  e->launches += 2;
+  e->launches += 1;
+  if (int rc = order_after(e, e->stream)) return rc;
   CU_TRY(e, cudaMemcpyAsync(pin_out, e->moments_dev.ptr, out_bytes, cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
   memcpy(out_host, pin_out, out_bytes);
@@ -544,6 +665,7 @@ int b200mc_structured_from_normals(b200mc_engine_t* e, const b200mc_spec_t* spec
   if (int rc = reserve(e, e->scratch_b, n_paths * sizeof(double))) return rc;
   if (int rc = reserve(e, e->partials, ctas * 2 * sizeof(double))) return rc;
   if (int rc = reserve(e, e->moments_dev, sizeof(b200mc_moments_t))) return rc;
+  if (int rc = order_before(e, e->stream)) return rc;
   CU_TRY(e, cudaMemcpyAsync(e->scratch_a.ptr, Z_host, z_bytes, cudaMemcpyHostToDevice, e->stream));
   StructuredF64Args a{};
   a.Z = (const double*)e->scratch_a.ptr;
@@ -555,7 +677,7 @@ int b200mc_structured_from_normals(b200mc_engine_t* e, const b200mc_spec_t* spec
   if (spec->kind == B200MC_CLIQUET) structured_from_normals_kernel<B200MC_CLIQUET><<<(unsigned)ctas, 128, 0, e->stream>>>(a);
   else structured_from_normals_kernel<B200MC_AUTOCALLABLE><<<(unsigned)ctas, 128, 0, e->stream>>>(a);
   CU_TRY(e, cudaGetLastError());
-  fold_kernel<<<1, 32, 0, e->stream>>>((const double*)e->partials.ptr, nullptr, (b200mc_moments_t*)e->moments_dev.ptr, 1, 1, (uint32_t)ctas, (double)n_paths);
+  fold_kernel<<<1, 32, 0, e->stream>>>((const double*)e->partials.ptr, (b200mc_moments_t*)e->moments_dev.ptr, (uint32_t)ctas, (double)n_paths);
   CU_TRY(e, cudaGetLastError());
   e->launches += 2;
   if (payoffs_host) CU_TRY(e, cudaMemcpyAsync(payoffs_host, e->scratch_b.ptr, n_paths * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
@@ -619,12 +741,12 @@ int b200mc_generate_normals(b200mc_engine_t* e, uint64_t seed, uint32_t stream, 
 // ---- Heston / jump-diffusion models -----------------------------------------------------------
 }  // extern "C" (templates below)
 
-// Shared host wrapper: stage `in_bytes` of parameters (two blocks), launch, fold with the spot taken from the
-// first block at a stride, copy [n_opt] moments back.
+// Shared host wrapper: stage `in_bytes` of parameters (two blocks), launch (the kernel folds its own tiles), copy
+// [n_opt] moments back.
 template <class Launch>
 static int simulate_model_host(b200mc_engine_t* e, const void* block_a, size_t bytes_a, const void* block_b, size_t bytes_b,
-                               uint32_t n_opt, uint32_t n_steps, uint32_t per_step_cost, uint64_t n_paths, size_t spot_stride_doubles,
-                               b200mc_moments_t* out_host, Launch&& launch) {
+                               uint32_t n_opt, uint32_t n_steps, uint32_t per_step_cost, uint64_t n_paths, b200mc_moments_t* out_host,
+                               Launch&& launch) {
   if (!block_a || !out_host) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
   if (n_opt == 0 || n_paths == 0 || n_steps == 0) return fail(e, B200MC_ERR_INVALID, "n_opt, n_paths and n_steps must be >= 1");
   CU_TRY(e, cudaSetDevice(e->device));
@@ -637,23 +759,27 @@ static int simulate_model_host(b200mc_engine_t* e, const void* block_a, size_t b
   memcpy(pin_in, block_a, bytes_a);
   if (bytes_b) memcpy(pin_in + bytes_a, block_b, bytes_b);
   CU_TRY(e, cudaMemcpyAsync(e->params_dev.ptr, pin_in, in_bytes, cudaMemcpyHostToDevice, e->stream));
-  uint32_t tiles, ppt;
-  plan_tiles(e, n_opt, n_paths, n_steps * per_step_cost, 1, false, tiles, ppt);
+  const TilePlan plan = plan_tiles(e, n_opt, n_paths, n_steps * per_step_cost, 1, false);
+  const uint32_t tiles = plan.tiles, ppt = plan.ppt;
   const uint64_t ctas = (uint64_t)tiles * n_opt;
   if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
-  if (int rc = reserve(e, e->partials, ctas * 2 * sizeof(double))) return rc;
+  if (int rc = reserve_fold(e, n_opt, tiles, 3)) return rc;
+  if (int rc = order_before(e, e->stream)) return rc;
+  FoldArgs fold{};
+  fold.partials = (double*)e->partials.ptr;
+  fold.tickets = (uint32_t*)e->tickets.ptr;
+  fold.out = e->moments_dev.ptr;
+  fold.samples = (double)n_paths;
   const int slot = (int)(e->timed % b200mc_engine::kRing);
   if (e->timing) CU_TRY(e, cudaEventRecord(e->ring0[slot], e->stream));
-  launch((const char*)e->params_dev.ptr, (const char*)e->params_dev.ptr + bytes_a, (double*)e->partials.ptr, tiles, ppt, dim3((unsigned)ctas));
+  launch((const char*)e->params_dev.ptr, (const char*)e->params_dev.ptr + bytes_a, fold, tiles, ppt, dim3((unsigned)ctas));
   CU_TRY(e, cudaGetLastError());
   if (e->timing) {
     CU_TRY(e, cudaEventRecord(e->ring1[slot], e->stream));
     e->timed += 1;
   }
-  fold_strided_kernel<<<n_opt, 32, 0, e->stream>>>((const double*)e->partials.ptr, (const double*)e->params_dev.ptr, (uint32_t)spot_stride_doubles,
-                                                    (b200mc_moments_t*)e->moments_dev.ptr, tiles, (double)n_paths);
-  CU_TRY(e, cudaGetLastError());
-  e->launches += 2;
+  e->launches += 1;
+  if (int rc = order_after(e, e->stream)) return rc;
   CU_TRY(e, cudaMemcpyAsync(pin_out, e->moments_dev.ptr, out_bytes, cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
   memcpy(out_host, pin_out, out_bytes);
@@ -667,12 +793,11 @@ int b200mc_simulate_heston(b200mc_engine_t* e, const b200mc_heston_params_t* par
   if (!e) return B200MC_ERR_INVALID;
   std::lock_guard<std::mutex> g(e->mutex);
   if (n_steps > 0x7fffffffu) return fail(e, B200MC_ERR_INVALID, "n_steps too large");
-  return simulate_model_host(e, params_host, (size_t)n_opt * sizeof(b200mc_heston_params_t), nullptr, 0, n_opt, n_steps, 2, n_paths,
-                             sizeof(b200mc_heston_params_t) / sizeof(double), out_host,
-                             [&](const char* pa, const char*, double* partials, uint32_t tiles, uint32_t ppt, dim3 grid) {
+  return simulate_model_host(e, params_host, (size_t)n_opt * sizeof(b200mc_heston_params_t), nullptr, 0, n_opt, n_steps, 2, n_paths, out_host,
+                             [&](const char* pa, const char*, const FoldArgs& fold, uint32_t tiles, uint32_t ppt, dim3 grid) {
                                HestonArgs a{};
                                a.params = (const b200mc_heston_params_t*)pa;
-                               a.partials = partials;
+                               a.fold = fold;
                                a.path_begin = path_begin, a.n_paths = n_paths;
                                a.n_opt = n_opt, a.tiles = tiles, a.paths_per_thread = ppt, a.n_steps = n_steps;
                                a.rk = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32)), a.stream_base = stream_base;
@@ -691,14 +816,17 @@ int b200mc_simulate_jump_diffusion(b200mc_engine_t* e, const b200mc_params_t* pa
     const b200mc_jump_params_t& j = jumps_host[i];
     if (j.model != B200MC_JUMP_MERTON && j.model != B200MC_JUMP_KOU) return fail(e, B200MC_ERR_INVALID, "unknown jump model %d", j.model);
     if (!(j.lambda_j >= 0.0)) return fail(e, B200MC_ERR_INVALID, "lambda_j must be non-negative");
+    // the jump count is inverted from p0 = exp(-lambda_j*T) upwards (models.cuh): beyond ~700 expected jumps p0 underflows
+    if (params_host && !(j.lambda_j * params_host[i].T <= 700.0))
+      return fail(e, B200MC_ERR_INVALID, "lambda_j * T = %g expected jumps per path is beyond the supported 700", j.lambda_j * params_host[i].T);
   }
   return simulate_model_host(e, params_host, (size_t)n_opt * sizeof(b200mc_params_t), jumps_host, (size_t)n_opt * sizeof(b200mc_jump_params_t),
-                             n_opt, n_steps, 1, n_paths, sizeof(b200mc_params_t) / sizeof(double), out_host,
-                             [&](const char* pa, const char* pb, double* partials, uint32_t tiles, uint32_t ppt, dim3 grid) {
+                             n_opt, n_steps, 1, n_paths, out_host,
+                             [&](const char* pa, const char* pb, const FoldArgs& fold, uint32_t tiles, uint32_t ppt, dim3 grid) {
                                JumpArgs a{};
                                a.params = (const b200mc_params_t*)pa;
                                a.jumps = (const b200mc_jump_params_t*)pb;
-                               a.partials = partials;
+                               a.fold = fold;
                                a.path_begin = path_begin, a.n_paths = n_paths;
                                a.n_opt = n_opt, a.tiles = tiles, a.paths_per_thread = ppt, a.n_steps = n_steps;
                                a.rk = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32)), a.stream_base = stream_base;
@@ -721,12 +849,13 @@ static int model_from_draws_host(b200mc_engine_t* e, const double* draws_a, size
   if (int rc = reserve(e, e->moments_dev, sizeof(b200mc_moments_t))) return rc;
   const uint64_t ctas = (n_paths + kBlock - 1) / kBlock;
   if (int rc = reserve(e, e->partials, ctas * 2 * sizeof(double))) return rc;
+  if (int rc = order_before(e, e->stream)) return rc;
   CU_TRY(e, cudaMemcpyAsync(e->scratch_a.ptr, draws_a, bytes_a, cudaMemcpyHostToDevice, e->stream));
   if (bytes_b) CU_TRY(e, cudaMemcpyAsync((char*)e->scratch_a.ptr + bytes_a, draws_b, bytes_b, cudaMemcpyHostToDevice, e->stream));
   launch((const double*)e->scratch_a.ptr, bytes_b ? (const double*)((char*)e->scratch_a.ptr + bytes_a) : nullptr,
          payoffs_host ? (double*)e->scratch_b.ptr : nullptr, (double*)e->partials.ptr, dim3((unsigned)ctas));
   CU_TRY(e, cudaGetLastError());
-  fold_kernel<<<1, 32, 0, e->stream>>>((const double*)e->partials.ptr, nullptr, (b200mc_moments_t*)e->moments_dev.ptr, 1, 1, (uint32_t)ctas, (double)n_paths);
+  fold_kernel<<<1, 32, 0, e->stream>>>((const double*)e->partials.ptr, (b200mc_moments_t*)e->moments_dev.ptr, (uint32_t)ctas, (double)n_paths);
   CU_TRY(e, cudaGetLastError());
   e->launches += 2;
   if (payoffs_host) CU_TRY(e, cudaMemcpyAsync(payoffs_host, e->scratch_b.ptr, n_paths * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
@@ -832,10 +961,14 @@ static int sobol_run(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc
   const uint64_t tiles = (n_points + tile_points - 1) / tile_points;
   const uint64_t ctas = tiles * n_opt;
   if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
-  if (int rc = reserve(e, e->partials, ctas * 2 * ns * sizeof(double))) return rc;
+  if (int rc = reserve_fold(e, n_opt, (uint32_t)tiles, 3 * ns)) return rc;
+  if (int rc = order_before(e, e->stream)) return rc;
   SobolArgs a{};
   a.params = (const b200mc_params_t*)e->params_dev.ptr;
-  a.partials = (double*)e->partials.ptr;
+  a.fold.partials = (double*)e->partials.ptr;
+  a.fold.tickets = (uint32_t*)e->tickets.ptr;
+  a.fold.out = e->moments_dev.ptr;
+  a.fold.samples = (double)n_points;
   a.dirnums = dir_dev;
   a.shift = shift_dev;
   a.point_begin = point_begin;
@@ -870,10 +1003,8 @@ static int sobol_run(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc
     CU_TRY(e, cudaEventRecord(e->ring1[slot], e->stream));
     e->timed += 1;
   }
-  fold_kernel<<<n_opt * n_scen, 32, 0, e->stream>>>((const double*)e->partials.ptr, a.params, (b200mc_moments_t*)e->moments_dev.ptr, n_scen, ns,
-                                                   (uint32_t)tiles, (double)n_points);
-  CU_TRY(e, cudaGetLastError());
-  e->launches += 2;
+  e->launches += 1;
+  if (int rc = order_after(e, e->stream)) return rc;
   CU_TRY(e, cudaMemcpyAsync(pin_out, e->moments_dev.ptr, out_bytes, cudaMemcpyDeviceToHost, e->stream));
   if (terminal_host) CU_TRY(e, cudaMemcpyAsync(terminal_host, e->scratch_b.ptr, terminal_bytes, cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
@@ -981,6 +1112,22 @@ int b200mc_philox_raw(b200mc_engine_t* e, const uint32_t* in_host, uint32_t n, u
 }
 
 uint64_t b200mc_kernel_launches(const b200mc_engine_t* e) { return e ? e->launches : 0; }
+
+int b200mc_set_plan(b200mc_engine_t* e, int split_shift, uint32_t paths_per_thread) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  if (split_shift > 3 || paths_per_thread > (uint32_t)kMaxPathsPerThread) return fail(e, B200MC_ERR_INVALID, "split_shift must be <= 3, paths_per_thread <= %d", kMaxPathsPerThread);
+  e->plan_split_shift = split_shift < 0 ? -1 : split_shift;
+  e->plan_ppt = paths_per_thread;
+  return 0;
+}
+
+int b200mc_last_plan(b200mc_engine_t* e, uint32_t* tiles, uint32_t* paths_per_thread, uint32_t* split_shift) {
+  if (!e || !tiles || !paths_per_thread || !split_shift) return fail(e, B200MC_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(e->mutex);
+  *tiles = e->last_plan[0], *paths_per_thread = e->last_plan[1], *split_shift = e->last_plan[2];
+  return 0;
+}
 
 int b200mc_set_kernel_timing(b200mc_engine_t* e, int enabled) {
   if (!e) return B200MC_ERR_INVALID;

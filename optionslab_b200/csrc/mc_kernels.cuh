@@ -1,15 +1,29 @@
-// Fused simulation kernels: Philox -> normals -> log-Euler GBM -> payoff -> (sum, sum^2).
+// Fused simulation kernels: Philox -> normals -> log-Euler GBM -> payoff -> (sum, sum^2) -> moments, ONE launch.
 //
 // Nothing per path or per step ever touches HBM: the only global traffic is the per-option
-// parameter block read once per CTA (64 B x n_scen) and one (sum, sum^2) FP64 pair per
-// (tile, scenario) written at the end.  A "tile" is one CTA's share of one option's paths:
-// kBlock threads x paths_per_thread paths.  A second, tiny kernel folds the tile partials in a
-// fixed order (deterministic: same seed => bit-identical moments, as the reference guarantees,
-// tests/test_monte_carlo.py:153-158).
+// parameter block read once per CTA (64 B x n_scen; single-option launches carry it in the kernel
+// arguments instead) and one FP64 partial per (tile, scenario, moment) written at the end.  A "tile"
+// is one CTA's share of one option's paths: kBlock threads x paths_per_thread paths.  The CTA that
+// arrives LAST at an option's ticket counter folds that option's tile partials in a fixed order
+// (finish_tile below) - no second launch, no atomics on the sums, same seed => bit-identical moments,
+// as the reference guarantees (tests/test_monte_carlo.py:153-158).
 //
 // All per-path arithmetic is FP32 on the quantity  l_t = log2(S_t / S_0)  (small magnitude, so
 // FP32 rounding is ~3e-8 per step), payoffs are normalised by S_0 and re-scaled in FP64 by the
-// fold kernel; cross-path accumulation is FP64 from the warp level up.
+// fold; cross-path accumulation is FP64 from the warp level up.
+//
+// Strike precision.  Scenarios that differ only in the spot (the S +- h re-pricings of delta_gamma,
+// monte_carlo_unified.py:513-560 with its default h = 1e-4) share every draw AND every normalised terminal
+// value e = S_T/S_0; the bump reaches the payoff max(e - K/S, 0) only through the strike ratio.  An FP32
+// K/S resolves a 2e-6 bump to ~17 ulps, and the FP32 difference e - K/S itself rounds in a K/S-dependent way
+// for large e - systematic errors no number of paths averages out.  So the strike never enters the FP32
+// first-moment arithmetic at all: per scenario a thread accumulates  sum of e over the samples that PAID
+// (payoff > 0, decided against the FP32 ratio) and counts them; the fold forms
+//     sum(payoff) = +-(sum_paid(e) - (K/S in FP64) * paid)
+// which is the exact piecewise-linear function of K/S for the draws at hand (the paid set is off only for paths
+// with e between the FP32 and FP64 ratio: measure ~1e-8, error < 6e-8 each).  sum_paid(e) is the SAME number for
+// every spot-bumped scenario, so its FP32 rounding cancels in finite differences.  The second moment keeps the
+// well-conditioned FP32 sum of payoff^2 and is moved to the FP64 strike to first order.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -22,21 +36,40 @@ namespace b200mc {
 
 constexpr int kBlock = 256;
 constexpr int kWarps = kBlock / 32;
-constexpr int kMaxPathsPerThread = 32;
+constexpr int kMaxPathsPerThread = 32;  // <= 64 samples per thread with mirrors: the paid-counts fit 8-bit lanes
+constexpr int kMaxSplit = 8;            // lanes that may share one European path (see european_kernel)
+
+// Where a launch's results go.
+struct FoldArgs {
+  double* partials;          // [n_opt * tiles][values per tile]: per-CTA FP64 partial sums (stay in L2)
+  uint32_t* tickets;         // [n_opt]: CTAs of the option that have delivered; zero between launches
+  void* out;                 // [n_opt][n_scen] moment records - device memory, or the device alias of mapped pinned host memory
+  unsigned long long* done;  // non-null: mapped host word that receives `seq` once `out` is complete (single-option launches)
+  unsigned long long seq;
+  double samples;            // the n of every record
+};
 
 struct SimArgs {
-  const b200mc_params_t* params;  // [n_opt][n_scen]
-  double* partials;               // [n_opt * tiles][2 * NS]
+  const b200mc_params_t* params;  // [n_opt][n_scen]; null: single-option launch, coefficients precomputed by the host (inl)
+  FoldArgs fold;
   uint64_t path_begin;
   uint64_t n_paths;
   uint32_t n_opt, n_scen;
   uint32_t tiles;                 // tiles per option
   uint32_t paths_per_thread;
   uint32_t n_steps;
+  uint32_t split_shift;           // European: 2^split_shift adjacent lanes share one path's Philox calls
   PhiloxKeys rk;                  // expanded from the 64-bit seed on the host
   uint32_t stream_base;
   int32_t is_put, barrier_in, lookback_fixed, sgn_negative;
   int32_t force_mufu_ex2;         // arithmetic Asian: always take the MUFU.EX2 form (tests / A-B timing)
+  // params == null (latency path of the host entry points, n_opt == 1): the host evaluated make_coef / the fold scale
+  // with the same FP64 expressions and passes the results in the kernel arguments - no H2D copy, no FP64 prologue
+  struct Inline {
+    float c[B200MC_MAX_SCENARIOS], d[B200MC_MAX_SCENARIOS], a[B200MC_MAX_SCENARIOS], kappa[B200MC_MAX_SCENARIOS],
+        beta[B200MC_MAX_SCENARIOS], inv_n[B200MC_MAX_SCENARIOS];
+    double spot[B200MC_MAX_SCENARIOS], kappa64[B200MC_MAX_SCENARIOS];
+  } inl;
 };
 
 // Per-scenario FP32 coefficients, computed in FP64 once per CTA (the reference's constants:
@@ -50,44 +83,261 @@ struct Coef {
   float inv_n;  // 1 / n_steps
 };
 
-__device__ __forceinline__ Coef make_coef(const b200mc_params_t& p, uint32_t n_steps, float sgn) {
+// Written with explicitly rounded operations so that host (engine.cu, single-option launches) and device
+// (batched launches) produce the same bits: nvcc would otherwise contract a*b+c into an FMA on the device only.
+#if defined(__CUDA_ARCH__)
+#define B200MC_DMUL(x, y) __dmul_rn((x), (y))
+#define B200MC_DSUB(x, y) __dsub_rn((x), (y))
+#define B200MC_DDIV(x, y) __ddiv_rn((x), (y))
+#else
+#define B200MC_DMUL(x, y) ((x) * (y))
+#define B200MC_DSUB(x, y) ((x) - (y))
+#define B200MC_DDIV(x, y) ((x) / (y))
+#endif
+
+__host__ __device__ __forceinline__ Coef make_coef(const b200mc_params_t& p, uint32_t n_steps, float sgn) {
   const double inv_ln2 = 1.44269504088896340736;
-  const double dt = p.T / (double)n_steps;
-  const double d = (p.r - p.q - 0.5 * p.sigma * p.sigma) * dt * inv_ln2;
-  const double c = p.sigma * sqrt(dt) * kCoefScaleD;
+  const double dt = B200MC_DDIV(p.T, (double)n_steps);
+  const double mu = B200MC_DSUB(B200MC_DSUB(p.r, p.q), B200MC_DMUL(B200MC_DMUL(0.5, p.sigma), p.sigma));
+  const double d = B200MC_DMUL(B200MC_DMUL(mu, dt), inv_ln2);
+  const double c = B200MC_DMUL(B200MC_DMUL(p.sigma, sqrt(dt)), kCoefScaleD);
   Coef k;
   k.c = sgn * (float)c;
   k.d = sgn * (float)d;
-  k.a = (float)(d * (double)n_steps);
-  k.kappa = (float)(p.K / p.S);
-  k.beta = sgn * (float)(log2(p.barrier / p.S));
-  k.inv_n = (float)(1.0 / (double)n_steps);
+  k.a = (float)B200MC_DMUL(d, (double)n_steps);
+  k.kappa = (float)B200MC_DDIV(p.K, p.S);
+  k.beta = sgn * (float)(log2(B200MC_DDIV(p.barrier, p.S)));
+  k.inv_n = (float)B200MC_DDIV(1.0, (double)n_steps);
   return k;
+}
+
+// Scenario k of option opt: from the parameter block in HBM, or from the host-evaluated inline block.
+__device__ __forceinline__ Coef scen_coef(const SimArgs& a, uint32_t opt, uint32_t k, float sgn) {
+  if (a.params) return make_coef(a.params[(size_t)opt * a.n_scen + k], a.n_steps, sgn);
+  Coef q;
+  q.c = a.inl.c[k], q.d = a.inl.d[k], q.a = a.inl.a[k], q.kappa = a.inl.kappa[k], q.beta = a.inl.beta[k], q.inv_n = a.inl.inv_n[k];
+  return q;
 }
 
 __device__ __forceinline__ float vanilla(float e, float kappa, bool is_put) {
   return is_put ? fmaxf(kappa - e, 0.0f) : fmaxf(e - kappa, 0.0f);
 }
 
-// ---- block-level FP64 reduction of per-thread FP32 partial sums ------------------------------
+// ---- per-sample accumulation ------------------------------------------------------------------------
+// x: the quantity the strike ratio is compared with (S_T/S_0, the average, the extremum ...); p: the FP32 payoff
+// max(+-(x - k32), 0) (0 when a barrier switched the path off).  acc[0] += x over the paid samples, acc[1] += p^2,
+// and the paid-count of scenario k sits in an 8-bit lane (a thread sees <= 64 samples: kMaxPathsPerThread x mirrors).
+// Payoffs without a strike (floating lookback, cliquet, autocallable) pass x = p: acc[0] is then sum(p) itself.
+template <int NS>
+__device__ __forceinline__ void add_sample(float* acc2, uint32_t (&cnt)[(NS + 3) / 4], int k, float x, float p) {
+  const bool paid = p > 0.0f;
+  acc2[0] += paid ? x : 0.0f;
+  acc2[1] = fmaf(p, p, acc2[1]);
+  cnt[k >> 2] += paid ? (1u << (8 * (k & 3))) : 0u;
+}
+
+// ---- CTA partials -> fixed-order two-level fold -> moment records ------------------------------------
+// What the fold needs to know about scenario k, evaluated in FP64 by the finishing CTA only.
+struct ScenScale {
+  double spot;     // currency units per normalised payoff unit (1 for per-notional payoffs)
+  double kappa;    // FP64 strike ratio K/S; has_strike = false: the payoff has no strike term
+  float kappa32;   // the FP32 value the paid / unpaid decision was made against
+  bool has_strike, is_put;
+};
+
+constexpr int kFoldGroup = 1024;  // tiles per first-level fold: four per thread of the folding CTA
+
+// NM sums per scenario: 2 = (sum_paid x, sum p^2); 5 adds (sum S_T, sum S_T^2, sum_paid x^2) for the control variate.
+// Every CTA: FP32 thread sums -> FP64 warp shuffles -> FP64 CTA partial (fixed order), written to the option's scratch.
+// Tiles of an option form groups of 1024; whichever CTA takes a group's last ticket folds the group with every load in
+// flight at once (one L2 round trip), and - only for options of more than 1024 tiles - whichever group finishes last
+// folds the group totals; that CTA also writes the option's moment records.  Every level reads ALL its inputs in index
+// order with a fixed association, so the result does not depend on which CTA did the work: no atomics on the sums, same
+// launch => bit-identical moments, no second kernel.
+// Scratch per option (doubles): [tiles][NV] tile partials, then [n_groups][NV] group totals.
+// Tickets per option (uint32): [0] groups folded, [1 + g] tiles delivered in group g; all zero between launches.
+__host__ __device__ inline uint32_t fold_groups(uint32_t tiles) { return (tiles + kFoldGroup - 1) / kFoldGroup; }
+__host__ __device__ inline size_t fold_scratch_doubles(uint32_t tiles, uint32_t nv) { return ((size_t)tiles + fold_groups(tiles)) * nv; }
+__host__ __device__ inline size_t fold_ticket_words(uint32_t tiles) { return (size_t)fold_groups(tiles) + 1; }
+
+// Sum x[v] over the CTA in a fixed order: shuffle tree per warp, then the warps in index order.  Threads v < NV return
+// the total of value v (others: garbage).  `red` is CTA-shared scratch.
 template <int NV>
-__device__ __forceinline__ void block_reduce_store(const float (&v)[NV], double* dst) {
-  __shared__ double warp_sums[kWarps][NV];
+__device__ __forceinline__ double cta_sum(const double (&x)[NV], double (*red)[NV]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    double x = (double)v[i];
+  for (int v = 0; v < NV; ++v) {
+    double y = x[v];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-    if (lane == 0) warp_sums[warp][i] = x;
+    for (int off = 16; off > 0; off >>= 1) y += __shfl_xor_sync(0xffffffffu, y, off);
+    if (lane == 0) red[warp][v] = y;
   }
   __syncthreads();
+  double t = 0.0;
   if (threadIdx.x < NV) {
-    double x = 0.0;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) x += warp_sums[w][threadIdx.x];
-    dst[threadIdx.x] = x;
+    for (int w = 0; w < kWarps; ++w) t += red[w][threadIdx.x];
   }
+  return t;
+}
+
+// Fold `count` (<= 1024) rows of NV doubles starting at `rows` into dst[NV] (CTA-shared or global), fixed association.
+template <int NV, class Store>
+__device__ __forceinline__ void fold_rows(const double* rows, uint32_t count, double (*red)[NV], Store&& store) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (NV <= 12) {
+    // few values per row: thread t takes rows t, t+256, t+512, t+768 - up to 4*NV independent loads - then a CTA sum
+    double x[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      double part[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t r = threadIdx.x + (uint32_t)kBlock * i;
+        part[i] = r < count ? __ldcg(rows + (size_t)r * NV + v) : 0.0;
+      }
+      x[v] = (part[0] + part[1]) + (part[2] + part[3]);
+    }
+    __syncthreads();  // `red` may still be read by the caller's previous cta_sum
+    const double t = cta_sum<NV>(x, red);
+    if (threadIdx.x < NV) store(threadIdx.x, t);
+  } else {
+    // many values per row (8-16 scenarios): one warp per value, lanes stride the rows with eight sums in flight
+    for (int v = warp; v < NV; v += kWarps) {
+      double x[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+      for (uint32_t j = 0; j < (uint32_t)kFoldGroup / 32; ++j) {
+        const uint32_t r = lane + 32u * j;
+        if (r < count) x[j & 7] += __ldcg(rows + (size_t)r * NV + v);
+      }
+      double y = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) y += __shfl_xor_sync(0xffffffffu, y, off);
+      if (lane == 0) store(v, y);
+    }
+  }
+}
+
+template <int NM, int NS, class ScaleFn>
+__device__ __forceinline__ void finish_tile(const float (&acc)[NM * NS], const uint32_t (&cnt)[(NS + 3) / 4], const FoldArgs& f,
+                                            uint32_t opt, uint32_t tile, uint32_t tiles, uint32_t n_scen, ScaleFn&& scale) {
+  constexpr int NA = NM * NS;  // accumulated sums
+  constexpr int NV = NA + NS;  // + one paid-count per scenario
+  __shared__ double red[kWarps][NV];
+  __shared__ double tot[NV];
+  __shared__ uint32_t is_last;
+  double mine[NV];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) mine[i] = (double)acc[i];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) mine[NA + k] = (double)((cnt[k >> 2] >> (8 * (k & 3))) & 0xffu);
+  const double cta_total = cta_sum<NV>(mine, red);
+
+  const uint32_t n_groups = fold_groups(tiles);
+  const uint32_t group = tile / kFoldGroup;
+  double* const scratch = f.partials + (size_t)opt * fold_scratch_doubles(tiles, NV);
+  double* const group_tot = scratch + (size_t)tiles * NV;  // [n_groups][NV]
+  uint32_t* const tickets = f.tickets + (size_t)opt * fold_ticket_words(tiles);
+  if (threadIdx.x < NV) {
+    if (tiles == 1) {
+      tot[threadIdx.x] = cta_total;  // the only tile of its option: nothing to fold
+    } else {
+      __stcg(scratch + (size_t)tile * NV + threadIdx.x, cta_total);
+      __threadfence();
+    }
+  }
+  if (tiles > 1) {
+    // ---- level 1: the group's last CTA folds its <= 1024 tiles ---------------------------------------------------
+    const uint32_t group_size = min((uint32_t)kFoldGroup, tiles - group * kFoldGroup);
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(tickets + 1 + group, 1u) == group_size - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (n_groups == 1) {
+      fold_rows<NV>(scratch, group_size, red, [&](int v, double x) { tot[v] = x; });
+    } else {
+      fold_rows<NV>(scratch + (size_t)group * kFoldGroup * NV, group_size, red, [&](int v, double x) {
+        __stcg(group_tot + (size_t)group * NV + v, x);
+        __threadfence();
+      });
+    }
+    if (threadIdx.x == 0) tickets[1 + group] = 0u;  // ready for the next launch
+    if (n_groups > 1) {
+      // ---- level 2 (options of more than 1024 tiles): the last group folds the group totals ----------------------
+      __syncthreads();
+      if (threadIdx.x == 0) is_last = atomicAdd(tickets, 1u) == n_groups - 1 ? 1u : 0u;
+      __syncthreads();
+      if (!is_last) return;
+      __threadfence();
+      for (uint32_t g0 = 0; g0 < n_groups; g0 += kFoldGroup) {  // > 2^20 tiles: chunks of 1024 groups, in order
+        const uint32_t n = min((uint32_t)kFoldGroup, n_groups - g0);
+        __syncthreads();
+        fold_rows<NV>(group_tot + (size_t)g0 * NV, n, red, [&](int v, double x) { tot[v] = g0 ? tot[v] + x : x; });
+      }
+      if (threadIdx.x == 0) tickets[0] = 0u;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < n_scen) {
+    const uint32_t k = threadIdx.x;
+    const ScenScale sc = scale(k);
+    const double paid = tot[NA + k];
+    const double a1 = tot[NM * k], p2 = tot[NM * k + 1];  // sum_paid(x), FP32-strike sum(p^2)
+    const double sgn = sc.is_put ? -1.0 : 1.0;
+    const double S = sc.spot;
+    double sum = a1, sum_sq = p2;
+    if (sc.has_strike) {
+      sum = sgn * (a1 - sc.kappa * paid);
+      const double sum32 = sgn * (a1 - (double)sc.kappa32 * paid);  // what the FP32 payoffs add up to
+      const double d = sgn * ((double)sc.kappa32 - sc.kappa);       // FP64-strike payoff = FP32-strike payoff + d on every paid sample
+      sum_sq = p2 + 2.0 * d * sum32 + d * d * paid;
+    }
+    if (NM == 2) {
+      b200mc_moments_t m;
+      m.sum = sum * S;
+      m.sum_sq = sum_sq * S * S;
+      m.n = f.samples;
+      static_cast<b200mc_moments_t*>(f.out)[(size_t)opt * n_scen + k] = m;
+    } else {
+      const double e1 = tot[NM * k + 2], e2 = tot[NM * k + 3], a2 = tot[NM * k + 4];  // sum S_T, sum S_T^2, sum_paid(x^2)
+      b200mc_cv_moments_t m;
+      m.sum_payoff = sum * S;
+      m.sum_payoff_sq = sum_sq * S * S;
+      m.sum_terminal = e1 * S;
+      m.sum_terminal_sq = e2 * S * S;
+      m.sum_payoff_terminal = sgn * (a2 - sc.kappa * a1) * S * S;  // payoff * S_T = +-(x - k) * x over the paid samples
+      m.n = f.samples;
+      static_cast<b200mc_cv_moments_t*>(f.out)[(size_t)opt * n_scen + k] = m;
+    }
+    if (f.done) __threadfence_system();
+  }
+  if (f.done) {  // host is polling: publish after every record is visible to it
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(f.done) = f.seq;
+  }
+}
+
+// The strike-bearing GBM payoffs of b200mc_params_t.
+__device__ __forceinline__ ScenScale vanilla_scale(const b200mc_params_t& p, bool is_put, bool has_strike = true) {
+  ScenScale sc;
+  sc.spot = p.S;
+  sc.kappa = B200MC_DDIV(p.K, p.S);
+  sc.kappa32 = (float)sc.kappa;
+  sc.has_strike = has_strike;
+  sc.is_put = is_put;
+  return sc;
+}
+
+__device__ __forceinline__ ScenScale scen_scale(const SimArgs& a, uint32_t opt, uint32_t k, bool is_put, bool has_strike) {
+  if (a.params) return vanilla_scale(a.params[(size_t)opt * a.n_scen + k], is_put, has_strike);
+  ScenScale sc;
+  sc.spot = a.inl.spot[k];
+  sc.kappa = a.inl.kappa64[k];
+  sc.kappa32 = a.inl.kappa[k];
+  sc.has_strike = has_strike;
+  sc.is_put = is_put;
+  return sc;
 }
 
 // ---- Philox call j of a path's word stream (layout documented in normal.cuh) -------------------
@@ -111,12 +361,16 @@ __device__ __forceinline__ void consume_call(const u32x4& x, F&& f) {
 }
 
 // SQUARED: the pairs carry rad^2 = -log2(u) instead of rad (see box_muller).
+// [j0, j1): the Philox calls of the path this thread visits (default: all of them; the lane-split European kernel
+// hands each lane of a group its own range).  The trailing 1..7 steps belong to call index n_steps / 8.
 template <int UNROLL = 1, bool SQUARED = false, class F>
-__device__ __forceinline__ void for_each_pair(uint64_t path, uint32_t n_steps, uint32_t stream, const PhiloxKeys& rk, F&& f) {
+__device__ __forceinline__ void for_each_pair(uint64_t path, uint32_t n_steps, uint32_t stream, const PhiloxKeys& rk, F&& f,
+                                              uint32_t j0 = 0u, uint32_t j1 = 0xffffffffu) {
   const uint32_t full = n_steps >> 3;
-  uint32_t j = 0;
+  const uint32_t stop = j1 < full ? j1 : full;
+  uint32_t j = j0;
   if (UNROLL > 1) {
-    for (; j + UNROLL <= full; j += UNROLL) {
+    for (; j + UNROLL <= stop; j += UNROLL) {
       u32x4 x[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) x[u] = draw4(path, j + u, stream, rk);
@@ -125,9 +379,9 @@ __device__ __forceinline__ void for_each_pair(uint64_t path, uint32_t n_steps, u
     }
   }
   // (plain #pragma unroll 2 / 4 of this loop measures 2.5% / 2% slower on the European kernel: profiles/r01_variants16_ffma2.txt)
-  for (; j < full; ++j) consume_call<SQUARED>(draw4(path, j, stream, rk), f);
+  for (; j < stop; ++j) consume_call<SQUARED>(draw4(path, j, stream, rk), f);
   const int rem = (int)(n_steps & 7u);
-  if (rem) {  // 1..7 trailing steps: same word layout, only the pairs that are needed
+  if (rem && j0 <= full && j1 > full) {  // 1..7 trailing steps: same word layout, only the pairs that are needed
     const u32x4 x = draw4(path, full, stream, rk);
     f(box_muller<SQUARED>(x.x), rem >= 2 ? 2 : 1);
     if (rem > 2) f(box_muller<SQUARED>(x.y), rem >= 4 ? 2 : 1);
@@ -161,18 +415,24 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 // (Accumulating the two branches in the halves of one packed FFMA2 register saves 4 issue slots per 8 steps and
 // measures 0.6% slower: the European loop is not issue-bound.  profiles/r01_variants16_ffma2.txt)
 template <int UNROLL = 1>
-__device__ __forceinline__ float terminal_sum(uint64_t path, uint32_t n_steps, uint32_t stream, const PhiloxKeys& rk) {
+__device__ __forceinline__ float terminal_sum(uint64_t path, uint32_t n_steps, uint32_t stream, const PhiloxKeys& rk,
+                                              uint32_t j0 = 0u, uint32_t j1 = 0xffffffffu) {
   float W = 0.0f;
   for_each_pair<UNROLL>(path, n_steps, stream, rk, [&](const NormalPair& p, int n_use) {
     W = fmaf(p.rad, p.cs, W);
     if (n_use > 1) W = fmaf(p.rad, p.sn, W);
-  });
+  }, j0, j1);
   return W;
 }
 
 // CV = true additionally accumulates sum S_T, sum S_T^2 and sum payoff*S_T per scenario (the
 // terminal-spot control variate of monte_carlo.py:154-186): 5 sums instead of 2.
-template <int NS, bool ANTI, int MINB, bool CV = false, int UNROLL = 1>
+//
+// SPLIT: launches too small to fill the chip with one thread per path (the reference's own sizes: 1e4..1e5 paths)
+// give each path to 2^split_shift ADJACENT lanes.  W is a plain sum over the path's draws, so every lane adds up a
+// contiguous range of the path's Philox calls and a butterfly of shuffles completes it; lane 0 of the group prices the
+// payoff.  Same draws, same stream contract - only the FP32 association of W changes (by ~1e-7 relative).
+template <int NS, bool ANTI, int MINB, bool CV = false, int UNROLL = 1, bool SPLIT = false>
 __global__ void __launch_bounds__(kBlock, MINB) european_kernel(const SimArgs a) {
   constexpr int NM = CV ? 5 : 2;
   __shared__ Coef coef[NS];
@@ -180,21 +440,43 @@ __global__ void __launch_bounds__(kBlock, MINB) european_kernel(const SimArgs a)
   const uint32_t tile = blockIdx.x - opt * a.tiles;
   if (threadIdx.x < NS) {
     const uint32_t k = threadIdx.x < a.n_scen ? threadIdx.x : a.n_scen - 1;
-    coef[threadIdx.x] = make_coef(a.params[(size_t)opt * a.n_scen + k], a.n_steps, 1.0f);
+    coef[threadIdx.x] = scen_coef(a, opt, k, 1.0f);
   }
   __syncthreads();
 
   float acc[NM * NS];
+  uint32_t paid[(NS + 3) / 4];
 #pragma unroll
   for (int i = 0; i < NM * NS; ++i) acc[i] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < (NS + 3) / 4; ++i) paid[i] = 0u;
 
   const uint32_t stream = a.stream_base + opt;
   const bool is_put = a.is_put != 0;
-  const uint64_t tile_first = (uint64_t)tile * (uint64_t)(kBlock * a.paths_per_thread);
+  const uint32_t shift = SPLIT ? a.split_shift : 0u;
+  const uint32_t lanes = 1u << shift;                      // lanes per path
+  const uint32_t sub = threadIdx.x & (lanes - 1u);         // this lane's share of the path
+  const uint32_t slot = threadIdx.x >> shift;              // the path this lane works on, within one pass of the CTA
+  const uint32_t per_pass = (uint32_t)kBlock >> shift;     // paths per pass
+  uint32_t j0 = 0u, j1 = 0xffffffffu;
+  if (SPLIT) {
+    const uint32_t calls = (a.n_steps + 7u) >> 3;
+    const uint32_t per = (calls + lanes - 1u) >> shift;
+    j0 = min(sub * per, calls);
+    j1 = min(j0 + per, calls);
+  }
+  const uint64_t tile_first = (uint64_t)tile * (uint64_t)(per_pass * a.paths_per_thread);
   for (uint32_t j = 0; j < a.paths_per_thread; ++j) {
-    const uint64_t local = tile_first + (uint64_t)j * kBlock + threadIdx.x;
-    if (local >= a.n_paths) break;  // paths are assigned in increasing order: nothing further for this thread
-    const float W = terminal_sum<UNROLL>(a.path_begin + local, a.n_steps, stream, a.rk);
+    const uint64_t local = tile_first + (uint64_t)j * per_pass + slot;
+    const bool live = local < a.n_paths;
+    if (!SPLIT && !live) break;  // paths are assigned in increasing order: nothing further for this thread
+    float W = 0.0f;
+    if (live) W = terminal_sum<UNROLL>(a.path_begin + local, a.n_steps, stream, a.rk, j0, j1);
+    if (SPLIT) {
+      if (__all_sync(0xffffffffu, !live)) break;
+      for (uint32_t off = 1u; off < lanes; off <<= 1) W += __shfl_xor_sync(0xffffffffu, W, off);
+      if (!live || sub != 0u) continue;
+    }
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
       const Coef q = coef[k];
@@ -202,17 +484,17 @@ __global__ void __launch_bounds__(kBlock, MINB) european_kernel(const SimArgs a)
       for (int mirror = 0; mirror < (ANTI ? 2 : 1); ++mirror) {
         const float e = mufu_ex2(fmaf(mirror ? -q.c : q.c, W, q.a));  // S_T / S_0
         const float p = vanilla(e, q.kappa, is_put);
-        acc[NM * k] += p;
-        acc[NM * k + 1] = fmaf(p, p, acc[NM * k + 1]);
+        add_sample<NS>(acc + NM * k, paid, k, e, p);
         if (CV) {
           acc[NM * k + 2] += e;
           acc[NM * k + 3] = fmaf(e, e, acc[NM * k + 3]);
-          acc[NM * k + 4] = fmaf(p, e, acc[NM * k + 4]);
+          acc[NM * k + 4] += p > 0.0f ? e * e : 0.0f;
         }
       }
     }
   }
-  block_reduce_store<NM * NS>(acc, a.partials + (size_t)blockIdx.x * (NM * NS));
+  finish_tile<NM, NS>(acc, paid, a.fold, opt, tile, a.tiles, a.n_scen,
+                      [&](uint32_t k) { return scen_scale(a, opt, k, is_put, true); });
 }
 
 // ============================ path-dependent kinds (register state) =============================
@@ -308,28 +590,31 @@ __device__ __forceinline__ void advance_pair_small(const NormalPair& p, int n_us
   }
 }
 
+// -> FP32 payoff p; x = the quantity compared with the strike ratio (p itself for the strike-less floating lookback).
 template <int KIND>
-__device__ __forceinline__ float path_payoff(float l, float aux, const Coef& q, const SimArgs& a) {
+__device__ __forceinline__ float path_payoff(float l, float aux, const Coef& q, const SimArgs& a, float& x) {
   const bool is_put = a.is_put != 0;
-  if (KIND == B200MC_ASIAN_ARITH) return vanilla(aux * q.inv_n, q.kappa, is_put);
-  if (KIND == B200MC_ASIAN_GEOM) return vanilla(mufu_ex2(aux * q.inv_n), q.kappa, is_put);
+  if (KIND == B200MC_ASIAN_ARITH) return vanilla(x = aux * q.inv_n, q.kappa, is_put);
+  if (KIND == B200MC_ASIAN_GEOM) return vanilla(x = mufu_ex2(aux * q.inv_n), q.kappa, is_put);
   const float sgn = a.sgn_negative ? -1.0f : 1.0f;
   const float e_T = mufu_ex2(sgn * l);
   if (KIND == B200MC_BARRIER) {
     const bool crossed = aux >= q.beta;
     const bool active = crossed == (a.barrier_in != 0);
+    x = e_T;
     return active ? vanilla(e_T, q.kappa, is_put) : 0.0f;
   }
   // LOOKBACK: aux tracks max(l) (sgn=+1) or max(-l) = -min(l) (sgn=-1)
   const float e_ext = mufu_ex2(sgn * aux);
-  if (a.lookback_fixed) return vanilla(e_ext, q.kappa, is_put);
-  return is_put ? e_ext - e_T : e_T - e_ext;
+  if (a.lookback_fixed) return vanilla(x = e_ext, q.kappa, is_put);
+  return x = (is_put ? e_ext - e_T : e_T - e_ext);
 }
 
 // One CTA's share of one option: paths_per_thread paths per thread, payoffs accumulated in FP32 per thread.
 // SMALL selects the multiplicative arithmetic-Asian update (state = S_t/S_0 instead of log2 of it).
 template <int KIND, int NS, bool SMALL, int UNROLL, int DEG = kSmallPacked4>
-__device__ __forceinline__ void simulate_tile(const SimArgs& a, const Coef (&q)[NS], uint32_t stream, uint64_t tile_first, float (&acc)[2 * NS]) {
+__device__ __forceinline__ void simulate_tile(const SimArgs& a, const Coef (&q)[NS], uint32_t stream, uint64_t tile_first, float (&acc)[2 * NS],
+                                              uint32_t (&paid)[(NS + 3) / 4]) {
   for (uint32_t j = 0; j < a.paths_per_thread; ++j) {
     const uint64_t local = tile_first + (uint64_t)j * kBlock + threadIdx.x;
     if (local >= a.n_paths) break;
@@ -342,9 +627,9 @@ __device__ __forceinline__ void simulate_tile(const SimArgs& a, const Coef (&q)[
     });
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
-      const float p = path_payoff<KIND>(l[k], aux[k], q[k], a);
-      acc[2 * k] += p;
-      acc[2 * k + 1] = fmaf(p, p, acc[2 * k + 1]);
+      float x;
+      const float p = path_payoff<KIND>(l[k], aux[k], q[k], a, x);
+      add_sample<NS>(acc + 2 * k, paid, k, x, p);
     }
   }
 }
@@ -356,7 +641,7 @@ __global__ void __launch_bounds__(kBlock, MINB) pathdep_kernel(const SimArgs a) 
   const uint32_t tile = blockIdx.x - opt * a.tiles;
   if (threadIdx.x < NS) {
     const uint32_t k = threadIdx.x < a.n_scen ? threadIdx.x : a.n_scen - 1;
-    coef_s[threadIdx.x] = make_coef(a.params[(size_t)opt * a.n_scen + k], a.n_steps, a.sgn_negative ? -1.0f : 1.0f);
+    coef_s[threadIdx.x] = scen_coef(a, opt, k, a.sgn_negative ? -1.0f : 1.0f);
   }
   __syncthreads();
   Coef q[NS];
@@ -364,8 +649,11 @@ __global__ void __launch_bounds__(kBlock, MINB) pathdep_kernel(const SimArgs a) 
   for (int k = 0; k < NS; ++k) q[k] = coef_s[k];
 
   float acc[2 * NS];
+  uint32_t paid[(NS + 3) / 4];
 #pragma unroll
   for (int i = 0; i < 2 * NS; ++i) acc[i] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < (NS + 3) / 4; ++i) paid[i] = 0u;
 
   const uint32_t stream = a.stream_base + opt;
   const uint64_t tile_first = (uint64_t)tile * (uint64_t)(kBlock * a.paths_per_thread);
@@ -374,23 +662,23 @@ __global__ void __launch_bounds__(kBlock, MINB) pathdep_kernel(const SimArgs a) 
 #pragma unroll
     for (int k = 0; k < NS; ++k) small = small && (fabsf(q[k].d) + fabsf(q[k].c) * kRadMax <= kSmallMove);  // NaN -> false
   }
-  if (small) simulate_tile<B200MC_ASIAN_ARITH, NS, true, UNROLL, DEG>(a, q, stream, tile_first, acc);  // CTA-uniform branch
-  else simulate_tile<KIND, NS, false, UNROLL>(a, q, stream, tile_first, acc);
-  block_reduce_store<2 * NS>(acc, a.partials + (size_t)blockIdx.x * (2 * NS));
+  if (small) simulate_tile<B200MC_ASIAN_ARITH, NS, true, UNROLL, DEG>(a, q, stream, tile_first, acc, paid);  // CTA-uniform branch
+  else simulate_tile<KIND, NS, false, UNROLL>(a, q, stream, tile_first, acc, paid);
+  // the floating-strike lookback pays S_T - min S / max S - S_T: no strike term to refine
+  const bool has_strike = !(KIND == B200MC_LOOKBACK && !a.lookback_fixed);
+  finish_tile<2, NS>(acc, paid, a.fold, opt, tile, a.tiles, a.n_scen,
+                     [&](uint32_t k) { return scen_scale(a, opt, k, a.is_put != 0, has_strike); });
 }
 
-// ================================ fold tile partials -> moments ================================
-// One warp per (option, scenario): lanes stride over the tiles in a fixed order, then a fixed
-// shuffle tree.  Re-scales the S_0-normalised sums to currency units in FP64.
-__global__ void __launch_bounds__(32) fold_kernel(const double* __restrict__ partials, const b200mc_params_t* __restrict__ params,
-                                                  b200mc_moments_t* __restrict__ out, uint32_t n_scen, uint32_t ns_pad,
-                                                  uint32_t tiles, double samples) {
-  const uint32_t opt = blockIdx.x / n_scen, k = blockIdx.x - opt * n_scen;
+// ================================ fold of the FP64 parity kernels ===============================
+// The from-normals kernels (f64_kernels.cuh, models.cuh, structured.cuh: test infrastructure fed the reference's own
+// draws) write one currency-unit (sum, sum^2) pair per CTA; one warp folds them in a fixed order.
+__global__ void __launch_bounds__(32) fold_kernel(const double* __restrict__ partials, b200mc_moments_t* __restrict__ out, uint32_t tiles,
+                                                  double samples) {
   double s1 = 0.0, s2 = 0.0;
   for (uint32_t t = threadIdx.x; t < tiles; t += 32) {
-    const double* p = partials + ((size_t)opt * tiles + t) * (2 * ns_pad) + 2 * k;
-    s1 += p[0];
-    s2 += p[1];
+    s1 += partials[2 * (size_t)t];
+    s2 += partials[2 * (size_t)t + 1];
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
@@ -398,38 +686,9 @@ __global__ void __launch_bounds__(32) fold_kernel(const double* __restrict__ par
     s2 += __shfl_xor_sync(0xffffffffu, s2, off);
   }
   if (threadIdx.x == 0) {
-    const double S = params ? params[(size_t)opt * n_scen + k].S : 1.0;  // parity mode folds currency sums
-    out[blockIdx.x].sum = s1 * S;
-    out[blockIdx.x].sum_sq = s2 * S * S;
-    out[blockIdx.x].n = samples;
-  }
-}
-
-// Control-variate flavour: 5 sums per (option, scenario), all quadratic ones scale with S^2.
-__global__ void __launch_bounds__(32) fold_cv_kernel(const double* __restrict__ partials, const b200mc_params_t* __restrict__ params,
-                                                     b200mc_cv_moments_t* __restrict__ out, uint32_t n_scen, uint32_t ns_pad,
-                                                     uint32_t tiles, double samples) {
-  const uint32_t opt = blockIdx.x / n_scen, k = blockIdx.x - opt * n_scen;
-  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  for (uint32_t t = threadIdx.x; t < tiles; t += 32) {
-    const double* p = partials + ((size_t)opt * tiles + t) * (5 * ns_pad) + 5 * k;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) s[i] += p[i];
-  }
-#pragma unroll
-  for (int i = 0; i < 5; ++i)
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], off);
-  if (threadIdx.x == 0) {
-    const double S = params[(size_t)opt * n_scen + k].S;
-    b200mc_cv_moments_t m;
-    m.sum_payoff = s[0] * S;
-    m.sum_payoff_sq = s[1] * S * S;
-    m.sum_terminal = s[2] * S;
-    m.sum_terminal_sq = s[3] * S * S;
-    m.sum_payoff_terminal = s[4] * S * S;
-    m.n = samples;
-    out[blockIdx.x] = m;
+    out->sum = s1;
+    out->sum_sq = s2;
+    out->n = samples;
   }
 }
 

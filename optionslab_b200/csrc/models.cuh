@@ -20,7 +20,7 @@ namespace b200mc {
 // step (:232) is the identity for v0 > 0 and is not repeated here.
 struct HestonArgs {
   const b200mc_heston_params_t* params;  // [n_opt]
-  double* partials;                      // [n_opt * tiles][2]
+  FoldArgs fold;                         // tile partials -> out[n_opt]
   uint64_t path_begin, n_paths;
   uint32_t n_opt, tiles, paths_per_thread, n_steps;
   PhiloxKeys rk;
@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(kBlock, 4) heston_kernel(const HestonArgs a) {
   __syncthreads();
   const HestonCoef c = coef_s;
   float acc[2] = {0.0f, 0.0f};
+  uint32_t paid[1] = {0u};
   const uint32_t stream = a.stream_base + ((a.is_put & B200MC_MODEL_SHARED_STREAM) ? 0u : opt);  // shared: CRN across the option axis
   const bool is_put = (a.is_put & B200MC_MODEL_PUT) != 0;
   const uint64_t tile_first = (uint64_t)tile * (uint64_t)(kBlock * a.paths_per_thread);
@@ -80,34 +81,15 @@ __global__ void __launch_bounds__(kBlock, 4) heston_kernel(const HestonArgs a) {
       u = fmaxf(fmaf(g, w, fmaf(u, c.one_minus_kdt, c.ktheta_dt)), 0.0f);  // heston.py:239-240
     });
     l += c.mu_total;
-    const float pay = vanilla(mufu_ex2(l), c.kappa_strike, is_put);
-    acc[0] += pay;
-    acc[1] = fmaf(pay, pay, acc[1]);
+    const float e = mufu_ex2(l);
+    add_sample<1>(acc, paid, 0, e, vanilla(e, c.kappa_strike, is_put));
   }
-  block_reduce_store<2>(acc, a.partials + (size_t)blockIdx.x * 2);
-}
-
-// Fold for parameter structs other than b200mc_params_t: the spot is passed as a strided FP64 field.
-__global__ void __launch_bounds__(32) fold_strided_kernel(const double* __restrict__ partials, const double* __restrict__ spot, uint32_t spot_stride,
-                                                          b200mc_moments_t* __restrict__ out, uint32_t tiles, double samples) {
-  const uint32_t opt = blockIdx.x;
-  double s1 = 0.0, s2 = 0.0;
-  for (uint32_t t = threadIdx.x; t < tiles; t += 32) {
-    const double* p = partials + ((size_t)opt * tiles + t) * 2;
-    s1 += p[0];
-    s2 += p[1];
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
-  }
-  if (threadIdx.x == 0) {
-    const double S = spot[(size_t)opt * spot_stride];
-    out[opt].sum = s1 * S;
-    out[opt].sum_sq = s2 * S * S;
-    out[opt].n = samples;
-  }
+  finish_tile<2, 1>(acc, paid, a.fold, opt, tile, a.tiles, 1u, [&](uint32_t) {
+    const b200mc_heston_params_t p = a.params[opt];
+    ScenScale sc;
+    sc.spot = p.S, sc.kappa = p.K / p.S, sc.kappa32 = (float)sc.kappa, sc.has_strike = true, sc.is_put = is_put;
+    return sc;
+  });
 }
 
 // ======================================= Merton / Kou jump diffusion =============================================
@@ -122,7 +104,7 @@ __global__ void __launch_bounds__(32) fold_strided_kernel(const double* __restri
 struct JumpArgs {
   const b200mc_params_t* params;       // [n_opt] (one scenario)
   const b200mc_jump_params_t* jumps;   // [n_opt]
-  double* partials;
+  FoldArgs fold;                       // tile partials -> out[n_opt]
   uint64_t path_begin, n_paths;
   uint32_t n_opt, tiles, paths_per_thread, n_steps;
   PhiloxKeys rk;
@@ -177,6 +159,7 @@ __global__ void __launch_bounds__(kBlock, 4) jump_kernel(const JumpArgs a) {
   __syncthreads();
   const JumpCoef c = coef_s;
   float acc[2] = {0.0f, 0.0f};
+  uint32_t paid[1] = {0u};
   const uint32_t stream = a.stream_base + ((a.is_put & B200MC_MODEL_SHARED_STREAM) ? 0u : opt);  // shared: CRN across the option axis
   const bool is_put = (a.is_put & B200MC_MODEL_PUT) != 0;
   const uint64_t tile_first = (uint64_t)tile * (uint64_t)(kBlock * a.paths_per_thread);
@@ -216,11 +199,10 @@ __global__ void __launch_bounds__(kBlock, 4) jump_kernel(const JumpArgs a) {
         l += jump_log2;  // -log2(U)/eta is the exponential jump already expressed in log2 units of S
       }
     }
-    const float pay = vanilla(mufu_ex2(l), c.kappa_strike, is_put);
-    acc[0] += pay;
-    acc[1] = fmaf(pay, pay, acc[1]);
+    const float e = mufu_ex2(l);
+    add_sample<1>(acc, paid, 0, e, vanilla(e, c.kappa_strike, is_put));
   }
-  block_reduce_store<2>(acc, a.partials + (size_t)blockIdx.x * 2);
+  finish_tile<2, 1>(acc, paid, a.fold, opt, tile, a.tiles, 1u, [&](uint32_t) { return vanilla_scale(a.params[opt], is_put); });
 }
 
 // ================================ FP64 parity kernels (caller-supplied draws) =====================================

@@ -38,7 +38,7 @@ static_assert(kBlock == 1 << kSobolTidBits, "thread-bit split assumes 256 thread
 
 struct SobolArgs {
   const b200mc_params_t* params;  // [n_opt][n_scen]
-  double* partials;               // [n_opt * tiles][2 * NS]
+  FoldArgs fold;                  // tile partials -> out[n_opt][n_scen]
   const uint32_t* dirnums;        // [n_steps][kSobolWords], natural (binary) order
   const uint32_t* shift;          // [n_steps]
   uint64_t point_begin;           // multiple of 1 << kSobolAlignShift
@@ -177,8 +177,11 @@ __global__ void __launch_bounds__(kBlock, NS <= 2 ? 4 : 2) qmc_european_kernel(c
   }
 
   float acc[2 * NS];
+  uint32_t paid[(NS + 3) / 4];
 #pragma unroll
   for (int i = 0; i < 2 * NS; ++i) acc[i] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < (NS + 3) / 4; ++i) paid[i] = 0u;
   const bool is_put = a.is_put != 0;
   const uint64_t first = ((uint64_t)tile * kBlock + threadIdx.x) * kPoints;  // local index of this thread's point 0
   if (a.terminal_out) {  // simulation layer (gbm_qmc.py:44-46, :70-76): the terminal prices of scenario 0, one option
@@ -198,13 +201,13 @@ __global__ void __launch_bounds__(kBlock, NS <= 2 ? 4 : 2) qmc_european_kernel(c
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         const QmcCoef q = coef[s];
-        const float p = vanilla(mufu_ex2(fmaf(q.c, W[k], q.a)), q.kappa, is_put);
-        acc[2 * s] += p;
-        acc[2 * s + 1] = fmaf(p, p, acc[2 * s + 1]);
+        const float e = mufu_ex2(fmaf(q.c, W[k], q.a));
+        add_sample<NS>(acc + 2 * s, paid, s, e, vanilla(e, q.kappa, is_put));
       }
     }
   }
-  block_reduce_store<2 * NS>(acc, a.partials + (size_t)blockIdx.x * (2 * NS));
+  finish_tile<2, NS>(acc, paid, a.fold, opt, tile, a.tiles, a.n_scen,
+                     [&](uint32_t k) { return vanilla_scale(a.params[(size_t)opt * a.n_scen + k], is_put); });
 }
 
 // Inspection: the Sobol integers of points [point_begin, point_begin + n_points) x n_dims, row-major.

@@ -6,7 +6,7 @@
 // observation schedule is a count-down register shared by all scenarios of the thread; it is the same for every
 // thread of the launch, so the event branch is warp-uniform.
 //
-// Output conventions (include/b200mc.h): CLIQUET accumulates the undiscounted payoff per unit spot (the fold kernel
+// Output conventions (include/b200mc.h): CLIQUET accumulates the undiscounted payoff per unit spot (the fold
 // multiplies by S); AUTOCALLABLE accumulates the DISCOUNTED payoff per unit notional (folded with S = 1).
 #pragma once
 #include <cuda_runtime.h>
@@ -64,8 +64,11 @@ __global__ void __launch_bounds__(kBlock, MINB) structured_kernel(const Structur
   const float step_frac = (float)g.period / (float)a.n_steps;             // t_i / T per observation
 
   float acc[2 * NS];
+  uint32_t paid[(NS + 3) / 4];
 #pragma unroll
   for (int i = 0; i < 2 * NS; ++i) acc[i] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < (NS + 3) / 4; ++i) paid[i] = 0u;
 
   const uint32_t stream = a.stream_base + opt;
   const uint64_t tile_first = (uint64_t)tile * (uint64_t)(kBlock * a.paths_per_thread);
@@ -127,11 +130,16 @@ __global__ void __launch_bounds__(kBlock, MINB) structured_kernel(const Structur
         if (aux[k] <= l_knock_in && l[k] < 0.0f) f = mufu_ex2(l[k]);
         p = f * q[k].disc_T;
       }
-      acc[2 * k] += p;
-      acc[2 * k + 1] = fmaf(p, p, acc[2 * k + 1]);
+      add_sample<NS>(acc + 2 * k, paid, k, p, p);
     }
   }
-  block_reduce_store<2 * NS>(acc, a.partials + (size_t)blockIdx.x * (2 * NS));
+  // neither product has a strike term; CLIQUET payoffs are per unit spot, AUTOCALLABLE per unit notional
+  finish_tile<2, NS>(acc, paid, a.fold, opt, tile, a.tiles, a.n_scen, [&](uint32_t k) {
+    ScenScale sc;
+    sc.spot = KIND == B200MC_CLIQUET ? a.params[(size_t)opt * a.n_scen + k].S : 1.0;
+    sc.kappa = 0.0, sc.kappa32 = 0.0f, sc.has_strike = false, sc.is_put = false;
+    return sc;
+  });
 }
 
 // ---- FP64 on caller-supplied draws: the reference's statements, one thread per path -----------------------------

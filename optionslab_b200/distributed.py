@@ -127,6 +127,18 @@ class local_devices:
         return False
 
 
+def local_device_count() -> int:
+    """Devices of the active ``local_devices`` block (0 outside one)."""
+    return len(_local) if _local is not None else 0
+
+
+def default_engine():
+    """The engine an unsharded call runs on: the first device of a ``local_devices`` block, else this process's device."""
+    from . import _ffi
+
+    return _ffi.get_engine(_local[0]) if _local else _ffi.get_engine()
+
+
 def run_sharded(fn, n_units: int, empty, partition=partition_paths) -> np.ndarray:
     """Run ``fn(engine, begin, count) -> moments`` over this process's share of ``n_units`` global paths (or Sobol points)
     and return the moments of ALL units: plain call when unsharded, threads + host sum under ``local_devices``, partition +

@@ -10,6 +10,7 @@ backend seeds option ``i`` with ``seed + i``, monte_carlo_unified.py:190) — an
 from __future__ import annotations
 
 import logging
+import math
 import threading
 from typing import Literal, Optional, Tuple, Union
 
@@ -63,8 +64,8 @@ class MonteCarloPricerUni:
               q: float = 0.0, seed: Optional[int] = None) -> float:
         self._validate(S, K, T, sigma, option_type)
         try:
-            m = self._batch_moments([S], [K], [T], [r], [sigma], [q], option_type, seed)
-            return float(runtime.discounted_price(m[0, 0], r, T))
+            (total, _, n), = self._scalar_moments([(S, K, T, r, sigma, q)], option_type, seed)
+            return runtime.discount(r, T) * total / n
         except Exception as e:  # same wrapping as monte_carlo_unified.py:510-511
             raise MonteCarloError(f"Monte Carlo pricing failed: {e}")
 
@@ -74,12 +75,18 @@ class MonteCarloPricerUni:
             seed = int(self.rng.integers(0, 2**31))
         self._validate(S + h, K, T, sigma, option_type)
         self._validate(S - h, K, T, sigma, option_type)
-        try:
-            m = self._batch_moments([S], [K], [T], [r], [sigma], [q], option_type, seed, bumps=(h, 0.0, -h))
+        try:  # S+h, S, S-h are three scenarios of ONE launch: same draws (monte_carlo_unified.py:547-549 re-seeds instead)
+            m = self._scalar_moments([(S + h, K, T, r, sigma, q), (S, K, T, r, sigma, q), (S - h, K, T, r, sigma, q)], option_type, seed)
         except Exception as e:
             raise MonteCarloError(f"Monte Carlo pricing failed: {e}")
-        up, mid, down = (float(x) for x in runtime.discounted_price(m[0], r, T))
+        disc = runtime.discount(r, T)
+        up, mid, down = (disc * total / n for total, _, n in m)
         return (up - down) / (2 * h), (up - 2 * mid + down) / (h**2)
+
+    def _scalar_moments(self, scenarios, option_type, seed):
+        spec = _ffi.make_spec(_ffi.EUROPEAN, self.num_steps, is_put=(option_type == "put"), antithetic=True)
+        with self._lock:
+            return runtime.simulate_scalars(spec, scenarios, seed if seed is not None else self.seed, self.num_simulations)
 
     @staticmethod
     def _arrays(S_vals, K_vals, T_vals, r_vals, sigma_vals, q_vals):
@@ -114,14 +121,11 @@ class MonteCarloPricerUni:
 
     # -- fused Greeks (PricerProtocol + price_scenarios) ----------------------------------------
     def price_scenarios(self, scenarios, option_type, seed: Optional[int] = None, **_ignored):
-        sc = np.asarray(scenarios, dtype=np.float64).reshape(-1, 6)
+        scenarios = [tuple(float(x) for x in sc) for sc in scenarios]
         out = []
-        for lo in range(0, len(sc), _ffi.MAX_SCENARIOS):
-            blk = sc[lo:lo + _ffi.MAX_SCENARIOS]
-            params = _ffi.make_params(blk[:, 0], blk[:, 1], blk[:, 2], blk[:, 3], blk[:, 4], blk[:, 5])[None, :]
-            spec = _ffi.make_spec(_ffi.EUROPEAN, self.num_steps, is_put=(option_type == "put"), antithetic=True)
-            m = runtime.simulate(spec, params, seed if seed is not None else self.seed, self.num_simulations)[0]
-            out += [float(p) for p in runtime.discounted_price(m, blk[:, 3], blk[:, 2])]
+        for lo in range(0, len(scenarios), _ffi.MAX_SCENARIOS):
+            blk = scenarios[lo:lo + _ffi.MAX_SCENARIOS]
+            out += [runtime.discount(sc[3], sc[2]) * total / n for sc, (total, _, n) in zip(blk, self._scalar_moments(blk, option_type, seed))]
         return out
 
     def greeks(self, S, K, T, r, sigma, option_type="call", q=0.0, include_second_order=True):

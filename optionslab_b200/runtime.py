@@ -38,6 +38,21 @@ def simulate(spec: _ffi.Spec, params: np.ndarray, seed: int, n_paths: int, *, st
         n_paths, lambda: np.zeros(np.shape(params), dtype=dtype))
 
 
+def simulate_scalars(spec: _ffi.Spec, scenarios, seed: int, n_paths: int, *, barrier: float = 0.0, stream_base: int = 0):
+    """One option, up to 16 common-random-number scenarios given as (S, K, T, r, sigma, q) tuples -> list of
+    (sum, sum_sq, n).  The single-device case takes the engine's latency path (no NumPy, one launch, mapped result);
+    sharded contexts go through ``simulate``."""
+    if n_paths < 1:
+        raise MonteCarloError("n_paths must be >= 1")
+    ctx = distributed.current()
+    if (ctx is None or ctx.world_size == 1) and distributed.local_device_count() <= 1:
+        return distributed.default_engine().simulate_scalars(spec, scenarios, seed, n_paths, barrier=barrier, stream_base=stream_base)
+    sc = np.asarray(scenarios, dtype=np.float64).reshape(-1, 6)
+    params = _ffi.make_params(sc[:, 0], sc[:, 1], sc[:, 2], sc[:, 3], sc[:, 4], sc[:, 5], barrier)[None, :]
+    m = simulate(spec, params, seed, n_paths, stream_base=stream_base)[0]
+    return [(float(x["sum"]), float(x["sum_sq"]), float(x["n"])) for x in m]
+
+
 def simulate_sobol(spec: _ffi.Spec, params: np.ndarray, seed, n_points: int) -> np.ndarray:
     """Moments [n_opt, n_scen] over the first ``n_points`` points of the reference's scrambled Sobol sequence
     (gbm_qmc.py:32-33: d = n_steps, scramble=True, seed).  Ranks take 4096-aligned slices of the same sequence."""
@@ -66,6 +81,11 @@ def control_variate_price(m, S, T, r, q) -> float:
     var_s = (float(m["sum_terminal_sq"]) - float(m["sum_terminal"]) ** 2 / n) / (n - 1)
     beta = cov_ds / var_s if var_s > 1e-10 else 0.0
     return float(mean_d - beta * (mean_s - forward))
+
+
+def discount(r, T) -> float:
+    """exp(-rT) through NumPy's exp, so scalar and batched routes (discounted_price) round identically."""
+    return float(np.exp(-r * T))
 
 
 def discounted_price(moments, r, T):

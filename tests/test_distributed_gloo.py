@@ -82,6 +82,12 @@ class _OracleEngine:
                 out[opt, k] = (pay.sum(), (pay**2).sum(), len(pay))
         return out
 
+    def simulate_scalars(self, spec, scenarios, seed, n_paths, *, barrier=0.0, stream_base=0, path_begin=0):
+        """The unsharded latency path of _ffi.Engine: one option, (S, K, T, r, sigma, q) tuples -> (sum, sum_sq, n) tuples."""
+        sc = np.asarray(scenarios, dtype=np.float64).reshape(-1, 6)
+        params = _ffi.make_params(sc[:, 0], sc[:, 1], sc[:, 2], sc[:, 3], sc[:, 4], sc[:, 5], barrier)[None, :]
+        m = self.simulate(spec, params, seed, n_paths, stream_base=stream_base, path_begin=path_begin)[0]
+        return [(float(x["sum"]), float(x["sum_sq"]), float(x["n"])) for x in m]
 
     def simulate_structured(self, spec, product, params, seed, n_paths, *, stream_base=0, path_begin=0):
         params = np.asarray(params)

@@ -32,32 +32,32 @@ def _heston_params(S, K, T, r, q, **h):
 # ------------------------------------------------------------------ test 1: FP64 on the reference's draws
 @pytest.mark.parametrize("n_paths,n_steps", [(20000, 50), (4097, 7), (1, 3), (129, 33)])
 @pytest.mark.parametrize("ot", ["call", "put"])
-def test_heston_fp64_from_reference_draws(engine, goldens, n_paths, n_steps, ot):
+def test_heston_fp64_from_reference_draws(engine, goldens, anchored, n_paths, n_steps, ot):
     Z = orc.heston_draws(42, n_paths, n_steps)
     want = orc.heston_payoffs_from_normals(**PT, q=0.01, **HES, Z=Z, option_type=ot)
     got, mom = engine.heston_from_normals(_heston_params(**PT, q=0.01, **HES), ot == "put", Z)
     assert np.max(np.abs(got - want) / np.maximum(want + PT["K"], PT["K"])) <= TOL
     assert mom["n"] == n_paths and mom["sum"] == pytest.approx(float(np.sum(want)), rel=TOL)
     key = f"heston_{ot}_{n_paths}x{n_steps}"
-    if goldens["numpy"] == np.__version__ and key in goldens["models"]:
+    if key in goldens["models"] and anchored():
         price = float(np.exp(-PT["r"] * PT["T"]) * mom["sum"] / mom["n"])
         assert price == pytest.approx(goldens["models"][key], rel=TOL)
 
 
-def test_heston_fp64_with_truncation_active(engine, goldens):
+def test_heston_fp64_with_truncation_active(engine, goldens, anchored):
     h = dict(kappa=1.0, theta=0.09, sigma_v=0.8, rho=-0.3, v0=0.02)  # Feller violated: v hits the floor
     Z = orc.heston_draws(7, 20000, 50)
     want = orc.heston_payoffs_from_normals(100.0, 110.0, 0.5, 0.03, 0.0, **h, Z=Z, option_type="call")
     got, mom = engine.heston_from_normals(_heston_params(100.0, 110.0, 0.5, 0.03, 0.0, **h), False, Z)
     assert np.max(np.abs(got - want)) <= TOL * 110.0
-    if goldens["numpy"] == np.__version__:
+    if anchored():
         assert float(np.exp(-0.03 * 0.5) * mom["sum"] / mom["n"]) == pytest.approx(goldens["models"]["heston_feller_violated_call_20000x50"], rel=TOL)
 
 
 @pytest.mark.parametrize("model", ["merton", "kou"])
 @pytest.mark.parametrize("n_paths,n_steps", [(5000, 20), (20000, 50)])
 @pytest.mark.parametrize("ot", ["call", "put"])
-def test_jump_diffusion_fp64_from_reference_draws(engine, goldens, model, n_paths, n_steps, ot):
+def test_jump_diffusion_fp64_from_reference_draws(engine, goldens, anchored, model, n_paths, n_steps, ot):
     if model == "merton":
         dW, J = orc.merton_draws(42, **MER, T=PT["T"], n_paths=n_paths, n_steps=n_steps)
         lk = MER["lambda_j"] * orc.merton_kappa(MER["mu_j"], MER["sigma_j"])
@@ -68,7 +68,7 @@ def test_jump_diffusion_fp64_from_reference_draws(engine, goldens, model, n_path
     want = orc.jump_payoffs_from_draws(**PT, sigma=0.2, q=0.01, lambda_kappa=lk, dW=dW, J=J, option_type=ot)
     got, mom = engine.jump_diffusion_from_draws(_ffi.make_params(**PT, sigma=0.2, q=0.01), lk, ot == "put", dW, J)
     assert np.max(np.abs(got - want) / np.maximum(want + PT["K"], PT["K"])) <= TOL
-    if goldens["numpy"] == np.__version__:
+    if anchored():
         price = float(np.exp(-PT["r"] * PT["T"]) * mom["sum"] / mom["n"])
         assert price == pytest.approx(goldens["models"][f"{model}_{ot}_{n_paths}x{n_steps}"], rel=TOL)
 
@@ -176,12 +176,12 @@ def test_model_scenarios_share_draws_and_match_separate_repricings():
     fused = hes.price_scenarios(sc, "put", n_paths=200_000, n_steps=50, seed=9)
     for (S, K, T, r, v0, q), got in zip(sc, fused):
         one = ob.HestonPricer(kappa=2.0, theta=0.04, sigma_v=0.3, rho=-0.7, v0=v0).price_monte_carlo(S, K, T, r, q, "put", 200_000, 50, seed=9)
-        assert got == pytest.approx(one, rel=1e-9)
+        assert got == pytest.approx(one, rel=1e-8)  # tile plans differ: FP32 thread sums associate differently
     for pricer in (ob.MertonJumpDiffusion(**MER), ob.KouJumpDiffusion(**KOU)):
         sj = [(100.0, 100.0, 1.0, 0.05, 0.2, 0.01), (99.0, 100.0, 1.0, 0.05, 0.21, 0.01)]
         fused = pricer.price_scenarios(sj, "call", n_paths=200_000, n_steps=40, seed=5)
         for (S, K, T, r, sig, q), got in zip(sj, fused):
-            assert got == pytest.approx(pricer.price_monte_carlo(S, K, T, r, sig, "call", q, 200_000, 40, seed=5), rel=1e-9)
+            assert got == pytest.approx(pricer.price_monte_carlo(S, K, T, r, sig, "call", q, 200_000, 40, seed=5), rel=1e-8)
 
 
 def test_adapter_greeks_fused_equal_call_by_call_and_approach_black_scholes():

@@ -51,7 +51,7 @@ def test_device_inverse_normal_matches_norm_ppf(engine):
 
 @pytest.mark.parametrize("n,d", [(4096, 7), (10000, 50), (16384, 64)])
 @pytest.mark.parametrize("ot", ["call", "put"])
-def test_fp64_parity_on_the_reference_qmc_draws(engine, goldens, n, d, ot):
+def test_fp64_parity_on_the_reference_qmc_draws(engine, goldens, anchored, n, d, ot):
     """Correctness test 1 for the QMC backend: the reference's own normals -> payoffs within 1e-12."""
     normals = orc.qmc_normals_from_uniforms(_ref_uniforms(42, n, d))
     terminal = orc.qmc_terminal_from_normals(P["S"], P["T"], P["r"], P["sigma"], 0.0, normals)
@@ -60,8 +60,7 @@ def test_fp64_parity_on_the_reference_qmc_draws(engine, goldens, n, d, ot):
     got, mom = engine.payoffs_from_normals(spec, _ffi.make_params(**P), normals)
     assert np.max(np.abs(got - want) / np.maximum(terminal, P["K"])) <= 1e-12
     price = float(np.exp(-P["r"] * P["T"]) * mom["sum"] / mom["n"])
-    import scipy
-    if goldens["numpy"] == np.__version__ and goldens["scipy"] == scipy.__version__:
+    if anchored(scipy=True):
         assert price == pytest.approx(goldens["qmc"][f"{n}x{d}_{ot}"]["price"], rel=1e-12)
 
 

@@ -89,7 +89,7 @@ def test_config2_greeks_1m_x_252_crn_single_launch(engine):
     pr = ob.MonteCarloPricer(1_000_000, 252, seed=42)
     before = engine.kernel_launches()
     g = pr.greeks(**P, option_type="call")
-    assert engine.kernel_launches() - before == 2  # one fused simulation + one fold for all 14 scenarios
+    assert engine.kernel_launches() - before == 1  # ONE launch: 14 scenarios simulated and folded by the same kernel
     d_bs, g_bs, v_bs = orc.black_scholes_greeks(**P)
     assert g["price"] == pytest.approx(BS_CALL, abs=3 * 0.0105)
     assert g["delta"] == pytest.approx(d_bs, abs=1.5e-3) and g["delta"] == pytest.approx(REF_1M["delta"], abs=2e-3)
@@ -125,17 +125,88 @@ def test_control_variate_next_row(engine):
         engine.simulate(_ffi.make_spec(_ffi.ASIAN_ARITH, 8), _ffi.make_params(**P).reshape(1, 1), 3, 100, control_variate=True)
 
 
-def test_fused_greeks_equal_separate_repricings_bitwise():
-    """One launch with 14 scenarios == 14 launches of 1 scenario (same draws, same reduction order)."""
+def test_fused_greeks_equal_separate_repricings_bitwise(engine):
+    """One launch with 14 scenarios == 14 launches of 1 scenario (same draws, same per-scenario expression shape, same
+    reduction order).  Bit-for-bit equality needs both launches to cut the paths into the same tiles - the planner sizes
+    tiles from the scenario count too - so the tile shape is pinned for that half of the test; with the automatic plan
+    the two routes agree to FP32 summation order."""
     pr = ob.MonteCarloPricer(50_000, 32, seed=9)
 
     class CallByCall:  # hides price_scenarios: forces the reference's route
         def price(self, *a, **k):
             return pr.price(*a, **k)
 
+    for shift, ppt in ((0, 1), (1, 3), (2, 7)):
+        engine.set_plan(shift, ppt)
+        try:
+            fused = ob.compute_greeks_unified(pr, **P, option_type="put", q=0.01)
+            separate = ob.compute_greeks_unified(CallByCall(), **P, option_type="put", q=0.01)
+        finally:
+            engine.set_plan()
+        assert dict(fused) == dict(separate)
     fused = ob.compute_greeks_unified(pr, **P, option_type="put", q=0.01)
     separate = ob.compute_greeks_unified(CallByCall(), **P, option_type="put", q=0.01)
-    assert dict(fused) == dict(separate)
+    assert fused["price"] == pytest.approx(separate["price"], rel=1e-6)
+    assert fused["delta"] == pytest.approx(separate["delta"], abs=1e-5) and fused["vega"] == pytest.approx(separate["vega"], abs=2e-3)
+
+
+def test_lane_split_plans_price_the_same_draws(engine):
+    """european_kernel<SPLIT>: 2, 4 or 8 adjacent lanes share one path's Philox calls and complete W = sum(z) with a
+    shuffle butterfly.  Same stream contract, so every tile shape agrees with the one-thread-per-path launch to FP32
+    summation order and with the FP64 oracle on the same draws - ragged path / step counts included."""
+    for n_paths, n_steps, seed in ((10_000, 252, 3), (1_237, 100, 4), (100_000, 33, 5), (257, 1000, 6), (5_000, 31, 7)):
+        Z = po.normals(seed, n_paths, n_steps)
+        for ot in ("call", "put"):
+            want = orc.vanilla_payoffs(orc.gbm_terminal_from_normals(P["S"], P["T"], P["r"], P["sigma"], 0.0, Z), P["K"], ot)
+            spec = _ffi.make_spec(_ffi.EUROPEAN, n_steps, is_put=ot == "put", antithetic=True)
+            params = np.stack([_ffi.make_params(**P), _ffi.make_params(**dict(P, sigma=0.21))]).reshape(1, 2)
+            base = None
+            for shift in (0, 1, 2, 3):
+                for ppt in (0, 1, 5):
+                    engine.set_plan(shift, ppt)
+                    try:
+                        m = engine.simulate(spec, params, seed, n_paths)[0]
+                    finally:
+                        engine.set_plan()
+                    assert m["n"][0] == 2 * n_paths
+                    assert m["sum"][0] == pytest.approx(want.sum(), rel=3e-4)
+                    if base is None:
+                        base = m
+                    assert m["sum"] == pytest.approx(base["sum"], rel=2e-6) and m["sum_sq"] == pytest.approx(base["sum_sq"], rel=4e-6)
+    # the automatic plan of an under-filled launch does split, and repeats bit for bit
+    spec = _ffi.make_spec(_ffi.EUROPEAN, 252, antithetic=True)
+    a = engine.simulate(spec, _ffi.make_params(**P).reshape(1, 1), 1, 10_000)
+    b = engine.simulate(spec, _ffi.make_params(**P).reshape(1, 1), 1, 10_000)
+    assert a.tobytes() == b.tobytes()
+
+
+def test_launches_on_different_streams_do_not_share_scratch_unordered(engine):
+    """b200mc_simulate_device on two caller streams: consecutive enqueues share the tile partials and the
+    ticket counters, so the engine orders each enqueue after the previous one; interleaved results equal the
+    one-stream results bit for bit."""
+    import torch
+
+    dev = torch.device("cuda", 0)
+    specs = [_ffi.make_spec(_ffi.EUROPEAN, 64, antithetic=True), _ffi.make_spec(_ffi.ASIAN_ARITH, 48)]
+    n_opt = 96
+    K = np.linspace(80.0, 120.0, n_opt)
+    params = torch.from_numpy(_ffi.make_params(100.0, K, 1.0, 0.05, 0.2).view(np.float64).reshape(n_opt, 8).copy()).to(dev)
+    main = torch.cuda.current_stream(dev)
+
+    def run(streams):
+        outs = [torch.zeros((n_opt, 3), dtype=torch.float64, device=dev) for _ in range(6)]
+        for i, out in enumerate(outs):
+            st = streams[i % len(streams)]
+            engine.simulate_device(specs[i % 2], params.data_ptr(), n_opt, 1, 7 + i, 40_000 + 1000 * i, out.data_ptr(), st.cuda_stream)
+        torch.cuda.synchronize(dev)
+        return [o.cpu().numpy() for o in outs]
+
+    want = run([main])
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    for _ in range(3):
+        got = run([s1, s2])
+        for g, w in zip(got, want):
+            assert g.tobytes() == w.tobytes()
 
 
 def test_config3_asian_4m_x_252():
