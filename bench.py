@@ -230,11 +230,13 @@ def run_engine_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    fused = ctx is not None and ctx.fused  # the ranks' moments are added up in the tail of the simulation kernel (NVLink peer reads)
+
     def device_step():
         flush.zero_()
         eng.simulate_device(spec, params_dev.data_ptr(), N_OPT, 1, SEED, count, out_dev.data_ptr(), stream.cuda_stream,
-                            path_begin=begin)
-        if world > 1:
+                            path_begin=begin, allreduce=fused)
+        if world > 1 and not fused:
             dist.all_reduce(out_dev)
 
     peaks = eng.measure_peaks() if rank == 0 else None
@@ -293,8 +295,9 @@ def run_engine_arm(args):
 
         def asian_step():
             flush.zero_()
-            eng.simulate_device(aspec, params_dev.data_ptr(), N_OPT, 1, SEED, count, aout.data_ptr(), stream.cuda_stream, path_begin=begin)
-            if world > 1:
+            eng.simulate_device(aspec, params_dev.data_ptr(), N_OPT, 1, SEED, count, aout.data_ptr(), stream.cuda_stream, path_begin=begin,
+                                allreduce=fused)
+            if world > 1 and not fused:
                 dist.all_reduce(aout)
 
         asian_step()
@@ -397,7 +400,9 @@ def run_engine_arm(args):
             "ms_per_step": 1e3 * elapsed_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_options": N_OPT, "paths_per_option": N_PATHS, "steps_per_path": N_STEPS,
-                       "parallelism": f"paths partitioned over {world} rank(s), one all-reduce of {N_OPT}x3 doubles per step",
+                       "parallelism": f"paths partitioned over {world} rank(s); the {N_OPT}x3 doubles of moments are summed over the ranks "
+                                      + ("in the tail of the simulation kernel over NVLink peer memory (b200mc_simulate_allreduce_device)" if fused
+                                         else "by one NCCL all-reduce per step" if world > 1 else "(single rank: no exchange)"),
                        "l2": "256 MiB memset between steps (inside the timed region); the kernel's HBM input is 262 KB"},
             "options_per_sec": N_OPT * args.steps / elapsed_s,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(params_np.nbytes),

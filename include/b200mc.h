@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200MC_ABI_VERSION 6
+#define B200MC_ABI_VERSION 7
 #define B200MC_MAX_SCENARIOS 16
 
 typedef struct b200mc_engine b200mc_engine_t;
@@ -31,6 +31,7 @@ typedef enum {
   B200MC_OK = 0,
   B200MC_ERR_INVALID = -1, /* bad argument (null pointer, zero size, unknown kind, ...) */
   B200MC_ERR_CUDA = -2,    /* CUDA runtime failure; message has the cudaError string */
+  B200MC_ERR_COMM = -3,    /* multi-GPU exchange failure (peer mapping, oversized record block, peer rank timed out) */
   B200MC_ERR_NOMEM = -4    /* device or pinned-host allocation failed */
 } b200mc_status;
 
@@ -174,6 +175,37 @@ int b200mc_simulate_device(b200mc_engine_t* eng, const b200mc_spec_t* spec, cons
                            uint32_t n_opt, uint32_t n_scen, uint64_t seed, uint32_t stream_base,
                            uint64_t path_begin, uint64_t n_paths, b200mc_moments_t* out_dev,
                            void* cuda_stream);
+
+/* ---- multi-GPU: the same launch with the all-reduce fused into its tail ------------------------------------------- *
+ * rank g of G simulates global paths [g*N/G, (g+1)*N/G) of every option and the per-(option,
+ * scenario) moment records are summed over the ranks.  Here that sum is the LAST thing the simulation kernel does: the
+ * CTA that folds a rank's last option publishes the rank's records in its exchange block, waits for the other ranks'
+ * flags and adds their records over NVLink peer memory in rank order (identical bits on every rank) - no host hop, no
+ * second kernel, no library collective.  Up to 8 ranks (one NVSwitch domain), one process per GPU or several devices of
+ * one process.
+ *
+ * Connecting (collective; a barrier must separate it from the first b200mc_simulate_allreduce):
+ *   1. every rank:  b200mc_comm_export(eng, handle)      -> 64-byte CUDA IPC handle of its exchange block
+ *   2. all-gather the handles with whatever the host side has (torch.distributed, MPI, a file)
+ *   3. every rank:  b200mc_comm_connect(eng, rank, world, handles[world][64])
+ *   one process, several devices:  b200mc_comm_connect_local(engines, n)  (rank = index; peer access instead of IPC)
+ * b200mc_simulate_allreduce[_device] then behave like b200mc_simulate[_device] on this rank's path range, except that
+ * `out` receives the moments of ALL ranks' paths; every rank must make the same sequence of calls.  n_paths may be 0
+ * (a rank with an empty share still contributes).  A peer that does not show up within 20 s makes the call fail with
+ * B200MC_ERR_COMM instead of hanging.  Unconnected engines (world <= 1) simply run b200mc_simulate. */
+#define B200MC_COMM_HANDLE_BYTES 64
+int b200mc_comm_export(b200mc_engine_t* eng, void* handle_out);
+int b200mc_comm_connect(b200mc_engine_t* eng, int rank, int world, const void* handles);
+int b200mc_comm_connect_local(b200mc_engine_t* const* engines, int n);
+int b200mc_comm_disconnect(b200mc_engine_t* eng);
+int b200mc_comm_world(const b200mc_engine_t* eng);
+int b200mc_simulate_allreduce(b200mc_engine_t* eng, const b200mc_spec_t* spec, const b200mc_params_t* params_host,
+                              uint32_t n_opt, uint32_t n_scen, uint64_t seed, uint32_t stream_base,
+                              uint64_t path_begin, uint64_t n_paths, b200mc_moments_t* out_host);
+int b200mc_simulate_allreduce_device(b200mc_engine_t* eng, const b200mc_spec_t* spec, const b200mc_params_t* params_dev,
+                                     uint32_t n_opt, uint32_t n_scen, uint64_t seed, uint32_t stream_base,
+                                     uint64_t path_begin, uint64_t n_paths, b200mc_moments_t* out_dev,
+                                     void* cuda_stream);
 
 /* European payoff + the sums np.cov(discounted, terminal) needs, same launch shape as b200mc_simulate
  * (spec->kind must be B200MC_EUROPEAN).  Replaces price_with_control_variate's simulation and

@@ -18,7 +18,7 @@ from .exceptions import AccelerationError, MonteCarloError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200mc.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_SCENARIOS = 16
 
 EUROPEAN, ASIAN_ARITH, ASIAN_GEOM, BARRIER, LOOKBACK, CLIQUET, AUTOCALLABLE = range(7)
@@ -74,6 +74,15 @@ SIGNATURES = {
                                   C.c_uint64, C.c_uint64, _P]),
     "b200mc_simulate_device": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
                                          C.c_uint64, C.c_uint64, _P, _P]),
+    "b200mc_simulate_allreduce": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
+                                            C.c_uint64, C.c_uint64, _P]),
+    "b200mc_simulate_allreduce_device": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
+                                                   C.c_uint64, C.c_uint64, _P, _P]),
+    "b200mc_comm_export": (C.c_int, [_P, _P]),
+    "b200mc_comm_connect": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "b200mc_comm_connect_local": (C.c_int, [C.POINTER(_P), C.c_int]),
+    "b200mc_comm_disconnect": (C.c_int, [_P]),
+    "b200mc_comm_world": (C.c_int, [_P]),
     "b200mc_simulate_control_variate": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
                                                   C.c_uint64, C.c_uint64, _P]),
     "b200mc_simulate_structured": (C.c_int, [_P, C.POINTER(Spec), C.POINTER(Product), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
@@ -179,7 +188,7 @@ class Engine:
             msg = self._lib.b200mc_last_error(self._h).decode()
             if rc == -1:
                 raise MonteCarloError(f"{what}: {msg}")
-            raise AccelerationError(f"{what}: {msg}", backend="cuda")
+            raise AccelerationError(f"{what}: {msg}", backend="nvlink" if rc == -3 else "cuda")
 
     # -- queries ----------------------------------------------------------------------------
     def info(self) -> dict:
@@ -217,20 +226,24 @@ class Engine:
 
     # -- hot path ---------------------------------------------------------------------------
     def simulate(self, spec: Spec, params: np.ndarray, seed: int, n_paths: int, *, stream_base: int = 0,
-                 path_begin: int = 0, control_variate: bool = False) -> np.ndarray:
-        """params: PARAMS_DTYPE array [n_opt, n_scen] -> MOMENTS_DTYPE (or CV_MOMENTS_DTYPE) array [n_opt, n_scen]."""
+                 path_begin: int = 0, control_variate: bool = False, allreduce: bool = False) -> np.ndarray:
+        """params: PARAMS_DTYPE array [n_opt, n_scen] -> MOMENTS_DTYPE (or CV_MOMENTS_DTYPE) array [n_opt, n_scen].
+        ``allreduce``: the moments of ALL connected ranks' path ranges (fused into the kernel's tail; collective call)."""
         params = np.ascontiguousarray(params, dtype=PARAMS_DTYPE)
         if params.ndim != 2:
             raise MonteCarloError("params must have shape [n_opt, n_scen]")
         out = np.empty(params.shape, dtype=CV_MOMENTS_DTYPE if control_variate else MOMENTS_DTYPE)
-        fn = self._lib.b200mc_simulate_control_variate if control_variate else self._lib.b200mc_simulate
+        if allreduce and control_variate:
+            raise MonteCarloError("the fused all-reduce carries (sum, sum_sq, n) records")
+        fn = self._lib.b200mc_simulate_control_variate if control_variate else \
+            self._lib.b200mc_simulate_allreduce if allreduce else self._lib.b200mc_simulate
         rc = fn(self._h, C.byref(spec), params.ctypes.data, params.shape[0], params.shape[1],
                 int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF, int(path_begin), int(n_paths), out.ctypes.data)
         self._check(rc, "b200mc_simulate_control_variate" if control_variate else "b200mc_simulate")
         return out
 
     def simulate_scalars(self, spec: Spec, scenarios, seed: int, n_paths: int, *, barrier: float = 0.0, stream_base: int = 0,
-                         path_begin: int = 0):
+                         path_begin: int = 0, allreduce: bool = False):
         """Latency path for ONE option: ``scenarios`` = up to 16 (S, K, T, r, sigma, q) tuples on common random numbers ->
         list of (sum, sum_sq, n) tuples.  No NumPy on the way: the parameter block is filled into a preallocated ctypes
         buffer and the C side launches one kernel whose arguments carry the coefficients and whose finishing CTA writes
@@ -247,20 +260,39 @@ class Engine:
         b = float(barrier)
         for k, sc in enumerate(scenarios):
             buf_in[8 * k:8 * k + 8] = (sc[0], sc[1], sc[2], sc[3], sc[4], sc[5], b, 0.0)
-        rc = self._lib.b200mc_simulate(self._h, C.byref(spec), buf_in, 1, n, int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF,
-                                       int(path_begin), int(n_paths), buf_out)
+        fn = self._lib.b200mc_simulate_allreduce if allreduce else self._lib.b200mc_simulate
+        rc = fn(self._h, C.byref(spec), buf_in, 1, n, int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF,
+                int(path_begin), int(n_paths), buf_out)
         if rc != 0:
-            self._check(rc, "b200mc_simulate")
+            self._check(rc, "b200mc_simulate_allreduce" if allreduce else "b200mc_simulate")
         out = buf_out[0:3 * n]
         return [(out[3 * k], out[3 * k + 1], out[3 * k + 2]) for k in range(n)]
 
     def simulate_device(self, spec: Spec, params_ptr: int, n_opt: int, n_scen: int, seed: int, n_paths: int, out_ptr: int,
-                        cuda_stream: int, *, stream_base: int = 0, path_begin: int = 0):
+                        cuda_stream: int, *, stream_base: int = 0, path_begin: int = 0, allreduce: bool = False):
         """Asynchronous variant on raw device pointers (params / moments already in HBM)."""
-        rc = self._lib.b200mc_simulate_device(self._h, C.byref(spec), params_ptr, n_opt, n_scen,
-                                              int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF,
-                                              int(path_begin), int(n_paths), out_ptr, cuda_stream)
-        self._check(rc, "b200mc_simulate_device")
+        fn = self._lib.b200mc_simulate_allreduce_device if allreduce else self._lib.b200mc_simulate_device
+        rc = fn(self._h, C.byref(spec), params_ptr, n_opt, n_scen, int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_base) & 0xFFFFFFFF,
+                int(path_begin), int(n_paths), out_ptr, cuda_stream)
+        self._check(rc, "b200mc_simulate_allreduce_device" if allreduce else "b200mc_simulate_device")
+
+    # -- communicator of the fused all-reduce ---------------------------------------------------
+    def comm_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this engine's exchange block (step 1 of connecting ranks)."""
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.b200mc_comm_export(self._h, buf), "b200mc_comm_export")
+        return buf.raw
+
+    def comm_connect(self, rank: int, world: int, handles: bytes):
+        if len(handles) != 64 * world:
+            raise MonteCarloError("handles must hold 64 bytes per rank")
+        self._check(self._lib.b200mc_comm_connect(self._h, int(rank), int(world), handles), "b200mc_comm_connect")
+
+    def comm_disconnect(self):
+        self._check(self._lib.b200mc_comm_disconnect(self._h), "b200mc_comm_disconnect")
+
+    def comm_world(self) -> int:
+        return int(self._lib.b200mc_comm_world(self._h))
 
     # -- structured products (cliquet / autocallable) ------------------------------------------
     def simulate_structured(self, spec: Spec, product: Product, params: np.ndarray, seed: int, n_paths: int, *, stream_base: int = 0,
@@ -449,6 +481,15 @@ class Engine:
         out = np.empty((ck.shape[0], 4), dtype=np.uint32)
         self._check(self._lib.b200mc_philox_raw(self._h, ck.ctypes.data, ck.shape[0], out.ctypes.data), "b200mc_philox_raw")
         return out
+
+
+def connect_local(engines) -> None:
+    """Connect engines of THIS process (one per device) for the fused all-reduce: rank = position in the list."""
+    arr = (_P * len(engines))(*[e._h for e in engines])
+    rc = load_library().b200mc_comm_connect_local(arr, len(engines))
+    if rc != 0:
+        msgs = "; ".join(e._lib.b200mc_last_error(e._h).decode() for e in engines)
+        raise AccelerationError(f"b200mc_comm_connect_local failed ({rc}): {msgs}", backend="nvlink")
 
 
 _engines = {}

@@ -54,6 +54,15 @@ struct b200mc_engine {
   cudaStream_t last_stream = nullptr;
   bool last_valid = false, last_own = true;
   cudaEvent_t order_ev = nullptr;
+  // fused all-reduce over peer memory (XchgArgs in mc_kernels.cuh); world <= 1: not connected
+  struct Comm {
+    int world = 0, rank = 0;
+    char* block = nullptr;            // this rank's exchange block (cudaMalloc; exported by IPC handle)
+    char* peer[kMaxRanks] = {};       // peer[rank] == block
+    bool ipc_opened[kMaxRanks] = {};  // peers mapped with cudaIpcOpenMemHandle (to be closed)
+    unsigned long long epoch = 0;
+    uint32_t* launch_ticket = nullptr;
+  } comm;
   int plan_split_shift = -1;  // b200mc_set_plan: -1 / 0 = automatic
   uint32_t plan_ppt = 0;
   uint32_t last_plan[3] = {0, 0, 0};  // tiles, paths per thread, split shift of the most recent fused launch
@@ -131,6 +140,8 @@ uint32_t pad_scenarios(uint32_t n) {
 
 constexpr size_t kMappedRecordBytes = B200MC_MAX_SCENARIOS * sizeof(b200mc_cv_moments_t);  // the largest single-option result
 constexpr size_t kMappedBytes = 4096;
+constexpr size_t kMappedTimeoutOffset = kMappedRecordBytes + 64;  // the exchange's timed_out word (after the sequence word)
+constexpr size_t kXchgSlotBytes = 8u << 20;                       // per epoch parity: header + up to ~174k moment records
 
 // Ticket counters start at zero and every launch leaves them at zero (finish_tile).
 // Scratch of the in-kernel fold (finish_tile): tile partials + group totals, and the ticket words.
@@ -297,17 +308,26 @@ cudaError_t launch_structured(const StructuredArgs& g, uint32_t ns, dim3 grid, c
 // the finishing CTA writes the records into the mapped pinned block, then publishes `seq` for the polling host.
 int enqueue_simulation(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc_params_t* params_dev, const b200mc_params_t* inline_params,
                        uint32_t n_opt, uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
-                       void* out_dev, cudaStream_t stream, bool time_it, bool cv = false) {
+                       void* out_dev, cudaStream_t stream, bool time_it, bool cv = false, bool allreduce = false) {
   if (int rc = check_spec(e, spec)) return rc;
   if ((!params_dev && !inline_params) || !out_dev) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
-  if (n_opt == 0 || n_paths == 0) return fail(e, B200MC_ERR_INVALID, "n_opt and n_paths must be >= 1");
+  const bool exchange = allreduce && e->comm.world > 1;
+  // a rank whose share of the paths is empty still takes part in the exchange (it contributes zero records)
+  if (n_opt == 0 || (n_paths == 0 && !exchange)) return fail(e, B200MC_ERR_INVALID, "n_opt and n_paths must be >= 1");
   if (n_scen == 0 || n_scen > B200MC_MAX_SCENARIOS)
     return fail(e, B200MC_ERR_INVALID, "n_scen must be in [1, %d]", B200MC_MAX_SCENARIOS);
   if (inline_params && n_opt != 1) return fail(e, B200MC_ERR_INVALID, "inline parameters carry one option");
 
   if (cv && spec->kind != B200MC_EUROPEAN) return fail(e, B200MC_ERR_INVALID, "the control variate is defined for the European payoff only");
   const uint32_t ns = pad_scenarios(n_scen);
-  const TilePlan plan = plan_tiles(e, n_opt, n_paths, spec->n_steps, ns, spec->kind != B200MC_EUROPEAN, spec->kind == B200MC_EUROPEAN && !cv);
+  TilePlan plan = plan_tiles(e, n_opt, std::max<uint64_t>(n_paths, 1), spec->n_steps, ns, spec->kind != B200MC_EUROPEAN, spec->kind == B200MC_EUROPEAN && !cv);
+  if (exchange) {
+    const size_t record_bytes = (size_t)n_opt * n_scen * (cv ? sizeof(b200mc_cv_moments_t) : sizeof(b200mc_moments_t));
+    if (record_bytes > kXchgSlotBytes - kXchgHeaderBytes)
+      return fail(e, B200MC_ERR_COMM, "%zu bytes of moment records exceed the exchange slot (%zu)", record_bytes, kXchgSlotBytes - kXchgHeaderBytes);
+    if (*(volatile unsigned int*)(e->mapped_host + kMappedTimeoutOffset))
+      return fail(e, B200MC_ERR_COMM, "an earlier fused all-reduce timed out waiting for a peer rank; reconnect the communicator");
+  }
   const uint64_t ctas = (uint64_t)plan.tiles * n_opt;
   if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
   e->last_plan[0] = plan.tiles, e->last_plan[1] = plan.ppt, e->last_plan[2] = plan.split_shift;
@@ -330,9 +350,19 @@ int enqueue_simulation(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc
   a.fold.tickets = (uint32_t*)e->tickets.ptr;
   a.fold.out = out_dev;
   a.fold.samples = (double)n_paths * (spec->antithetic ? 2.0 : 1.0);
+  a.fold.n_opt = n_opt;
   if (inline_params) {
     a.fold.done = (unsigned long long*)(e->mapped_dev + kMappedRecordBytes);
     a.fold.seq = ++e->seq;
+  }
+  if (exchange) {
+    a.fold.x.world = (uint32_t)e->comm.world;
+    a.fold.x.rank = (uint32_t)e->comm.rank;
+    a.fold.x.epoch = ++e->comm.epoch;
+    for (int r = 0; r < e->comm.world; ++r) a.fold.x.peer[r] = e->comm.peer[r];
+    a.fold.x.slot_bytes = kXchgSlotBytes;
+    a.fold.x.launch_ticket = e->comm.launch_ticket;
+    a.fold.x.timed_out = (unsigned int*)(e->mapped_dev + kMappedTimeoutOffset);
   }
   a.path_begin = path_begin;
   a.n_paths = n_paths;
@@ -501,6 +531,10 @@ void b200mc_destroy(b200mc_engine_t* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (DeviceBuffer* b : {&e->partials, &e->tickets, &e->params_dev, &e->moments_dev, &e->scratch_a, &e->scratch_b})
     if (b->ptr) cudaFree(b->ptr);
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (e->comm.ipc_opened[r] && e->comm.peer[r]) cudaIpcCloseMemHandle(e->comm.peer[r]);
+  if (e->comm.block) cudaFree(e->comm.block);
+  if (e->comm.launch_ticket) cudaFree(e->comm.launch_ticket);
   if (e->pinned) cudaFreeHost(e->pinned);
   if (e->mapped_host) cudaFreeHost(e->mapped_host);
   if (e->order_ev) cudaEventDestroy(e->order_ev);
@@ -534,20 +568,32 @@ int b200mc_device_info(b200mc_engine_t* e, b200mc_info_t* out) {
   return 0;
 }
 
-int b200mc_simulate_device(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_dev, uint32_t n_opt,
-                           uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
-                           b200mc_moments_t* out_dev, void* cuda_stream) {
+static int simulate_device_impl(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_dev, uint32_t n_opt,
+                                uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
+                                b200mc_moments_t* out_dev, void* cuda_stream, bool allreduce) {
   if (!e) return B200MC_ERR_INVALID;
   std::lock_guard<std::mutex> g(e->mutex);
   CU_TRY(e, cudaSetDevice(e->device));
   if (!params_dev) return fail(e, B200MC_ERR_INVALID, "params pointer is null");
   return enqueue_simulation(e, spec, params_dev, nullptr, n_opt, n_scen, seed, stream_base, path_begin, n_paths, out_dev,
-                            (cudaStream_t)cuda_stream, e->timing);
+                            (cudaStream_t)cuda_stream, e->timing, false, allreduce);
+}
+
+int b200mc_simulate_device(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_dev, uint32_t n_opt,
+                           uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
+                           b200mc_moments_t* out_dev, void* cuda_stream) {
+  return simulate_device_impl(e, spec, params_dev, n_opt, n_scen, seed, stream_base, path_begin, n_paths, out_dev, cuda_stream, false);
+}
+
+int b200mc_simulate_allreduce_device(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_dev, uint32_t n_opt,
+                                     uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
+                                     b200mc_moments_t* out_dev, void* cuda_stream) {
+  return simulate_device_impl(e, spec, params_dev, n_opt, n_scen, seed, stream_base, path_begin, n_paths, out_dev, cuda_stream, true);
 }
 
 static int simulate_host(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_host, uint32_t n_opt,
                          uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
-                         void* out_host, bool cv) {
+                         void* out_host, bool cv, bool allreduce = false) {
   if (!e) return B200MC_ERR_INVALID;
   std::lock_guard<std::mutex> g(e->mutex);
   if (!params_host || !out_host) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
@@ -557,9 +603,11 @@ static int simulate_host(b200mc_engine_t* e, const b200mc_spec_t* spec, const b2
   const size_t in_bytes = n * sizeof(b200mc_params_t), out_bytes = n * (cv ? sizeof(b200mc_cv_moments_t) : sizeof(b200mc_moments_t));
   if (n_opt == 1) {  // one launch, nothing else: parameters in the kernel arguments, records through mapped memory
     if (int rc = enqueue_simulation(e, spec, nullptr, params_host, 1, n_scen, seed, stream_base, path_begin, n_paths, e->mapped_dev,
-                                    e->stream, e->timing, cv))
+                                    e->stream, e->timing, cv, allreduce))
       return rc;
     if (int rc = wait_mapped(e, e->seq)) return rc;
+    if (allreduce && *(volatile unsigned int*)(e->mapped_host + kMappedTimeoutOffset))
+      return fail(e, B200MC_ERR_COMM, "fused all-reduce timed out waiting for a peer rank");
     memcpy(out_host, e->mapped_host, out_bytes);
     return 0;
   }
@@ -571,10 +619,12 @@ static int simulate_host(b200mc_engine_t* e, const b200mc_spec_t* spec, const b2
   memcpy(pin_in, params_host, in_bytes);
   CU_TRY(e, cudaMemcpyAsync(e->params_dev.ptr, pin_in, in_bytes, cudaMemcpyHostToDevice, e->stream));
   if (int rc = enqueue_simulation(e, spec, (const b200mc_params_t*)e->params_dev.ptr, nullptr, n_opt, n_scen, seed, stream_base,
-                                  path_begin, n_paths, e->moments_dev.ptr, e->stream, e->timing, cv))
+                                  path_begin, n_paths, e->moments_dev.ptr, e->stream, e->timing, cv, allreduce))
     return rc;
   CU_TRY(e, cudaMemcpyAsync(pin_out, e->moments_dev.ptr, out_bytes, cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
+  if (allreduce && *(volatile unsigned int*)(e->mapped_host + kMappedTimeoutOffset))
+    return fail(e, B200MC_ERR_COMM, "fused all-reduce timed out waiting for a peer rank");
   memcpy(out_host, pin_out, out_bytes);
   return 0;
 }
@@ -584,6 +634,116 @@ int b200mc_simulate(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_
                     b200mc_moments_t* out_host) {
   return simulate_host(e, spec, params_host, n_opt, n_scen, seed, stream_base, path_begin, n_paths, out_host, false);
 }
+
+int b200mc_simulate_allreduce(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_host, uint32_t n_opt,
+                              uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin, uint64_t n_paths,
+                              b200mc_moments_t* out_host) {
+  return simulate_host(e, spec, params_host, n_opt, n_scen, seed, stream_base, path_begin, n_paths, out_host, false, true);
+}
+
+// ---- communicator of the fused all-reduce -------------------------------------------------------------------------
+static int comm_alloc(b200mc_engine_t* e) {
+  CU_TRY(e, cudaSetDevice(e->device));
+  if (!e->comm.block) {
+    CU_TRY(e, cudaMalloc((void**)&e->comm.block, 2 * kXchgSlotBytes));
+    CU_TRY(e, cudaMalloc((void**)&e->comm.launch_ticket, 256));
+    CU_TRY(e, cudaMemset(e->comm.launch_ticket, 0, 256));
+  }
+  return 0;
+}
+
+static int comm_reset(b200mc_engine_t* e) {  // forget the peers; flags back to zero, epochs restart at 1
+  CU_TRY(e, cudaSetDevice(e->device));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  for (int r = 0; r < kMaxRanks; ++r) {
+    if (e->comm.ipc_opened[r] && e->comm.peer[r]) cudaIpcCloseMemHandle(e->comm.peer[r]);
+    e->comm.peer[r] = nullptr, e->comm.ipc_opened[r] = false;
+  }
+  e->comm.world = 0, e->comm.rank = 0, e->comm.epoch = 0;
+  if (e->comm.block) {
+    CU_TRY(e, cudaMemset(e->comm.block, 0, kXchgHeaderBytes));
+    CU_TRY(e, cudaMemset(e->comm.block + kXchgSlotBytes, 0, kXchgHeaderBytes));
+    CU_TRY(e, cudaMemset(e->comm.launch_ticket, 0, 256));
+  }
+  *(volatile unsigned int*)(e->mapped_host + kMappedTimeoutOffset) = 0;
+  return 0;
+}
+
+int b200mc_comm_export(b200mc_engine_t* e, void* handle_out) {
+  if (!e || !handle_out) return fail(e, B200MC_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(e->mutex);
+  static_assert(sizeof(cudaIpcMemHandle_t) == B200MC_COMM_HANDLE_BYTES, "handle size");
+  if (int rc = comm_alloc(e)) return rc;
+  if (int rc = comm_reset(e)) return rc;
+  cudaIpcMemHandle_t h;
+  const cudaError_t err = cudaIpcGetMemHandle(&h, e->comm.block);
+  if (err != cudaSuccess) return fail(e, B200MC_ERR_COMM, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(err));
+  memcpy(handle_out, &h, sizeof h);
+  return 0;
+}
+
+int b200mc_comm_connect(b200mc_engine_t* e, int rank, int world, const void* handles) {
+  if (!e || !handles) return fail(e, B200MC_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(e->mutex);
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world)
+    return fail(e, B200MC_ERR_INVALID, "rank %d / world %d out of range (at most %d ranks: one NVSwitch domain)", rank, world, kMaxRanks);
+  if (!e->comm.block) return fail(e, B200MC_ERR_INVALID, "call b200mc_comm_export first");
+  CU_TRY(e, cudaSetDevice(e->device));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      e->comm.peer[r] = e->comm.block;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * sizeof h, sizeof h);
+    void* p = nullptr;
+    const cudaError_t err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) {
+      comm_reset(e);
+      return fail(e, B200MC_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(err));
+    }
+    e->comm.peer[r] = (char*)p, e->comm.ipc_opened[r] = true;
+  }
+  e->comm.world = world, e->comm.rank = rank, e->comm.epoch = 0;
+  return 0;
+}
+
+int b200mc_comm_connect_local(b200mc_engine_t* const* engines, int n) {
+  if (!engines || n < 1 || n > kMaxRanks) return B200MC_ERR_INVALID;
+  for (int i = 0; i < n; ++i) {
+    if (!engines[i]) return B200MC_ERR_INVALID;
+    std::lock_guard<std::mutex> g(engines[i]->mutex);
+    if (int rc = comm_alloc(engines[i])) return rc;
+    if (int rc = comm_reset(engines[i])) return rc;
+  }
+  for (int i = 0; i < n; ++i) {
+    b200mc_engine_t* e = engines[i];
+    std::lock_guard<std::mutex> g(e->mutex);
+    CU_TRY(e, cudaSetDevice(e->device));
+    for (int j = 0; j < n; ++j) {
+      if (j != i && engines[j]->device != e->device) {
+        int can = 0;
+        CU_TRY(e, cudaDeviceCanAccessPeer(&can, e->device, engines[j]->device));
+        if (!can) return fail(e, B200MC_ERR_COMM, "device %d cannot access device %d", e->device, engines[j]->device);
+        const cudaError_t err = cudaDeviceEnablePeerAccess(engines[j]->device, 0);
+        if (err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled)
+          return fail(e, B200MC_ERR_COMM, "cudaDeviceEnablePeerAccess(%d) failed: %s", engines[j]->device, cudaGetErrorString(err));
+        cudaGetLastError();
+      }
+      e->comm.peer[j] = engines[j]->comm.block;
+    }
+    e->comm.world = n, e->comm.rank = i, e->comm.epoch = 0;
+  }
+  return 0;
+}
+
+int b200mc_comm_disconnect(b200mc_engine_t* e) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  return comm_reset(e);
+}
+
+int b200mc_comm_world(const b200mc_engine_t* e) { return e ? e->comm.world : 0; }
 
 int b200mc_simulate_control_variate(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_host,
                                     uint32_t n_opt, uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin,

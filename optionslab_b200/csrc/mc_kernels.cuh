@@ -39,6 +39,26 @@ constexpr int kWarps = kBlock / 32;
 constexpr int kMaxPathsPerThread = 32;  // <= 64 samples per thread with mirrors: the paid-counts fit 8-bit lanes
 constexpr int kMaxSplit = 8;            // lanes that may share one European path (see european_kernel)
 
+// Fused all-reduce of a launch's moment records across the GPUs of one NVSwitch domain (world == 0: off).  Every rank
+// owns an exchange block in its HBM that its peers map (CUDA IPC between processes, peer access inside one):
+//   [2 slots] x { uint64 epoch flag | pad to 128 B | records[n_opt * n_scen] }
+// The CTA that finishes a rank's LAST option publishes the rank's records (slot = epoch & 1) with a system-scope release,
+// waits for every peer's flag of the same epoch, adds the peers' records over NVLink in rank order - the same order on
+// every rank, so all ranks end with identical bits - and writes the totals to `out`.  No second kernel, no host hop:
+// the exchange is the tail of the simulation kernel.  Two slots suffice: a rank can start epoch e+1 only after every peer
+// has published e, i.e. after every peer finished reading slot (e-1) & 1.
+constexpr int kMaxRanks = 8;
+constexpr size_t kXchgHeaderBytes = 128;
+struct XchgArgs {
+  uint32_t world, rank;
+  unsigned long long epoch;
+  char* peer[kMaxRanks];      // exchange blocks by rank; peer[rank] is this rank's own
+  size_t slot_bytes;
+  uint32_t* launch_ticket;    // options of this launch whose records are complete; zero between launches
+  unsigned int* timed_out;    // mapped host word, set to 1 if a peer's flag did not arrive within kXchgTimeoutNs
+};
+constexpr unsigned long long kXchgTimeoutNs = 20ull * 1000 * 1000 * 1000;
+
 // Where a launch's results go.
 struct FoldArgs {
   double* partials;          // [n_opt * tiles][values per tile]: per-CTA FP64 partial sums (stay in L2)
@@ -47,6 +67,8 @@ struct FoldArgs {
   unsigned long long* done;  // non-null: mapped host word that receives `seq` once `out` is complete (single-option launches)
   unsigned long long seq;
   double samples;            // the n of every record
+  XchgArgs x;                // x.world > 1: `out` receives the sum over all ranks
+  uint32_t n_opt;            // options of this launch (the exchange starts when all of them are folded)
 };
 
 struct SimArgs {
@@ -160,17 +182,46 @@ __host__ __device__ inline uint32_t fold_groups(uint32_t tiles) { return (tiles 
 __host__ __device__ inline size_t fold_scratch_doubles(uint32_t tiles, uint32_t nv) { return ((size_t)tiles + fold_groups(tiles)) * nv; }
 __host__ __device__ inline size_t fold_ticket_words(uint32_t tiles) { return (size_t)fold_groups(tiles) + 1; }
 
-// Sum x[v] over the CTA in a fixed order: shuffle tree per warp, then the warps in index order.  Threads v < NV return
+// Sum x[v] over the CTA in a fixed order: a butterfly per warp, then the warps in index order.  Threads v < NV return
 // the total of value v (others: garbage).  `red` is CTA-shared scratch.
+// Few values: one xor-butterfly per value (5 double shuffles each).  Many values (4-16 scenarios: 12..96 values): the
+// butterfly runs on ALL values at once by recursive halving - at offset 16 a lane keeps one half of the values and hands
+// the other half to its partner, at offset 8 a quarter, ... - so a warp spends ~P double shuffles for P values instead
+// of 5P (the 14-scenario Greeks launch was SHFL-bound in its reduction: 480 -> 124 SHFL per warp).  After the five
+// rounds lane L holds the warp totals of values L*P/32 .. L*P/32 + P/32 - 1.  Same association for every value.
 template <int NV>
 __device__ __forceinline__ double cta_sum(const double (&x)[NV], double (*red)[NV]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if constexpr (NV <= 8) {
 #pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    double y = x[v];
+    for (int v = 0; v < NV; ++v) {
+      double y = x[v];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) y += __shfl_xor_sync(0xffffffffu, y, off);
-    if (lane == 0) red[warp][v] = y;
+      for (int off = 16; off > 0; off >>= 1) y += __shfl_xor_sync(0xffffffffu, y, off);
+      if (lane == 0) red[warp][v] = y;
+    }
+  } else {
+    constexpr int P = NV <= 32 ? 32 : NV <= 64 ? 64 : 128;
+    double y[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) y[i] = i < NV ? x[i] : 0.0;
+#pragma unroll
+    for (int round = 0; round < 5; ++round) {
+      const int off = 16 >> round;
+      const int h = P >> (round + 1);
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < h; ++i) {
+        const double keep = upper ? y[i + h] : y[i];
+        const double send = upper ? y[i] : y[i + h];
+        y[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < P / 32; ++j) {
+      const int v = lane * (P / 32) + j;
+      if (v < NV) red[warp][v] = y[j];
+    }
   }
   __syncthreads();
   double t = 0.0;
@@ -184,8 +235,7 @@ __device__ __forceinline__ double cta_sum(const double (&x)[NV], double (*red)[N
 // Fold `count` (<= 1024) rows of NV doubles starting at `rows` into dst[NV] (CTA-shared or global), fixed association.
 template <int NV, class Store>
 __device__ __forceinline__ void fold_rows(const double* rows, uint32_t count, double (*red)[NV], Store&& store) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (NV <= 12) {
+  if constexpr (NV <= 8) {
     // few values per row: thread t takes rows t, t+256, t+512, t+768 - up to 4*NV independent loads - then a CTA sum
     double x[NV];
 #pragma unroll
@@ -202,18 +252,25 @@ __device__ __forceinline__ void fold_rows(const double* rows, uint32_t count, do
     const double t = cta_sum<NV>(x, red);
     if (threadIdx.x < NV) store(threadIdx.x, t);
   } else {
-    // many values per row (8-16 scenarios): one warp per value, lanes stride the rows with eight sums in flight
-    for (int v = warp; v < NV; v += kWarps) {
-      double x[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll 8
-      for (uint32_t j = 0; j < (uint32_t)kFoldGroup / 32; ++j) {
-        const uint32_t r = lane + 32u * j;
-        if (r < count) x[j & 7] += __ldcg(rows + (size_t)r * NV + v);
-      }
-      double y = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+    // many values per row (4-16 scenarios): eight values per pass, thread t again takes rows t, t+256, t+512, t+768
+    // (32 independent loads), then one CTA sum per pass
+    static_assert(NV % 4 == 0, "rows of 3*NS doubles with NS >= 4");
+    constexpr int kPass = NV % 8 == 0 ? 8 : 4;
+    for (int v0 = 0; v0 < NV; v0 += kPass) {
+      double part[4][kPass];
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) y += __shfl_xor_sync(0xffffffffu, y, off);
-      if (lane == 0) store(v, y);
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t r = threadIdx.x + (uint32_t)kBlock * i;
+#pragma unroll
+        for (int v = 0; v < kPass; ++v) part[i][v] = r < count ? __ldcg(rows + (size_t)r * NV + v0 + v) : 0.0;
+      }
+      double x[kPass];
+#pragma unroll
+      for (int v = 0; v < kPass; ++v) x[v] = (part[0][v] + part[1][v]) + (part[2][v] + part[3][v]);
+      __syncthreads();
+      double (*red8)[kPass] = reinterpret_cast<double (*)[kPass]>(&red[0][0]);  // NV >= kPass: the scratch is large enough
+      const double t = cta_sum<kPass>(x, red8);
+      if (threadIdx.x < kPass) store(v0 + threadIdx.x, t);
     }
   }
 }
@@ -279,6 +336,11 @@ __device__ __forceinline__ void finish_tile(const float (&acc)[NM * NS], const u
     }
   }
   __syncthreads();
+  constexpr int kRecDoubles = NM == 2 ? 3 : 6;
+  const bool exchange = f.x.world > 1;
+  // with the exchange on, this rank's records go to its exchange slot first
+  double* const records = exchange ? reinterpret_cast<double*>(f.x.peer[f.x.rank] + (f.x.epoch & 1ull) * f.x.slot_bytes + kXchgHeaderBytes)
+                                   : static_cast<double*>(f.out);
   if (threadIdx.x < n_scen) {
     const uint32_t k = threadIdx.x;
     const ScenScale sc = scale(k);
@@ -293,22 +355,59 @@ __device__ __forceinline__ void finish_tile(const float (&acc)[NM * NS], const u
       const double d = sgn * ((double)sc.kappa32 - sc.kappa);       // FP64-strike payoff = FP32-strike payoff + d on every paid sample
       sum_sq = p2 + 2.0 * d * sum32 + d * d * paid;
     }
-    if (NM == 2) {
-      b200mc_moments_t m;
-      m.sum = sum * S;
-      m.sum_sq = sum_sq * S * S;
-      m.n = f.samples;
-      static_cast<b200mc_moments_t*>(f.out)[(size_t)opt * n_scen + k] = m;
-    } else {
+    double* const rec = records + ((size_t)opt * n_scen + k) * kRecDoubles;
+    if (NM == 2) {  // b200mc_moments_t
+      rec[0] = sum * S;
+      rec[1] = sum_sq * S * S;
+      rec[2] = f.samples;
+    } else {        // b200mc_cv_moments_t
       const double e1 = tot[NM * k + 2], e2 = tot[NM * k + 3], a2 = tot[NM * k + 4];  // sum S_T, sum S_T^2, sum_paid(x^2)
-      b200mc_cv_moments_t m;
-      m.sum_payoff = sum * S;
-      m.sum_payoff_sq = sum_sq * S * S;
-      m.sum_terminal = e1 * S;
-      m.sum_terminal_sq = e2 * S * S;
-      m.sum_payoff_terminal = sgn * (a2 - sc.kappa * a1) * S * S;  // payoff * S_T = +-(x - k) * x over the paid samples
-      m.n = f.samples;
-      static_cast<b200mc_cv_moments_t*>(f.out)[(size_t)opt * n_scen + k] = m;
+      rec[0] = sum * S;
+      rec[1] = sum_sq * S * S;
+      rec[2] = e1 * S;
+      rec[3] = e2 * S * S;
+      rec[4] = sgn * (a2 - sc.kappa * a1) * S * S;  // payoff * S_T = +-(x - k) * x over the paid samples
+      rec[5] = f.samples;
+    }
+    if (exchange) __threadfence();
+    else if (f.done) __threadfence_system();
+  }
+  if (exchange) {
+    // ---- the launch's last option triggers the all-reduce over peer memory ------------------------------------------
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      is_last = atomicAdd(f.x.launch_ticket, 1u) == f.n_opt - 1 ? 1u : 0u;
+      if (is_last) *f.x.launch_ticket = 0u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    const size_t slot_off = (f.x.epoch & 1ull) * f.x.slot_bytes;
+    __threadfence_system();  // every option's records (observed through the ticket) before the flag, at system scope
+    __syncthreads();
+    if (threadIdx.x == 0)
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.x.peer[f.x.rank] + slot_off), "l"(f.x.epoch) : "memory");
+    if (threadIdx.x < f.x.world && threadIdx.x != f.x.rank) {
+      const char* flag = f.x.peer[threadIdx.x] + slot_off;
+      unsigned long long seen, t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      } while (seen != f.x.epoch && t1 - t0 < kXchgTimeoutNs);
+      if (seen != f.x.epoch) *reinterpret_cast<volatile unsigned int*>(f.x.timed_out) = 1u;
+    }
+    __syncthreads();
+    const size_t n_doubles = (size_t)f.n_opt * n_scen * kRecDoubles;
+    double* const out = static_cast<double*>(f.out);
+    for (size_t i = threadIdx.x; i < n_doubles; i += kBlock) {
+      double total = 0.0;
+      for (uint32_t r = 0; r < f.x.world; ++r) {  // rank order: identical bits on every rank
+        const double* src = reinterpret_cast<const double*>(f.x.peer[r] + slot_off + kXchgHeaderBytes) + i;
+        double v;
+        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(src) : "memory");
+        total += v;
+      }
+      out[i] = total;
     }
     if (f.done) __threadfence_system();
   }

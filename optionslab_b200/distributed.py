@@ -8,8 +8,14 @@ ctypes releases the GIL, the partial moments are summed on the host).  Both spli
 Every (option, path) is independent: rank g of G simulates global paths
 [g*N/G, (g+1)*N/G) of every option — the Philox counter carries the global path index, so the
 draws are disjoint by construction and independent of G — and the only exchanged data are the
-FP64 (sum, sum^2, n) triples.  ``torch.distributed`` is plumbing only (NCCL over NVLink on the
-GPU box, gloo in the CPU tests); the simulation never touches torch.
+FP64 (sum, sum^2, n) triples.
+
+The exchange itself: on NVLink-connected GPUs (the NCCL backend under torchrun, or ``local_devices``) the fused GBM
+launches (European / Asian / barrier / lookback: ``b200mc_simulate_allreduce``) add up the ranks' records in the TAIL OF
+THE SIMULATION KERNEL over peer memory — the finishing CTA of every rank reads its peers' exchange blocks in rank order,
+so there is no collective launch and no host hop between the kernel and the result (include/b200mc.h, "multi-GPU").
+``torch.distributed`` then only carries the 64-byte IPC handles at ``init()`` time.  Everything else (the other model
+families, gloo in the CPU tests, ``B200MC_FUSED_ALLREDUCE=0``) sums the moment records with one ``all_reduce``.
 """
 
 from __future__ import annotations
@@ -20,7 +26,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-__all__ = ["ShardContext", "init", "shutdown", "current", "partition_paths", "allreduce_moments", "run_sharded", "local_devices"]
+__all__ = ["ShardContext", "init", "shutdown", "current", "partition_paths", "allreduce_moments", "run_sharded", "local_devices", "fused_exchange"]
 
 
 @dataclass
@@ -30,6 +36,7 @@ class ShardContext:
     backend: str
     device: Optional[int]  # CUDA device index for NCCL, None for gloo/CPU
     owns_group: bool = False
+    fused: bool = False    # the engines of all ranks are connected for the in-kernel all-reduce
 
 
 _ctx: Optional[ShardContext] = None
@@ -67,11 +74,50 @@ def init(backend: Optional[str] = None) -> ShardContext:
         dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
         owns = True
     _ctx = ShardContext(rank=rank, world_size=world, backend=backend, device=device, owns_group=owns)
+    if world > 1 and backend == "nccl" and os.environ.get("B200MC_FUSED_ALLREDUCE", "1") != "0":
+        _connect_fused(_ctx)
     return _ctx
+
+
+def _connect_fused(ctx: ShardContext) -> None:
+    """Exchange the engines' IPC handles and map every peer's exchange block (include/b200mc.h).  Ranks that cannot
+    (more than 8 ranks, no peer access) all fall back to the all_reduce route together."""
+    import torch.distributed as dist
+
+    from . import _ffi
+    from .exceptions import MonteCarloError
+
+    eng = _ffi.get_engine(ctx.device)
+    ok = True
+    try:
+        mine = eng.comm_export() if ctx.world_size <= 8 else b""
+    except MonteCarloError:
+        mine = b""
+    handles = [None] * ctx.world_size
+    dist.all_gather_object(handles, mine)
+    if all(len(h) == 64 for h in handles):
+        try:
+            eng.comm_connect(ctx.rank, ctx.world_size, b"".join(handles))
+        except MonteCarloError:
+            ok = False
+    else:
+        ok = False
+    flags = [None] * ctx.world_size
+    dist.all_gather_object(flags, ok)  # also the barrier between connecting and the first exchange
+    ctx.fused = all(flags)
+    if not ctx.fused and ok:
+        eng.comm_disconnect()
 
 
 def shutdown():
     global _ctx
+    if _ctx is not None and _ctx.fused:
+        from . import _ffi
+
+        try:
+            _ffi.get_engine(_ctx.device).comm_disconnect()
+        except Exception:
+            pass
     if _ctx is not None and _ctx.owns_group:
         import torch.distributed as dist
 
@@ -103,6 +149,25 @@ def allreduce_moments(moments: np.ndarray, ctx: Optional[ShardContext] = None) -
 
 # ---- one process, several devices --------------------------------------------------------------------------------
 _local: Optional[Tuple[int, ...]] = None
+_local_fused = False
+
+
+def _connect_local(devices) -> None:
+    global _local_fused
+    _local_fused = False
+    if len(devices) < 2 or len(set(devices)) != len(devices) or os.environ.get("B200MC_FUSED_ALLREDUCE", "1") == "0":
+        return
+    from . import _ffi
+    from .exceptions import MonteCarloError
+
+    try:
+        engines = [_ffi.get_engine(d) for d in devices]
+        if not all(isinstance(e, _ffi.Engine) for e in engines):
+            return  # stand-in engines (CPU tests of the host logic): host-side sum
+        _ffi.connect_local(engines)
+        _local_fused = True
+    except MonteCarloError:
+        _local_fused = False  # no peer access between these devices: host-side sum
 
 
 class local_devices:
@@ -118,12 +183,19 @@ class local_devices:
         global _local
         if _ctx is not None and _ctx.world_size > 1:
             raise RuntimeError("local_devices cannot be nested inside a multi-process shard context")
-        self._previous, _local = _local, self.devices
+        self._previous, self._previous_fused = _local, _local_fused
+        _local = self.devices
+        _connect_local(self.devices)
         return self
 
     def __exit__(self, *exc):
-        global _local
-        _local = self._previous
+        global _local, _local_fused
+        if _local_fused:
+            from . import _ffi
+
+            for d in self.devices:
+                _ffi.get_engine(d).comm_disconnect()
+        _local, _local_fused = self._previous, self._previous_fused
         return False
 
 
@@ -139,22 +211,36 @@ def default_engine():
     return _ffi.get_engine(_local[0]) if _local else _ffi.get_engine()
 
 
-def run_sharded(fn, n_units: int, empty, partition=partition_paths) -> np.ndarray:
+def fused_exchange() -> bool:
+    """True when the active sharding (process group or local_devices) adds up moment records inside the kernel."""
+    if _local is not None and len(_local) > 1:
+        return _local_fused
+    return _ctx is not None and _ctx.world_size > 1 and _ctx.fused
+
+
+def run_sharded(fn, n_units: int, empty, partition=partition_paths, fused_fn=None) -> np.ndarray:
     """Run ``fn(engine, begin, count) -> moments`` over this process's share of ``n_units`` global paths (or Sobol points)
     and return the moments of ALL units: plain call when unsharded, threads + host sum under ``local_devices``, partition +
-    all-reduce under a process group.  ``empty()`` builds the zero moments of a shard that received no unit."""
+    all-reduce under a process group.  ``empty()`` builds the zero moments of a shard that received no unit.
+    ``fused_fn(engine, begin, count)`` - when given and the engines are connected - runs the same shard with the
+    all-reduce fused into the kernel and returns the total directly (it is called on every rank, empty shards included)."""
     from . import _ffi
 
     ctx = _ctx
+    fused = fused_fn is not None and fused_exchange()
     if _local is not None and len(_local) > 1:
         from concurrent.futures import ThreadPoolExecutor
 
         def one(i):
             begin, count = partition(n_units, i, len(_local))
+            if fused:
+                return fused_fn(_ffi.get_engine(_local[i]), begin, count)
             return fn(_ffi.get_engine(_local[i]), begin, count) if count > 0 else empty()
 
         with ThreadPoolExecutor(max_workers=len(_local)) as pool:
             parts = list(pool.map(one, range(len(_local))))
+        if fused:
+            return parts[0]  # every device holds the identical total
         total = np.ascontiguousarray(parts[0]).copy()
         flat = total.view(np.float64)
         for part in parts[1:]:
@@ -164,5 +250,7 @@ def run_sharded(fn, n_units: int, empty, partition=partition_paths) -> np.ndarra
     if ctx is None or ctx.world_size == 1:
         return fn(eng, 0, n_units)
     begin, count = partition(n_units, ctx.rank, ctx.world_size)
+    if fused:
+        return fused_fn(eng, begin, count)
     local = fn(eng, begin, count) if count > 0 else empty()
     return allreduce_moments(local, ctx)

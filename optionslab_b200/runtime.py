@@ -32,10 +32,12 @@ def simulate(spec: _ffi.Spec, params: np.ndarray, seed: int, n_paths: int, *, st
     if n_paths < 1:
         raise MonteCarloError("n_paths must be >= 1")
     dtype = _ffi.CV_MOMENTS_DTYPE if control_variate else _ffi.MOMENTS_DTYPE
+    fused = None if control_variate else (
+        lambda eng, begin, count: eng.simulate(spec, params, seed, count, stream_base=stream_base, path_begin=begin, allreduce=True))
     return distributed.run_sharded(
         lambda eng, begin, count: eng.simulate(spec, params, seed, count, stream_base=stream_base, path_begin=begin,
                                                control_variate=control_variate),
-        n_paths, lambda: np.zeros(np.shape(params), dtype=dtype))
+        n_paths, lambda: np.zeros(np.shape(params), dtype=dtype), fused_fn=fused)
 
 
 def simulate_scalars(spec: _ffi.Spec, scenarios, seed: int, n_paths: int, *, barrier: float = 0.0, stream_base: int = 0):
@@ -47,6 +49,10 @@ def simulate_scalars(spec: _ffi.Spec, scenarios, seed: int, n_paths: int, *, bar
     ctx = distributed.current()
     if (ctx is None or ctx.world_size == 1) and distributed.local_device_count() <= 1:
         return distributed.default_engine().simulate_scalars(spec, scenarios, seed, n_paths, barrier=barrier, stream_base=stream_base)
+    if ctx is not None and ctx.world_size > 1 and ctx.fused:  # one process per GPU: still one launch per rank, nothing else
+        begin, count = distributed.partition_paths(n_paths, ctx.rank, ctx.world_size)
+        return distributed.default_engine().simulate_scalars(spec, scenarios, seed, count, barrier=barrier, stream_base=stream_base,
+                                                             path_begin=begin, allreduce=True)
     sc = np.asarray(scenarios, dtype=np.float64).reshape(-1, 6)
     params = _ffi.make_params(sc[:, 0], sc[:, 1], sc[:, 2], sc[:, 3], sc[:, 4], sc[:, 5], barrier)[None, :]
     m = simulate(spec, params, seed, n_paths, stream_base=stream_base)[0]

@@ -78,8 +78,56 @@ def test_two_ranks_reproduce_single_process_prices(tmp_path):
     assert a == b  # every rank holds the identical all-reduced result
 
 
+def _fused_pair(engines, spec, params, seed, n_paths, split_at):
+    """Both connected engines price their path range with the all-reduce fused into the kernel tail (threads: the two
+    launches wait for each other's records)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    ranges = [(0, split_at), (split_at, n_paths - split_at)]
+    with ThreadPoolExecutor(max_workers=2) as pool:
+        return list(pool.map(lambda i: engines[i].simulate(spec, params, seed, ranges[i][1], path_begin=ranges[i][0], allreduce=True), range(2)))
+
+
+def test_fused_allreduce_between_two_engines_of_one_device():
+    """The in-kernel exchange (b200mc_simulate_allreduce) with two engine handles on cuda:0: each rank's finishing CTA
+    publishes its records, waits for the peer's flag and adds the peer's records in rank order.  Both ranks end with
+    identical bits, equal to the sum of two plain launches over the same path ranges; empty shards, many options and the
+    latency path (one option, mapped result) included.  The same kernel code runs between GPUs over NVLink."""
+    from optionslab_b200 import _ffi
+
+    a, b = _ffi.Engine(0), _ffi.Engine(0)
+    plain = _ffi.get_engine(0)
+    try:
+        _ffi.connect_local([a, b])
+        assert a.comm_world() == b.comm_world() == 2
+        K = np.linspace(80.0, 120.0, 37)
+        cases = [(_ffi.make_spec(_ffi.EUROPEAN, 32, antithetic=True), _ffi.make_params(100.0, K, 1.0, 0.05, 0.2).reshape(37, 1), 50_001, 20_000),
+                 (_ffi.make_spec(_ffi.ASIAN_ARITH, 24), np.stack([_ffi.make_params(100.0 + d, 100.0, 1.0, 0.05, 0.2) for d in (1.0, 0.0, -1.0)]).reshape(1, 3), 70_003, 1),
+                 (_ffi.make_spec(_ffi.BARRIER, 40, barrier_in=False), _ffi.make_params(100.0, 100.0, 1.0, 0.05, 0.2, barrier=120.0).reshape(1, 1), 300_000, 299_999),
+                 (_ffi.make_spec(_ffi.EUROPEAN, 8, is_put=True, antithetic=True), _ffi.make_params(100.0, 105.0, 0.5, 0.03, 0.3).reshape(1, 1), 4_096, 0)]  # rank 0 empty
+        for rep in range(3):  # consecutive epochs alternate the exchange slot
+            for spec, params, n_paths, split_at in cases:
+                got = _fused_pair([a, b], spec, params, 11 + rep, n_paths, split_at)
+                assert got[0].tobytes() == got[1].tobytes()
+                want = plain.simulate(spec, params, 11 + rep, n_paths - split_at, path_begin=split_at).copy()
+                if split_at:
+                    first = plain.simulate(spec, params, 11 + rep, split_at)
+                    for f in ("sum", "sum_sq", "n"):
+                        want[f] = first[f] + want[f]
+                assert np.array_equal(got[0]["n"], want["n"])
+                np.testing.assert_allclose(got[0]["sum"], want["sum"], rtol=1e-12)
+                np.testing.assert_allclose(got[0]["sum_sq"], want["sum_sq"], rtol=1e-12)
+        # unconnected again: allreduce degrades to the plain launch
+        a.comm_disconnect(), b.comm_disconnect()
+        spec, params, n_paths, _ = cases[0]
+        assert a.simulate(spec, params, 5, n_paths, allreduce=True).tobytes() == plain.simulate(spec, params, 5, n_paths).tobytes()
+    finally:
+        a.close(), b.close()
+
+
 def test_local_devices_mode_on_two_gpus():
-    """One process driving two GPUs from threads (distributed.local_devices): same global paths, host-side sum."""
+    """One process driving two GPUs from threads (distributed.local_devices): same global paths; the GBM launches add
+    up their records in the kernel tail over peer memory, the other model families on the host."""
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -90,6 +138,7 @@ def test_local_devices_mode_on_two_gpus():
     distributed.shutdown()
     whole = _prices()
     with distributed.local_devices(2):
+        assert distributed.fused_exchange()
         split = _prices()
     assert split["euro"][2] == whole["euro"][2]
     assert split["euro"][0] == pytest.approx(whole["euro"][0], rel=1e-6)
