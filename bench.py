@@ -7,16 +7,20 @@ Workload (BASELINE.json configs[4], SURVEY.md §8d "C5"): a grid of 4096 Europea
 One "step" = one pass over the whole grid = 4096 x 1e6 x 252 = 1.032e12 GBM path-steps.
 Metric: GBM path-steps / second (independent normal streams x steps; antithetic mirrors and
 CRN scenarios are NOT counted), whole job over all N GPUs.  N > 1: paths are partitioned across
-ranks (strong scaling: total work fixed) and the (sum, sum^2, n) moments are combined with ONE
-NCCL all-reduce per step.
+ranks (strong scaling: total work fixed) and the (sum, sum^2, n) moments are added up in the tail
+of the simulation kernel over NVLink peer memory (b200mc_simulate_allreduce_device; NCCL all-reduce
+only if the engines could not be connected).
 
-The JSON line also carries: `e2e` (MonteCarloPricerUni.price_batch with host arrays in / prices out), `roofline` (XU and
-dispatch fractions of the peaks measured live by b200mc_measure_peaks, HBM figure, ncu DRAM traffic), `cpu_baseline`
-(the NumPy restatement of the reference on one core, bounded sample), `asian_grid` (the same grid as arithmetic-average
-Asian calls, 2 passes), `z_vs_black_scholes` (z-scores of the timed prices) and `clocks` (nvidia-smi during the run).
+The JSON line also carries: `e2e` (MonteCarloPricerUni.price_batch with host arrays in / prices out, same step count),
+`roofline` (XU and dispatch fractions of the peaks measured live by b200mc_measure_peaks next to the paper peak, HBM
+figure, DRAM traffic read from the committed ncu capture), `cpu_baseline` (the UNMODIFIED reference installed in
+oracle/_ref - its Numba batch backend on all host threads - on a bounded sample; the NumPy restatement if that install
+is absent), `configs` (BASELINE.json configs C1-C4, the Greeks launch and the Asian grid through the public API: kernel
+and API time, path-steps/s, XU fraction, price, standard error - at N > 1 these are strong-scaling numbers),
+`z_vs_black_scholes` (z-scores of the timed prices) and `clocks` (nvidia-smi during the run).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA engine
-  python bench.py --impl reference [...]                        # the reference's NumPy algorithm on host cores
+  python bench.py --impl reference [...]                        # the reference's own CPU implementation on host cores
 """
 
 from __future__ import annotations
@@ -143,46 +147,130 @@ def cpu_sample(option_indices, n_paths, processes):
     return time.perf_counter() - t0, np.array(prices)
 
 
+def _load_reference():
+    """The unmodified reference installed by oracle/build_ref.py, or None (then the NumPy restatement stands in)."""
+    try:
+        from oracle import build_ref
+
+        if not build_ref.available():
+            return None
+        import logging
+        import warnings
+
+        warnings.simplefilter("ignore")
+        ref = build_ref.load()
+        logging.getLogger("src").setLevel(logging.WARNING)
+        return ref
+    except Exception as exc:  # a broken install must not take the bench down: fall back to the port and say so
+        sys.stderr.write(f"bench.py: oracle/_ref unusable ({exc!r}); timing the NumPy restatement instead\n")
+        return None
+
+
+def reference_grid_sample(ref, option_indices, n_paths, warm=False):
+    """One pass of the REFERENCE over a slice of the C5 grid: MonteCarloPricerUni.price_batch on its Numba batch backend
+    (monte_carlo_unified.py:145-204, prange over options - the reference's own multi-core path for this workload).
+    -> (seconds, prices)."""
+    g = grid_params()
+    idx = np.asarray(option_indices)
+    pricer = ref.MonteCarloPricerUni(num_simulations=n_paths, num_steps=N_STEPS, seed=SEED, use_numba=True)
+    if warm:  # JIT (cache=True: compiled once per box)
+        pricer.price_batch(g["S"][idx[:2]], g["K"][idx[:2]], g["T"][idx[:2]], g["r"][idx[:2]], g["sigma"][idx[:2]], "call", g["q"][idx[:2]])
+    t0 = time.perf_counter()
+    prices = pricer.price_batch(g["S"][idx], g["K"][idx], g["T"][idx], g["r"][idx], g["sigma"][idx], "call", g["q"][idx])
+    return time.perf_counter() - t0, np.asarray(prices)
+
+
+def reference_extras(ref):
+    """The reference's other backends on the single-option configs ("CPU baseline beside it"),
+    bounded sizes: NumPy (one thread - NumPy's generator is serial) and MCMethod.NUMBA (prange over paths) for the
+    European call, AsianOption / BarrierOption NumPy, compute_greeks_unified.  Best of 2 after a warm-up."""
+    P = dict(S=100.0, K=100.0, T=1.0, r=0.05, sigma=0.2)
+    out = {}
+
+    def best(fn, reps=2):
+        fn()
+        t = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            res = fn()
+            t.append(time.perf_counter() - t0)
+        return min(t), res
+
+    try:
+        pr = ref.MonteCarloPricer(100_000, N_STEPS, seed=SEED)
+        t, res = best(lambda: pr.price(**P, option_type="call"))
+        out["C1 MonteCarloPricer NUMPY 100k x 252"] = {"seconds": t, "path_steps_per_s": 100_000 * N_STEPS / t, "price": float(res), "threads": 1}
+        prn = ref.MonteCarloPricer(100_000, N_STEPS, seed=SEED, method=ref.MCMethod.NUMBA)
+        t, res = best(lambda: prn.price(**P, option_type="call"))
+        import numba
+
+        out["C1 MonteCarloPricer NUMBA 100k x 252"] = {"seconds": t, "path_steps_per_s": 100_000 * N_STEPS / t, "price": float(res),
+                                                        "threads": int(numba.get_num_threads())}
+        t, res = best(lambda: ref.AsianOption(**P, seed=SEED).price(n_paths=100_000, n_steps=N_STEPS), reps=1)
+        out["C3 AsianOption 100k x 252"] = {"seconds": t, "path_steps_per_s": 100_000 * N_STEPS / t, "price": float(res), "threads": 1}
+        t, res = best(lambda: ref.BarrierOption(**P, seed=SEED, barrier=120.0).price(n_paths=100_000, n_steps=365), reps=1)
+        out["C4 BarrierOption 100k x 365"] = {"seconds": t, "path_steps_per_s": 100_000 * 365 / t, "price": float(res), "threads": 1}
+        t, res = best(lambda: ref.compute_greeks_unified(pr, **P, option_type="call"), reps=1)
+        out["C2 compute_greeks_unified 100k x 252 (14 re-simulations)"] = {"seconds": t, "path_steps_per_s": 14 * 100_000 * N_STEPS / t,
+                                                                           "delta": float(res["delta"]), "threads": 1}
+    except Exception as exc:
+        out["error"] = repr(exc)
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 64))
     n_paths = 100_000
-    per_step = procs * 2  # options per timed step: two per worker
-    idx = list(np.linspace(0, N_OPT - 1, per_step).astype(int))
-    for _ in range(args.warmup):
-        cpu_sample(idx[:procs], 2_000, procs)
-    total_t = 0.0
-    for _ in range(args.steps):
-        t, _ = cpu_sample(idx, n_paths, procs)
-        total_t += t
-    work = per_step * n_paths * N_STEPS * args.steps
-    value = work / total_t
-    sample = (f"{per_step} grid options x {n_paths} paths x {N_STEPS} steps per step, NumPy restatement of "
-              f"simulate_gbm_numpy+payoff (oracle/reference_mc.py), one process per core over options")
-    # the reference's own multi-core backend (MCMethod.NUMBA, prange over paths) beside it, when numba is present
-    numba_line = None
-    try:
-        from oracle import reference_mc as orc
+    # stdout carries ONE JSON line: whatever the reference or Numba print goes to stderr meanwhile
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    ref = _load_reference()
+    extras = None
+    if ref is not None:
         import numba
 
-        orc.numba_backend_terminal(100.0, 1.0, 0.05, 0.2, 0.0, 1000, N_STEPS, SEED)  # JIT
-        t0 = time.perf_counter()
-        term = orc.numba_backend_terminal(100.0, 1.0, 0.05, 0.2, 0.0, 400_000, N_STEPS, SEED)
-        dt_numba = time.perf_counter() - t0
-        numba_line = {"value": 400_000 * N_STEPS / dt_numba, "unit": UNIT, "threads": int(numba.get_num_threads()),
-                      "sample": f"1 option x 400000 paths x {N_STEPS} steps, restatement of _gbm_terminal_parallel (gbm_numba.py:74-97)",
-                      "mean_terminal": float(term.mean())}
-    except Exception as exc:  # numba missing or unusable on this host: the NumPy arm above stands alone
-        numba_line = {"unavailable": repr(exc)}
+        threads = int(numba.get_num_threads())
+        per_step = max(2 * threads, 8)  # options per timed step: two per Numba thread (prange over options)
+        idx = list(np.linspace(0, N_OPT - 1, per_step).astype(int))
+        reference_grid_sample(ref, idx[:max(threads, 2)], 2_000, warm=True)
+        for _ in range(max(args.warmup - 1, 0)):
+            reference_grid_sample(ref, idx[:max(threads, 2)], 2_000)
+        total_t = 0.0
+        for _ in range(args.steps):
+            t, _ = reference_grid_sample(ref, idx, n_paths)
+            total_t += t
+        kind, used = "reference", threads
+        sample = (f"{per_step} grid options x {n_paths} paths x {N_STEPS} steps per step through the UNMODIFIED reference "
+                  f"(oracle/_ref: MonteCarloPricerUni.price_batch, Numba batch backend, prange over options, {threads} threads; host has {cores} cores)")
+        extras = reference_extras(ref)
+    else:
+        procs = max(1, min(cores, 64))
+        per_step = procs * 2  # options per timed step: two per worker
+        idx = list(np.linspace(0, N_OPT - 1, per_step).astype(int))
+        for _ in range(args.warmup):
+            cpu_sample(idx[:procs], 2_000, procs)
+        total_t = 0.0
+        for _ in range(args.steps):
+            t, _ = cpu_sample(idx, n_paths, procs)
+            total_t += t
+        kind, used = "port", procs
+        sample = (f"{per_step} grid options x {n_paths} paths x {N_STEPS} steps per step, NumPy restatement of "
+                  f"simulate_gbm_numpy+payoff (oracle/reference_mc.py; oracle/_ref not installed), one process per core over options")
+    work = per_step * n_paths * N_STEPS * args.steps
+    value = work / total_t
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "numba_prange": numba_line}
+            "gpu_launches": 0, "reference_other_backends": extras}
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
     print(json.dumps(line))
     return 0
 
@@ -190,6 +278,86 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+# MUFU per path-step of each kernel family (profiles/r02_sass_loops.txt): the XU pipe is the roof of all of them
+CONFIG_MUFU = {"european": 2.0, "asian": 2.0, "barrier": 2.0}
+NCU_CAPTURE = os.path.join(ROOT, "profiles", "r02_ncu_european.txt")
+
+
+def traffic_from_capture(path=NCU_CAPTURE):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the headline kernel, per launch, from the COMMITTED ncu --set full
+    capture of this bench command (tools/ncu_summary.py output).  Fails loudly when the capture is missing."""
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    if not os.path.exists(path):
+        raise SystemExit(f"bench.py: {path} is missing - roofline.traffic is read from the committed ncu capture, not typed in "
+                         "(regenerate with tools/gpu/r02_full_pass.sh)")
+    total, seen, in_kernel = 0.0, 0, False
+    with open(path) as f:
+        for line in f:
+            if line.startswith("=="):
+                if seen:
+                    break
+                in_kernel = "european_kernel<1, 1" in line
+            elif in_kernel and (line.startswith("dram__bytes_read.sum") or line.startswith("dram__bytes_write.sum")):
+                parts = line.split()
+                total += float(parts[1]) * scale[parts[2]]
+                seen += 1
+    if seen != 2:
+        raise SystemExit(f"bench.py: {path} holds no european_kernel<1,1,...> capture with DRAM byte counters")
+    return total, os.path.relpath(path, ROOT)
+
+
+def measure_configs(eng, peaks, rank, world, barrier):
+    """BASELINE.json configs[0..3] (SURVEY.md section 8d inputs) through the PUBLIC API, on every rank collectively: the
+    pricer classes shard the global path range and the kernel tail adds up the ranks' moments.  Best of `reps` after one
+    warm-up; kernel time from the engine's event ring (rank 0's share of the paths), API time by the host clock."""
+    import optionslab_b200 as ob
+
+    P = dict(S=100.0, K=100.0, T=1.0, r=0.05, sigma=0.2)
+    rows = {}
+
+    def record(name, family, path_steps, fn, reps, describe):
+        fn()
+        barrier()
+        eng.set_kernel_timing(True)
+        best, result = 1e30, None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            result = fn()
+            best = min(best, time.perf_counter() - t0)
+        kt = eng.kernel_timing()
+        eng.set_kernel_timing(False)
+        barrier()
+        if rank == 0:
+            kernel_s = kt["min_ms"] * 1e-3
+            row = {"kernel_ms": kt["min_ms"], "api_ms": best * 1e3, "path_steps": path_steps,
+                   "path_steps_per_s_api": path_steps / best, "path_steps_per_s_kernel": path_steps / world / kernel_s * world,
+                   "xu_frac_kernel": path_steps / world * CONFIG_MUFU[family] / kernel_s / peaks["mufu_per_s"],
+                   "plan": eng.last_plan()}
+            row.update(describe(result))
+            rows[name] = row
+
+    c1 = ob.MonteCarloPricer(100_000, 252, seed=42)
+    record("C1 European call 100k x 252", "european", 100_000 * 252, lambda: c1.price(**P, option_type="call", return_error=True), 50,
+           lambda r: {"price": r.price, "std_error": r.std_error})
+    c1d = ob.MonteCarloPricer(100_000, seed=42)
+    record("MonteCarloPricer default (100k x 1 step)", "european", 100_000, lambda: c1d.price(**P, option_type="call", return_error=True), 50,
+           lambda r: {"price": r.price, "std_error": r.std_error})
+    uni = ob.MonteCarloPricerUni(100_000, 100, seed=42)
+    record("MonteCarloPricerUni default delta_gamma (100k x 100, h=1e-4, 3 scenarios)", "european", 100_000 * 100,
+           lambda: uni.delta_gamma(**P, option_type="call", seed=7), 50, lambda r: {"delta": r[0], "gamma": r[1]})
+    c2 = ob.MonteCarloPricer(1_000_000, 252, seed=42)
+    for ot in ("call", "put"):
+        record(f"C2 Greeks {ot} 1M x 252 (14 CRN scenarios, one launch)", "european", 1_000_000 * 252,
+               lambda ot=ot: c2.greeks(**P, option_type=ot), 10, lambda g: {k: g[k] for k in ("price", "delta", "gamma", "vega")})
+    asian = ob.AsianOption(**P, seed=42)
+    record("C3 arithmetic Asian call 4M x 252", "asian", 4_000_000 * 252, lambda: asian.price(4_000_000, 252, return_error=True), 10,
+           lambda r: {"price": r.price, "std_error": r.std_error})
+    bar = ob.BarrierOption(**P, seed=42, barrier=120.0)
+    record("C4 up-and-out barrier call 16M x 365", "barrier", 16_000_000 * 365, lambda: bar.price(16_000_000, 365, "up-and-out", return_error=True), 5,
+           lambda r: {"price": r.price, "std_error": r.std_error})
+    return rows
+
+
 def run_engine_arm(args):
     import torch
 
@@ -274,7 +442,7 @@ def run_engine_arm(args):
 
     # ---- e2e: the public API, host buffers in, host prices out ---------------------------------------
     pricer = MonteCarloPricerUni(num_simulations=N_PATHS, num_steps=N_STEPS, seed=SEED)
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = args.steps  # the same K steps as `value`
     prices = pricer.price_batch(g["S"], g["K"], g["T"], g["r"], g["sigma"], "call", g["q"])  # warm-up (pinned buffers)
     barrier()
     t0 = time.perf_counter()
@@ -324,6 +492,9 @@ def run_engine_arm(args):
                      "xu_frac": arate * 2.0 / peaks["mufu_per_s"], "issue_frac": arate * ASIAN_INSTR_PER_STEP / peaks["issue_per_s"],
                      "all_prices_below_european": None, "moments": am}
 
+    # ---- BASELINE configs C1-C4 + the Greeks launch through the public API (collective under torchrun) -------------
+    configs = None if args.no_configs else measure_configs(eng, peaks, rank, world, barrier)
+
     if rank == 0:
         # sanity: the timed run produced prices (checked against Black-Scholes within 4 standard errors)
         from optionslab_b200 import runtime
@@ -347,6 +518,7 @@ def run_engine_arm(args):
             ap = runtime.discounted_price(asian.pop("moments"), g["r"], g["T"])
             asian["all_prices_below_european"] = bool(np.all(ap <= dev_prices + 5.0 * se + 1e-5))
 
+        traffic, traffic_src = (None, "not read (--traffic-capture none)") if args.traffic_capture == "none" else traffic_from_capture(args.traffic_capture)
         kernel_s = ktime["mean_ms"] * 1e-3
         per_gpu_steps = work_per_step / world
         kernel_rate = per_gpu_steps / kernel_s  # path-steps/s of ONE GPU inside the kernel
@@ -368,6 +540,9 @@ def run_engine_arm(args):
             "unit": "MUFU op/s" if bound == "xu" else "thread-instr/s",
             "frac": max(mufu_frac, issue_frac),
             "peak_source": "measured live by b200mc_measure_peaks on this GPU (pipe microbenchmarks)",
+            # 16 MUFU lanes per SM per clock at the SM clock the run sustained (B200: 148 SMs)
+            "peak_paper": eng.info()["sm_count"] * 16 * (clocks["sm_mhz"] or 1965.0) * 1e6,
+            "frac_of_paper": kernel_rate * MUFU_PER_STEP / (eng.info()["sm_count"] * 16 * (clocks["sm_mhz"] or 1965.0) * 1e6),
             "per_path_step": {"instructions": INSTR_PER_STEP, "mufu": MUFU_PER_STEP, "imad_wide": IMAD_PER_STEP, "alu": LOP_PER_STEP},
             "xu_frac": mufu_frac, "issue_frac": issue_frac,
             "imad_frac": kernel_rate * IMAD_PER_STEP / peaks["imad_wide_per_s"],
@@ -376,10 +551,10 @@ def run_engine_arm(args):
             # dispatch-port view (profiles/r01_variants15_fma_pipe_model.txt): an IMAD.WIDE holds an SMSP's dispatch port for
             # ~4 cycles (measured 4.1-4.4 including loop overhead), every other instruction for 1; fraction of the measured issue peak under that weighting
             "dispatch_frac": kernel_rate * (INSTR_PER_STEP + IMAD_PER_STEP * (IMAD_WIDE_DISPATCH_CYCLES - 1.0)) / peaks["issue_per_s"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size (N=1) from the ncu --set full capture
-            # (profiles/r01_ncu_european.txt: 369 KB read, 0 B written - the 8 MB of tile partials are still in the 126 MB
-            # L2 when the launch ends and are consumed there by fold_kernel); algorithmic: 262 KB in + 98 KB moments out
-            "traffic": 368640.0 if world == 1 else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size (N=1), read from the committed ncu --set
+            # full capture of this bench command (the tile partials stay in the 126 MB L2 and are folded there by the same
+            # kernel); algorithmic: 262 KB of parameters in + 98 KB of moments out
+            "traffic": traffic if world == 1 else None, "traffic_source": traffic_src,
             "hbm": {"achieved_gbs": hbm_bytes / kernel_s / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
                     "frac": hbm_bytes / kernel_s / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": hbm_bytes},
             "pipe_peaks": peaks,
@@ -387,14 +562,26 @@ def run_engine_arm(args):
         cores = os.cpu_count() or 1
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            idx = list(np.linspace(0, N_OPT - 1, 40).astype(int))  # ~12 s of single-core NumPy work
-            cpu_sample(idx[:1], 2_000, 1)
-            t_cpu, cpu_prices = cpu_sample(idx, 100_000, 1)
-            cpu = {"value": len(idx) * 100_000 * N_STEPS / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": f"{len(idx)} grid options x 100000 paths x {N_STEPS} steps, NumPy restatement of the reference "
-                             f"(oracle/reference_mc.py; NumPy's generator is single-threaded), host has {cores} cores",
-                   "seconds": t_cpu,
-                   "max_abs_price_diff_vs_gpu": float(np.max(np.abs(cpu_prices - dev_prices[idx])))}
+            ref = _load_reference()
+            if ref is not None:  # the unmodified reference, its own multi-core path, ~10-30 core-seconds
+                import numba
+
+                threads = int(numba.get_num_threads())
+                idx = list(np.linspace(0, N_OPT - 1, max(4 * threads, 16)).astype(int))
+                reference_grid_sample(ref, idx[:max(threads, 2)], 2_000, warm=True)
+                t_cpu, cpu_prices = reference_grid_sample(ref, idx, 100_000)
+                cpu = {"value": len(idx) * 100_000 * N_STEPS / t_cpu, "unit": UNIT, "cores": threads, "kind": "reference",
+                       "sample": f"{len(idx)} grid options x 100000 paths x {N_STEPS} steps through the UNMODIFIED reference (oracle/_ref: "
+                                 f"MonteCarloPricerUni.price_batch, Numba batch backend, prange over options, {threads} threads; host has {cores} cores)",
+                       "seconds": t_cpu, "max_abs_price_diff_vs_gpu": float(np.max(np.abs(cpu_prices - dev_prices[idx])))}
+            else:
+                idx = list(np.linspace(0, N_OPT - 1, 40).astype(int))  # ~12 s of single-core NumPy work
+                cpu_sample(idx[:1], 2_000, 1)
+                t_cpu, cpu_prices = cpu_sample(idx, 100_000, 1)
+                cpu = {"value": len(idx) * 100_000 * N_STEPS / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                       "sample": f"{len(idx)} grid options x 100000 paths x {N_STEPS} steps, NumPy restatement of the reference "
+                                 f"(oracle/reference_mc.py; oracle/_ref not installed), host has {cores} cores",
+                       "seconds": t_cpu, "max_abs_price_diff_vs_gpu": float(np.max(np.abs(cpu_prices - dev_prices[idx])))}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * elapsed_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -409,7 +596,7 @@ def run_engine_arm(args):
                     "d2h_bytes_per_step": int(N_OPT * 24), "steps": e2e_steps, "api": "MonteCarloPricerUni.price_batch (numpy in/out)"},
             "gpu_launches": int(launches),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "asian_grid": asian,
+            "asian_grid": asian, "configs": configs,
             "prices_ok": ok, "max_abs_z_vs_black_scholes": float(np.max(np.abs(z))),
             "z_vs_black_scholes": {"options_in_clt_regime": int(clt.sum()), "max_abs_clt": float(np.max(z[clt])),
                                    "mean_clt": float(np.mean(((dev_prices - bs) / np.maximum(se, 1e-300))[clt])),
@@ -435,6 +622,8 @@ def main():
     ap.add_argument("--impl", choices=["engine", "reference"], default="engine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-asian-grid", action="store_true", help="skip the extra Asian-grid measurement (ncu runs)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1-C4 block (ncu runs)")
+    ap.add_argument("--traffic-capture", default=NCU_CAPTURE, help="ncu summary roofline.traffic is read from; 'none' only for the run that produces it")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -36,21 +36,26 @@ class ExoticOptionBase:
         return self.seed if self.seed is not None else runtime.entropy_seed()
 
     def _run(self, spec, scenarios: Sequence, n_paths: int, barrier: float = 0.0):
-        sc = np.asarray(scenarios, dtype=np.float64).reshape(-1, 6)
-        out_m = []
+        """-> ([(sum, sum_sq, n)], scenarios) of (S, K, T, r, sigma, q) tuples on common random numbers: one fused launch per
+        16 scenarios through the engine's latency path (runtime.simulate_scalars)."""
+        sc = [tuple(float(x) for x in s) for s in scenarios]
         seed = self._seed()
+        out = []
         for lo in range(0, len(sc), _ffi.MAX_SCENARIOS):
-            blk = sc[lo:lo + _ffi.MAX_SCENARIOS]
-            params = _ffi.make_params(blk[:, 0], blk[:, 1], blk[:, 2], blk[:, 3], blk[:, 4], blk[:, 5], barrier)[None, :]
-            out_m.append(runtime.simulate(spec, params, seed, n_paths)[0])
-        return np.concatenate(out_m), sc
+            out += runtime.simulate_scalars(spec, sc[lo:lo + _ffi.MAX_SCENARIOS], seed, n_paths, barrier=barrier)
+        return out, sc
 
     def _finish(self, m, sc, return_error):
-        prices = runtime.discounted_price(m, sc[:, 3], sc[:, 2])
-        if return_error:
-            se = runtime.discounted_std_error(m, sc[:, 3], sc[:, 2])
-            return [MCResult(float(p), float(e), int(n)) for p, e, n in zip(prices, se, m["n"])]
-        return [np.float64(p) for p in prices]
+        res = []
+        for (total, total_sq, n), s in zip(m, sc):
+            disc = runtime.discount(s[3], s[2])
+            price = disc * total / n  # exp(-rT) * mean(payoffs), exotic_options.py:131
+            if return_error:
+                mean = total / n
+                res.append(MCResult(float(price), float(disc * np.sqrt(max(total_sq / n - mean * mean, 0.0)) / np.sqrt(n)), int(n)))
+            else:
+                res.append(np.float64(price))
+        return res
 
     def _self_scenario(self):
         return [(self.S, self.K, self.T, self.r, self.sigma, self.q)]
@@ -134,6 +139,10 @@ class LookbackOption(ExoticOptionBase):
         return [float(p) for p in self._finish(m, sc, False)]
 
 
+def _as_tuples(m):
+    return [(float(x["sum"]), float(x["sum_sq"]), float(x["n"])) for x in m]
+
+
 def _run_structured(opt: ExoticOptionBase, spec, product, scenarios: Sequence, n_paths: int):
     """Moments of every (S, K, T, r, sigma, q) scenario on common random numbers, sharded over ranks like runtime.simulate."""
     from . import distributed
@@ -206,13 +215,13 @@ class CliquetOption(ExoticOptionBase):
             p = self._degenerate(self._self_scenario(), n_steps, n_periods)[0]
             return MCResult(p, 0.0, int(n_paths)) if return_error else np.float64(p)
         m, sc = self._launch(self._self_scenario(), n_paths, n_steps, n_periods)
-        return self._finish(m, sc, return_error)[0]
+        return self._finish(_as_tuples(m), sc.tolist(), return_error)[0]
 
     def price_scenarios(self, scenarios, n_paths: int = 100000, n_steps: int = 252, n_periods: int = 12, **kwargs):
         if 0 < n_steps < n_periods:
             return self._degenerate(scenarios, n_steps, n_periods)
         m, sc = self._launch(scenarios, n_paths, n_steps, n_periods)
-        return [float(p) for p in self._finish(m, sc, False)]
+        return [float(p) for p in self._finish(_as_tuples(m), sc.tolist(), False)]
 
 
 def price_asian(S, K, T, r, sigma, avg_type="arithmetic", option_type="call", n_paths=100000, seed=None) -> float:

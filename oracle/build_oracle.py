@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY — compile oracle/philox_oracle.c into oracle/_build/libphilox_oracle.so.
 
-The reference is pure Python (no C sources to compile), so there is no oracle/_ref: the real
-reference is exercised at golden-generation time instead (tests/golden/make_goldens.py).
+The reference is pure Python (no C sources to compile); its unmodified package is installed into
+oracle/_ref by oracle/build_ref.py (timed by bench.py, compared with the restatement by
+tests/test_reference_install.py) and exercised at golden-generation time (tests/golden/make_goldens.py).
 """
 
 import os

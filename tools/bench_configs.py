@@ -151,7 +151,7 @@ def main():
     except Exception as exc:  # measurement extra; never fatal
         print(json.dumps({"parity_mode_timing_failed": repr(exc)}), flush=True)
     out = {"peaks": peaks, "device": eng.info(), "rows": rows}
-    path = os.path.join(ROOT, "gpurun_out", "configs_r01.json")
+    path = os.path.join(ROOT, "gpurun_out", "configs_r02.json")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as f:
         json.dump(out, f, indent=1)
