@@ -518,7 +518,12 @@ def run_engine_arm(args):
             ap = runtime.discounted_price(asian.pop("moments"), g["r"], g["T"])
             asian["all_prices_below_european"] = bool(np.all(ap <= dev_prices + 5.0 * se + 1e-5))
 
-        traffic, traffic_src = (None, "not read (--traffic-capture none)") if args.traffic_capture == "none" else traffic_from_capture(args.traffic_capture)
+        if world > 1:
+            traffic, traffic_src = None, "single-GPU figure only (the capture is of the N=1 launch)"
+        elif args.traffic_capture == "none":
+            traffic, traffic_src = None, "not read (--traffic-capture none)"
+        else:
+            traffic, traffic_src = traffic_from_capture(args.traffic_capture)
         kernel_s = ktime["mean_ms"] * 1e-3
         per_gpu_steps = work_per_step / world
         kernel_rate = per_gpu_steps / kernel_s  # path-steps/s of ONE GPU inside the kernel

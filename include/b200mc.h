@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200MC_ABI_VERSION 7
+#define B200MC_ABI_VERSION 8
 #define B200MC_MAX_SCENARIOS 16
 
 typedef struct b200mc_engine b200mc_engine_t;
@@ -323,6 +323,23 @@ int b200mc_payoffs_from_normals_device(b200mc_engine_t* eng, const b200mc_spec_t
  * for step s of global path p of (seed, stream). */
 int b200mc_generate_normals(b200mc_engine_t* eng, uint64_t seed, uint32_t stream, uint64_t path_begin,
                             uint64_t n_paths, uint32_t n_steps, float* out_host);
+/* Statistics of the normals of paths [path_begin, path_begin + n_paths) x n_steps of (seed, stream), gathered on the
+ * device (the stream a simulation consumes, at GPU scale: 1e10 draws take tens of milliseconds):
+ *   hist_z[256]      counts of z in 256 equal bins over [-6, 6) (outer bins collect the rest)
+ *   hist_joint[64*64] counts of (z_cos, z_sin) - the two normals of ONE random word - on a 64 x 64 grid over [-4, 4)^2,
+ *                    row = cosine-branch normal (outer cells collect the rest)
+ *   tails[4]         exact counts of z > 4, z > 5, z < -4, z < -5
+ *   moments[16]      0..3: sum z, z^2, z^3, z^4;  4..7: same-word sums z1 z2, z1^2 z2^2, z1 z2^3, z1^3 z2;
+ *                    8..10: lag-1 sums a b, a^2 b^2, a b^3 (a = sine branch of word n, b = cosine branch of word n+1);
+ *                    11: normals counted, 12: same-word pairs counted, 13: lag-1 pairs counted; 14, 15 unused */
+typedef struct {
+  uint64_t hist_z[256];
+  uint64_t hist_joint[64 * 64];
+  uint64_t tails[4];
+  double moments[16];
+} b200mc_rng_stats_t;
+int b200mc_rng_statistics(b200mc_engine_t* eng, uint64_t seed, uint32_t stream, uint64_t path_begin, uint64_t n_paths,
+                          uint32_t n_steps, b200mc_rng_stats_t* out);
 /* Raw Philox4x32-10: in = n x {c0,c1,c2,c3,k0,k1}, out = n x 4 words (known-answer tests). */
 int b200mc_philox_raw(b200mc_engine_t* eng, const uint32_t* ctr_key_host, uint32_t n, uint32_t* out_host);
 

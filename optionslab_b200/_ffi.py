@@ -18,7 +18,7 @@ from .exceptions import AccelerationError, MonteCarloError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200mc.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_SCENARIOS = 16
 
 EUROPEAN, ASIAN_ARITH, ASIAN_GEOM, BARRIER, LOOKBACK, CLIQUET, AUTOCALLABLE = range(7)
@@ -56,6 +56,7 @@ MOMENTS_DTYPE = np.dtype([("sum", "f8"), ("sum_sq", "f8"), ("n", "f8")])
 CV_MOMENTS_DTYPE = np.dtype([("sum_payoff", "f8"), ("sum_payoff_sq", "f8"), ("sum_terminal", "f8"), ("sum_terminal_sq", "f8"),
                              ("sum_payoff_terminal", "f8"), ("n", "f8")])
 
+RNG_STATS_DTYPE = np.dtype([("hist_z", "u8", (256,)), ("hist_joint", "u8", (4096,)), ("tails", "u8", (4,)), ("moments", "f8", (16,))])
 HESTON_PARAMS_DTYPE = np.dtype([(n, "f8") for n in ("S", "K", "T", "r", "q", "kappa", "theta", "sigma_v", "rho", "v0")] + [("reserved", "f8", (2,))])
 JUMP_PARAMS_DTYPE = np.dtype([("model", "i4"), ("reserved0", "i4"), ("lambda_j", "f8"), ("a", "f8"), ("b", "f8"), ("c", "f8"),
                               ("reserved", "f8", (3,))])
@@ -101,6 +102,7 @@ SIGNATURES = {
     "b200mc_payoffs_from_normals": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_int, _P, C.c_uint64, _P, _P]),
     "b200mc_payoffs_from_normals_device": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_int, _P, C.c_uint64, _P, _P, _P]),
     "b200mc_generate_normals": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, _P]),
+    "b200mc_rng_statistics": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, _P]),
     "b200mc_philox_raw": (C.c_int, [_P, _P, C.c_uint32, _P]),
     "b200mc_measure_peaks": (C.c_int, [_P, C.POINTER(Peaks)]),
     "b200mc_kernel_launches": (C.c_uint64, [_P]),
@@ -475,6 +477,16 @@ class Engine:
                                                out.ctypes.data)
         self._check(rc, "b200mc_generate_normals")
         return out
+
+    def rng_statistics(self, seed: int, n_paths: int, n_steps: int, *, stream: int = 0, path_begin: int = 0) -> dict:
+        """Device-side histograms / cross moments / tail counts of the normal stream (b200mc_rng_stats_t)."""
+        out = np.zeros(1, dtype=RNG_STATS_DTYPE)
+        rc = self._lib.b200mc_rng_statistics(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream) & 0xFFFFFFFF, int(path_begin), int(n_paths),
+                                             int(n_steps), out.ctypes.data)
+        self._check(rc, "b200mc_rng_statistics")
+        r = out[0]
+        return {"hist_z": r["hist_z"].copy(), "hist_joint": r["hist_joint"].reshape(64, 64).copy(), "tails": r["tails"].copy(),
+                "moments": r["moments"].copy()}
 
     def philox_raw(self, ctr_key: np.ndarray) -> np.ndarray:
         ck = np.ascontiguousarray(ctr_key, dtype=np.uint32).reshape(-1, 6)

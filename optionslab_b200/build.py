@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200mc.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["philox.cuh", "normal.cuh", "mc_kernels.cuh", "f64_kernels.cuh", "peaks.cuh", "sobol.cuh", "models.cuh", "structured.cuh", "../../include/b200mc.h"]
+HEADERS = ["philox.cuh", "normal.cuh", "mc_kernels.cuh", "f64_kernels.cuh", "peaks.cuh", "sobol.cuh", "models.cuh", "structured.cuh", "rng_stats.cuh", "../../include/b200mc.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

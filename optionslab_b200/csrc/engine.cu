@@ -19,6 +19,7 @@
 #include "mc_kernels.cuh"
 #include "models.cuh"
 #include "peaks.cuh"
+#include "rng_stats.cuh"
 #include "sobol.cuh"
 #include "structured.cuh"
 
@@ -42,7 +43,7 @@ struct b200mc_engine {
   cudaDeviceProp prop{};
   std::string error;
   std::mutex mutex;  // one call at a time per engine (the reference's pricer objects are single-threaded too)
-  DeviceBuffer partials, tickets, params_dev, moments_dev, scratch_a, scratch_b;
+  DeviceBuffer partials, tickets, params_dev, moments_dev, scratch_a, scratch_b, qmc_wpart, qmc_tickets;
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   // single-option launches: parameters ride in the kernel arguments, the finishing CTA writes the records straight into
@@ -529,7 +530,7 @@ void b200mc_destroy(b200mc_engine_t* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  for (DeviceBuffer* b : {&e->partials, &e->tickets, &e->params_dev, &e->moments_dev, &e->scratch_a, &e->scratch_b})
+  for (DeviceBuffer* b : {&e->partials, &e->tickets, &e->params_dev, &e->moments_dev, &e->scratch_a, &e->scratch_b, &e->qmc_wpart, &e->qmc_tickets})
     if (b->ptr) cudaFree(b->ptr);
   for (int r = 0; r < kMaxRanks; ++r)
     if (e->comm.ipc_opened[r] && e->comm.peer[r]) cudaIpcCloseMemHandle(e->comm.peer[r]);
@@ -1112,15 +1113,36 @@ static int sobol_run(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc
   CU_TRY(e, cudaMemcpyAsync(e->params_dev.ptr, pin_in, in_bytes, cudaMemcpyHostToDevice, e->stream));
 
   const uint32_t ns = pad_scenarios(n_scen);
-  // points per thread 2^pb: 16 when that still gives every SM a CTA, else 4, else 1.  (At 2^20 points 256 CTAs of 16
-  // points per thread beat 1024 CTAs of 4: 0.291 vs 0.301 ms; the smaller tiles only pay when SMs would sit idle.)
-  const uint64_t want_ctas = (uint64_t)e->prop.multiProcessorCount;
+  // Tile shape: 2^pb points per thread (16 amortises the per-thread table work best) x dsplit CTAs per point tile, each taking a
+  // share of the dimensions (whole 64-dimension chunks).  What a small point set needs is BALANCE, not occupancy: 2^20 points
+  // are 256 sixteen-point tiles on 148 SMs - the busiest SM gets 2 of them against an average of 1.73 - and two half-tiles per
+  // tile leave that ratio where it was (measured: 0.275 -> 0.273 ms).  Four quarter-tiles (1024 CTAs, handed out dynamically:
+  // at most 7 per SM against an average of 6.9) even it out.  So: the fewest CTAs whose per-SM maximum is within 5% of the mean.
+  const uint32_t chunks = (spec->n_steps + kSobolDimChunk - 1) / kSobolDimChunk;
+  const double n_sm = (double)e->prop.multiProcessorCount;
   int pb = kSobolMaxPointBits;
-  while (pb > 0 && ((n_points >> (pb + kSobolTidBits)) * n_opt) < want_ctas) pb -= 2;
+  uint32_t dsplit = 1;
+  double best_balance = -1.0;
+  for (int cand_pb = kSobolMaxPointBits; cand_pb >= 0 && best_balance < 0.95; cand_pb -= 2) {
+    for (uint32_t cand_ds = 1; cand_ds <= 4 && cand_ds <= chunks && best_balance < 0.95; cand_ds *= 2) {
+      const double ctas_c = std::ceil((double)n_points / (double)((uint64_t)kBlock << cand_pb)) * n_opt * cand_ds;
+      const double balance = (ctas_c / n_sm) / std::ceil(ctas_c / n_sm);
+      if (balance > best_balance + 0.05) best_balance = balance, pb = cand_pb, dsplit = cand_ds;
+    }
+  }
+  if (terminal_host) dsplit = 1;  // the terminal-price output is written by the CTA that owns all dimensions
   const uint64_t tile_points = (uint64_t)kBlock << pb;
   const uint64_t tiles = (n_points + tile_points - 1) / tile_points;
-  const uint64_t ctas = tiles * n_opt;
+  const uint64_t ctas = tiles * n_opt * dsplit;
   if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
+  if (dsplit > 1) {
+    if (int rc = reserve(e, e->qmc_wpart, tiles * n_opt * dsplit * tile_points * sizeof(float))) return rc;
+    const size_t ticket_bytes = tiles * n_opt * sizeof(uint32_t);
+    if (e->qmc_tickets.bytes < ticket_bytes) {
+      if (int rc = reserve(e, e->qmc_tickets, ticket_bytes)) return rc;
+      CU_TRY(e, cudaMemset(e->qmc_tickets.ptr, 0, e->qmc_tickets.bytes));
+    }
+  }
   if (int rc = reserve_fold(e, n_opt, (uint32_t)tiles, 3 * ns)) return rc;
   if (int rc = order_before(e, e->stream)) return rc;
   SobolArgs a{};
@@ -1129,6 +1151,9 @@ static int sobol_run(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc
   a.fold.tickets = (uint32_t*)e->tickets.ptr;
   a.fold.out = e->moments_dev.ptr;
   a.fold.samples = (double)n_points;
+  a.dsplit = dsplit;
+  a.wpart = (float*)e->qmc_wpart.ptr;
+  a.tile_tickets = (uint32_t*)e->qmc_tickets.ptr;
   a.dirnums = dir_dev;
   a.shift = shift_dev;
   a.point_begin = point_begin;
@@ -1253,6 +1278,33 @@ int b200mc_sobol_normals(b200mc_engine_t* e, const uint32_t* x_host, uint64_t n,
   CU_TRY(e, cudaMemcpyAsync(out_host, e->scratch_b.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
   return 0;
+}
+
+int b200mc_rng_statistics(b200mc_engine_t* e, uint64_t seed, uint32_t stream, uint64_t path_begin, uint64_t n_paths, uint32_t n_steps,
+                          b200mc_rng_stats_t* out) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  if (!out || n_paths == 0 || n_steps == 0) return fail(e, B200MC_ERR_INVALID, "bad argument");
+  static_assert(sizeof(b200mc_rng_stats_t) == (kStatsBinsZ + kStatsBinsJoint * kStatsBinsJoint + 4) * 8 + kStatsMoments * 8, "stats layout");
+  CU_TRY(e, cudaSetDevice(e->device));
+  if (int rc = reserve(e, e->scratch_a, sizeof(b200mc_rng_stats_t))) return rc;
+  if (int rc = order_before(e, e->stream)) return rc;
+  CU_TRY(e, cudaMemsetAsync(e->scratch_a.ptr, 0, sizeof(b200mc_rng_stats_t), e->stream));
+  b200mc_rng_stats_t* d = (b200mc_rng_stats_t*)e->scratch_a.ptr;
+  RngStatsArgs a{};
+  a.rk = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32));
+  a.stream = stream, a.path_begin = path_begin, a.n_paths = n_paths, a.n_steps = n_steps;
+  a.hist_z = (unsigned long long*)d->hist_z;
+  a.hist_joint = (unsigned long long*)d->hist_joint;
+  a.moments = d->moments;
+  a.tails = (unsigned long long*)d->tails;
+  const unsigned grid = (unsigned)std::min<uint64_t>((n_paths + kBlock - 1) / kBlock, (uint64_t)e->prop.multiProcessorCount * 8);
+  rng_stats_kernel<<<grid, kBlock, 0, e->stream>>>(a);
+  CU_TRY(e, cudaGetLastError());
+  e->launches += 1;
+  CU_TRY(e, cudaMemcpyAsync(out, d, sizeof(b200mc_rng_stats_t), cudaMemcpyDeviceToHost, e->stream));
+  CU_TRY(e, cudaStreamSynchronize(e->stream));
+  return order_after(e, e->stream);
 }
 
 int b200mc_philox_raw(b200mc_engine_t* e, const uint32_t* in_host, uint32_t n, uint32_t* out_host) {

@@ -16,15 +16,16 @@
 //           u = j/2^23 is 2 * (1 - 1.0598e-6)), so E[z^2] = 1 exactly; the radius is capped at 5.65.
 //   angle:  g = float in [1,2) whose mantissa is the top 23 bits of the BYTE-REVERSED word
 //           [b0 b1 b2>>1] (one PRMT + one LEA.HI) = the angle in turns; theta = fma(g, 2pi, -3pi) in
-//           [-pi, pi).  The angle's leading 9 bits (b0 and bit 0 of b1) are bits the radius never
-//           sees, so every one of the 2^23 radius values is paired with exactly 512 equally spaced
-//           angles: every product moment E[r^a cos^b sin^c] with b + c < 512 equals that of a
-//           continuous uniform angle.  The angle's trailing bits re-use the radius' LEAST significant
-//           bits (b1>>1 moves r by < 2^-16 relative), which shifts those 512-angle combs by a
-//           quasi-independent offset: the 2^32 (u, theta) points fill the square evenly instead of
-//           stacking on 512 lines (a fixed 512-angle grid puts an atom of mass 1/256 at z = 0; taking
-//           the offset from the radius' leading bits skews z near 0 and in the tails -- both fail a
-//           Kolmogorov-Smirnov test at 1e7 draws; this layout passes at 3e7, tests/test_philox_oracle.py).
+//           [-pi, pi).  The radius reads the word's bits 31..9 (b3, b2, and b1 without its lowest bit); the angle's
+//           leading 8 bits are b0 - bits the radius never sees - so every one of the 2^23 radius values is paired
+//           with exactly 256 equally spaced angles: every product moment E[r^a cos^b sin^c] with b + c < 256
+//           equals that of a continuous uniform angle.  From its 9th bit on the angle re-uses bits of the radius,
+//           the radius' LEAST significant ones first (bit 0 of b1 is the angle's 16th bit and outside the radius;
+//           b1>>1 moves r by < 2^-16 relative), which shifts those 256-angle combs by a quasi-independent offset:
+//           the 2^32 (u, theta) points fill the square evenly instead of stacking on 256 lines (a fixed angle grid
+//           puts an atom at z = 0; taking the offset from the radius' leading bits skews z near 0 and in the tails
+//           -- both fail a Kolmogorov-Smirnov test at 1e7 draws; this layout passes at 3e7,
+//           tests/test_philox_oracle.py, and a 1e10-draw binned chi-square on the device, tests/test_gpu_rng.py).
 //   z_cos = kRadScale*rad*cos(theta), z_sin = kRadScale*rad*sin(theta)
 #pragma once
 #include <cuda_runtime.h>

@@ -2,10 +2,12 @@
 // published round function: two 32x32->64 multiplies by fixed constants, the high words XORed with
 // the other counter words and the round key, the key bumped by Weyl constants each round.
 //
-// RNG stream contract of this engine (documented in DESIGN.md, restated in oracle/philox_oracle.c):
+// RNG stream contract of this engine (normative statement: normal.cuh; restated in
+// oracle/philox_oracle.c):
 //   key     = (seed & 0xffffffff, seed >> 32)
-//   counter = (path & 0xffffffff, path >> 32, step_block, stream)
-//   the 4 output words feed the normals of steps 4*step_block + {0,1,2,3} of that path.
+//   counter = (path & 0xffffffff, j, path >> 32, stream),   j = 0, 1, 2, ... the call index of the path
+//   the 4 output words of call j are 4 Box-Muller pairs and feed the normals of steps 8j .. 8j+7 of that path
+//   (word i: steps 8j + 2i and 8j + 2i + 1).  The fast-varying word j sits in c1, which round 1 only XORs.
 #pragma once
 #include <stdint.h>
 

@@ -47,6 +47,11 @@ struct SobolArgs {
   int32_t is_put;
   double* terminal_out;           // non-null: also write S_T per point ([n_points], then the mirrored [n_points] when terminal_anti)
   int32_t terminal_anti;
+  // dimension split: point sets too small to fill the chip give each point tile to `dsplit` CTAs, each summing the normals of
+  // its share of the dimensions; the tile's last CTA adds the partial sums (in part order) and prices the payoff
+  uint32_t dsplit;
+  float* wpart;                   // [n_opt * tiles][dsplit][points per tile]
+  uint32_t* tile_tickets;         // [n_opt * tiles], zero between launches
 };
 
 // Phi^-1 in FP32, branch-free.  t = min(u, 1-u) in [1e-10, 1/2], y = sqrt(-2 ln t) in [1.1774, 6.7861]:
@@ -54,13 +59,16 @@ struct SobolArgs {
 //   tools/fit_inverse_normal.py (max abs error of the FP32 Horner form: 1.3e-6, at |z| = 6).  2 MUFU + 15 FFMA.
 //   A piecewise central/tail form (Giles) is more accurate in relative terms near z = 0 but its tail branch
 //   diverges in 19% of the warps: measured 25% slower (profiles/r01_variants13_inverse_normal.txt).
-// x in [0, 2^bits): the Sobol integer.  u = x * 2^-bits clipped to [1e-10, 1 - 1e-10] (gbm_qmc.py:36).
-// y = sqrt(-2 ln min(u, 1-u)) and the half u falls in.
-__device__ __forceinline__ float inverse_normal_radius(uint32_t x, uint32_t one, float scale, bool& lower) {
-  const uint32_t xr = one - x;
-  lower = x < xr;                                             // u < 1/2
-  const float t = fmaxf((float)(lower ? x : xr) * scale, 1e-10f);
-  return mufu_sqrt(mufu_lg2(t) * -1.38629436111989061883f);   // sqrt(-2 ln t)
+// xs = the Sobol integer shifted so that its top bit sits at bit 31 (u = xs * 2^-32; the table is staged top-aligned, so
+// the shift is free).  t = min(u, 1 - u) clipped to [1e-10, 1/2] (gbm_qmc.py:36), y = sqrt(-2 ln t) and the half u falls in.
+// (A branch-free fold (xs ^ m) + (xs >> 31) with the sign applied by one LOP3 was measured 4% SLOWER at 2^24 points than
+// this compare-select form; written as (xs ^ m) - m the compiler emits IABS + a signed conversion, 3% faster but wrong for
+// u = 1/2 exactly.)
+__device__ __forceinline__ float inverse_normal_radius(uint32_t xs, bool& lower) {
+  const uint32_t xr = 0u - xs;  // 2^32 - xs: exactly 1 - u
+  lower = (int32_t)xs >= 0;     // u < 1/2
+  const float t = fmaxf(__uint2float_rn(lower ? xs : xr) * 2.3283064365386963e-10f, 1e-10f);
+  return mufu_sqrt(mufu_lg2(t) * -1.38629436111989061883f);  // sqrt(-2 ln t)
 }
 
 #define B200MC_NDTRI_HORNER(FMA, C)                                                                   \
@@ -70,9 +78,9 @@ __device__ __forceinline__ float inverse_normal_radius(uint32_t x, uint32_t one,
   p = FMA(p, v, C(-4.184841491e-02f)); p = FMA(p, v, C(7.395411314e-02f));  p = FMA(p, v, C(-1.353623019e-01f)); \
   p = FMA(p, v, C(3.068033996e+00f));  p = FMA(p, v, C(3.381260124e+00f));
 
-__device__ __forceinline__ float inverse_normal_from_sobol(uint32_t x, uint32_t one, float scale) {
+__device__ __forceinline__ float inverse_normal_from_sobol(uint32_t xs) {
   bool lower;
-  const float y = inverse_normal_radius(x, one, scale, lower);
+  const float y = inverse_normal_radius(xs, lower);
   const float v = fmaf(y, 3.565869380e-01f, -1.419849035e+00f);
   float p = -2.964769098e-03f;
 #define B200MC_ID(c) (c)
@@ -83,10 +91,10 @@ __device__ __forceinline__ float inverse_normal_from_sobol(uint32_t x, uint32_t 
 
 // Two points at once: the polynomial runs as packed FFMA2 (coefficients are FFMA2 immediates), 16 issue slots
 // for two normals instead of 30; the roundings are those of the scalar form, so both give the same bits.
-__device__ __forceinline__ void inverse_normal_from_sobol2(uint32_t x0, uint32_t x1, uint32_t one, float scale, float& z0, float& z1) {
+__device__ __forceinline__ void inverse_normal_from_sobol2(uint32_t xs0, uint32_t xs1, float& z0, float& z1) {
   bool lower0, lower1;
-  const float y0 = inverse_normal_radius(x0, one, scale, lower0);
-  const float y1 = inverse_normal_radius(x1, one, scale, lower1);
+  const float y0 = inverse_normal_radius(xs0, lower0);
+  const float y1 = inverse_normal_radius(xs1, lower1);
 #define B200MC_BOTH(c) pack2((c), (c))
   const f32x2 v = fma2(pack2(y0, y1), B200MC_BOTH(3.565869380e-01f), B200MC_BOTH(-1.419849035e+00f));
   f32x2 p = B200MC_BOTH(-2.964769098e-03f);
@@ -111,8 +119,12 @@ __global__ void __launch_bounds__(kBlock, NS <= 2 ? 4 : 2) qmc_european_kernel(c
   __shared__ __align__(16) uint32_t c_s[kSobolDimChunk][kSobolWords];
   __shared__ uint32_t xcta_s[kSobolDimChunk];
   __shared__ QmcCoef coef[NS];
-  const uint32_t opt = blockIdx.x / a.tiles;
-  const uint32_t tile = blockIdx.x - opt * a.tiles;
+  __shared__ uint32_t last_part;
+  const uint32_t dsplit = a.dsplit;
+  const uint32_t part = blockIdx.x % dsplit;
+  const uint32_t ot = blockIdx.x / dsplit;  // (option, tile)
+  const uint32_t opt = ot / a.tiles;
+  const uint32_t tile = ot - opt * a.tiles;
   if (threadIdx.x < NS) {
     const uint32_t k = threadIdx.x < a.n_scen ? threadIdx.x : a.n_scen - 1;
     const b200mc_params_t p = a.params[(size_t)opt * a.n_scen + k];
@@ -129,20 +141,24 @@ __global__ void __launch_bounds__(kBlock, NS <= 2 ? 4 : 2) qmc_european_kernel(c
   uint32_t tid_mask[kSobolTidBits];
 #pragma unroll
   for (int b = 0; b < kSobolTidBits; ++b) tid_mask[b] = 0u - ((threadIdx.x >> b) & 1u);
-  const uint32_t one = 1u << a.bits;
-  const float scale = 1.0f / (float)one;
+  const uint32_t up = 32u - a.bits;  // the table is staged top-aligned: integers x << up, u = (x << up) * 2^-32
 
   float W[kPoints];
 #pragma unroll
   for (int k = 0; k < kPoints; ++k) W[k] = 0.0f;
 
-  for (uint32_t d0 = 0; d0 < a.n_steps; d0 += kSobolDimChunk) {
-    const uint32_t nd = min((uint32_t)kSobolDimChunk, a.n_steps - d0);
+  // this CTA's share of the dimensions: whole 64-dimension chunks
+  const uint32_t chunks = (a.n_steps + kSobolDimChunk - 1) / kSobolDimChunk;
+  const uint32_t chunks_per_part = (chunks + dsplit - 1) / dsplit;
+  const uint32_t d_begin = min(part * chunks_per_part * kSobolDimChunk, a.n_steps);
+  const uint32_t d_end = min(d_begin + chunks_per_part * kSobolDimChunk, a.n_steps);
+  for (uint32_t d0 = d_begin; d0 < d_end; d0 += kSobolDimChunk) {
+    const uint32_t nd = min((uint32_t)kSobolDimChunk, d_end - d0);
     __syncthreads();  // the previous chunk is fully consumed
-    for (uint32_t i = threadIdx.x; i < nd * kSobolWords; i += kBlock) (&c_s[0][0])[i] = a.dirnums[(size_t)d0 * kSobolWords + i];
+    for (uint32_t i = threadIdx.x; i < nd * kSobolWords; i += kBlock) (&c_s[0][0])[i] = a.dirnums[(size_t)d0 * kSobolWords + i] << up;
     __syncthreads();
     if (threadIdx.x < nd) {
-      uint32_t x = a.shift[d0 + threadIdx.x];
+      uint32_t x = a.shift[d0 + threadIdx.x] << up;
       for (uint32_t ci = cta_index, b = kCtaShift; ci != 0; ci >>= 1, ++b)
         if (ci & 1u) x ^= c_s[threadIdx.x][b];
       xcta_s[threadIdx.x] = x;
@@ -160,7 +176,7 @@ __global__ void __launch_bounds__(kBlock, NS <= 2 ? 4 : 2) qmc_european_kernel(c
 #pragma unroll
       for (int b = 0; b < kSobolTidBits; ++b) x ^= word[PB + b] & tid_mask[b];
       if (kPoints == 1) {
-        W[0] += inverse_normal_from_sobol(x, one, scale);
+        W[0] += inverse_normal_from_sobol(x);
       } else {
 #pragma unroll
         for (int g = 0; g < kPoints; g += 2) {  // local point bits visited in Gray order: one XOR per point, two points per polynomial
@@ -168,13 +184,36 @@ __global__ void __launch_bounds__(kBlock, NS <= 2 ? 4 : 2) qmc_european_kernel(c
           const uint32_t x0 = x;
           x ^= word[0];                                         // g + 1: lowest set bit 0
           float z0, z1;
-          inverse_normal_from_sobol2(x0, x, one, scale, z0, z1);
+          inverse_normal_from_sobol2(x0, x, z0, z1);
           W[g ^ (g >> 1)] += z0;
           W[(g + 1) ^ ((g + 1) >> 1)] += z1;
         }
       }
     }
   }
+
+  if (dsplit > 1) {  // hand the partial sums to the tile's last CTA
+    float* mine = a.wpart + ((size_t)ot * dsplit + part) * (kBlock * kPoints);
+#pragma unroll
+    for (int k = 0; k < kPoints; ++k) __stcg(mine + k * kBlock + threadIdx.x, W[k]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      last_part = atomicAdd(a.tile_tickets + ot, 1u) == dsplit - 1 ? 1u : 0u;
+      if (last_part) a.tile_tickets[ot] = 0u;
+    }
+    __syncthreads();
+    if (!last_part) return;
+    __threadfence();
+    const float* parts = a.wpart + (size_t)ot * dsplit * (kBlock * kPoints);
+#pragma unroll
+    for (int k = 0; k < kPoints; ++k) {
+      float w = 0.0f;
+      for (uint32_t pp = 0; pp < dsplit; ++pp) w += __ldcg(parts + (size_t)pp * (kBlock * kPoints) + k * kBlock + threadIdx.x);  // part order: fixed
+      W[k] = w;
+    }
+  }
+  __syncthreads();  // coef[] (written before the loop) is read below; a launch of fewer than one chunk has no barrier yet
 
   float acc[2 * NS];
   uint32_t paid[(NS + 3) / 4];
@@ -226,10 +265,8 @@ __global__ void sobol_points_kernel(const uint32_t* __restrict__ dirnums, const 
 
 // Inspection: the FP32 normals the QMC kernel derives from given Sobol integers.
 __global__ void sobol_normals_kernel(const uint32_t* __restrict__ x, uint64_t n, uint32_t bits, float* __restrict__ out) {
-  const uint32_t one = 1u << bits;
-  const float scale = 1.0f / (float)one;
   for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (uint64_t)gridDim.x * blockDim.x)
-    out[idx] = inverse_normal_from_sobol(x[idx], one, scale);
+    out[idx] = inverse_normal_from_sobol(x[idx] << (32u - bits));
 }
 
 }  // namespace b200mc

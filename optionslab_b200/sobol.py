@@ -56,7 +56,34 @@ def _build_table(n_dims: int, seed) -> Tuple[np.ndarray, np.ndarray, int]:
         raise MonteCarloError("this SciPy does not expose the Sobol direction numbers (Sobol._sv/_shift)") from exc
     if sv.shape != (n_dims, bits) or bits > 31:
         raise MonteCarloError(f"unexpected Sobol table shape {sv.shape} / bits {bits}")
-    return gray_to_natural(sv, bits), shift.astype(np.uint32), bits
+    table, shift32 = gray_to_natural(sv, bits), shift.astype(np.uint32)
+    _self_test(table, shift32, bits, n_dims, seed)
+    return table, shift32, bits
+
+
+_VERIFIED_SCIPY: "set[str]" = set()
+
+
+def _self_test(table: np.ndarray, shift: np.ndarray, bits: int, n_dims: int, seed) -> None:
+    """``Sobol._sv`` / ``._shift`` are private: the first table built under a given SciPy version is checked against the
+    public API - the first 64 points regenerated from the table must equal ``Sobol(...).random(64)`` bit for bit - so
+    that a SciPy that changes its internals makes ``MCMethod.QMC`` fail loudly instead of pricing another point set."""
+    import scipy
+
+    if scipy.__version__ in _VERIFIED_SCIPY or not isinstance(seed, (int, np.integer)):
+        return  # (a Generator / None seed cannot rebuild the same scramble twice: checked on the next integer seed)
+    import warnings
+
+    from scipy.stats.qmc import Sobol
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = Sobol(d=int(n_dims), scramble=True, seed=seed).random(64)
+    got = points_from_table(table, shift, 0, 64).astype(np.float64) * 2.0 ** -bits
+    if not np.array_equal(got, want):
+        raise MonteCarloError(f"SciPy {scipy.__version__}: the Sobol points rebuilt from Sobol._sv/_shift differ from Sobol.random(); "
+                              "the QMC backend does not know this SciPy's generator layout")
+    _VERIFIED_SCIPY.add(scipy.__version__)
 
 
 def gray_to_natural(sv: np.ndarray, bits: int) -> np.ndarray:

@@ -100,3 +100,47 @@ def test_header_is_plain_c_and_a_c_client_links():
                         f"-Wl,-rpath,{libdir}"], check=True)
         out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
         assert out == [str(_ffi.ABI_VERSION), "65"]
+
+
+@pytest.mark.gpu
+def test_c_client_prices_through_the_c_abi_bit_for_bit(tmp_path):
+    """a call THROUGH the boundary from C.  tests/c_client/price_client.c does b200mc_create ->
+    b200mc_simulate (one option / three CRN scenarios, then a five-option barrier batch) -> b200mc_destroy and prints the
+    moments as exact hexadecimal doubles; the Python pricer path (ctypes onto the same entry points) must return the
+    same bits, and the delta the C client's moments imply equals MonteCarloPricerUni.delta_gamma at the default bump."""
+    import shutil
+    import subprocess
+
+    import numpy as np
+
+    import optionslab_b200 as ob
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "price_client")
+    libdir = os.path.dirname(_ffi.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_client", "price_client.c"), "-o", exe, "-L", libdir, "-l:libb200mc.so", f"-Wl,-rpath,{libdir}"],
+                   check=True)
+    lines = subprocess.run([exe, "0"], check=True, capture_output=True, text=True).stdout.splitlines()
+    rows = {(f[0], int(f[1])): tuple(float.fromhex(x) for x in f[2:5]) for f in (ln.split() for ln in lines) if f[0] in ("european", "barrier")}
+    assert len(rows) == 8
+    eng = _ffi.get_engine(0)
+    h = 1e-4
+    params = np.stack([_ffi.make_params(100.0 + b, 100.0, 1.0, 0.05, 0.2, 0.01) for b in (h, 0.0, -h)]).reshape(1, 3)
+    m = eng.simulate(_ffi.make_spec(_ffi.EUROPEAN, 50, antithetic=True), params, 42, 100_000)[0]
+    for i in range(3):
+        assert rows[("european", i)] == (m["sum"][i], m["sum_sq"][i], m["n"][i])
+    K = 90.0 + 5.0 * np.arange(5)
+    mb = eng.simulate(_ffi.make_spec(_ffi.BARRIER, 64), _ffi.make_params(100.0, K, 0.5, 0.03, 0.25, 0.0, 125.0).reshape(5, 1), 7, 200_001,
+                      stream_base=3, path_begin=1000)[:, 0]
+    for i in range(5):
+        assert rows[("barrier", i)] == (mb["sum"][i], mb["sum_sq"][i], mb["n"][i])
+    disc = float(np.exp(-0.05))
+    up, down = (disc * rows[("european", i)][0] / rows[("european", i)][2] for i in (0, 2))
+    delta, _ = ob.MonteCarloPricerUni(100_000, 50, seed=1).delta_gamma(100.0, 100.0, 1.0, 0.05, 0.2, "call", q=0.01, seed=42)
+    assert (up - down) / (2 * h) == delta
+    invalid = [ln for ln in lines if ln.startswith("invalid")][0]
+    assert invalid.startswith("invalid -1 ") and "n_steps" in invalid
+    assert [ln for ln in lines if ln.startswith("launches")] == ["launches 2"]
