@@ -50,6 +50,9 @@ def main():
     import torch
     import torch.distributed as dist
 
+    sys.stdout.flush()
+    real_stdout = os.dup(1)  # NCCL prints its version banner on fd 1: park stdout on stderr until the JSON line
+    os.dup2(2, 1)
     ctx = distributed.init(backend="nccl")
     fused_ok = ctx.fused
     a = prices()
@@ -80,8 +83,8 @@ def main():
         # (rank order in the kernel, NCCL's tree) are amplified by 1/h^2 = 1e8 there - compare the delta only
         a["delta_gamma"], b["delta_gamma"] = a["delta_gamma"][:1], b["delta_gamma"][:1]
         agree = {k: close(a[k], b[k]) for k in a}
-        print(json.dumps({"world": ctx.world_size, "fused_connected": fused_ok, "identical_on_all_ranks": same_on_all_ranks,
-                          "fused_equals_nccl": agree, "latency": lat, "prices": a}))
+        os.write(real_stdout, (json.dumps({"world": ctx.world_size, "fused_connected": fused_ok, "identical_on_all_ranks": same_on_all_ranks,
+                          "fused_equals_nccl": agree, "latency": lat, "prices": a}) + "\n").encode())
     distributed.shutdown()
 
 
