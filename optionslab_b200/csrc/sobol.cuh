@@ -59,15 +59,16 @@ struct SobolArgs {
 //   tools/fit_inverse_normal.py (max abs error of the FP32 Horner form: 1.3e-6, at |z| = 6).  2 MUFU + 15 FFMA.
 //   A piecewise central/tail form (Giles) is more accurate in relative terms near z = 0 but its tail branch
 //   diverges in 19% of the warps: measured 25% slower (profiles/r01_variants13_inverse_normal.txt).
-// xs = the Sobol integer shifted so that its top bit sits at bit 31 (u = xs * 2^-32; the table is staged top-aligned, so
-// the shift is free).  t = min(u, 1 - u) clipped to [1e-10, 1/2] (gbm_qmc.py:36), y = sqrt(-2 ln t) and the half u falls in.
-// (A branch-free fold (xs ^ m) + (xs >> 31) with the sign applied by one LOP3 was measured 4% SLOWER at 2^24 points than
-// this compare-select form; written as (xs ^ m) - m the compiler emits IABS + a signed conversion, 3% faster but wrong for
-// u = 1/2 exactly.)
+// xs = the Sobol integer scaled to 31 bits (u = xs * 2^-31; the table is staged pre-shifted, so the scaling is free).
+// t = min(u, 1 - u) clipped to [1e-10, 1/2] (gbm_qmc.py:36), y = sqrt(-2 ln t) and the half u falls in.
+// 31 bits, not 32, on purpose: with u on the full word 1 - u is a negation, min(u, 1 - u) an absolute value, and the compiler
+// emits IABS + a SIGNED int-to-float conversion - wrong for the one value 2^31 (u = 1/2 exactly: it becomes -2^31 and the clip
+// turns it into 1e-10).  (A branch-free fold with the sign applied by one LOP3 was measured 4% slower than compare-select.)
+constexpr uint32_t kSobolOne = 0x80000000u;  // 1.0 on the 31-bit scale
 __device__ __forceinline__ float inverse_normal_radius(uint32_t xs, bool& lower) {
-  const uint32_t xr = 0u - xs;  // 2^32 - xs: exactly 1 - u
-  lower = (int32_t)xs >= 0;     // u < 1/2
-  const float t = fmaxf(__uint2float_rn(lower ? xs : xr) * 2.3283064365386963e-10f, 1e-10f);
+  const uint32_t xr = kSobolOne - xs;
+  lower = xs < xr;  // u < 1/2
+  const float t = fmaxf(__uint2float_rn(lower ? xs : xr) * 4.6566128730773926e-10f, 1e-10f);
   return mufu_sqrt(mufu_lg2(t) * -1.38629436111989061883f);  // sqrt(-2 ln t)
 }
 
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kBlock, NS <= 2 ? 4 : 2) qmc_european_kernel(c
   uint32_t tid_mask[kSobolTidBits];
 #pragma unroll
   for (int b = 0; b < kSobolTidBits; ++b) tid_mask[b] = 0u - ((threadIdx.x >> b) & 1u);
-  const uint32_t up = 32u - a.bits;  // the table is staged top-aligned: integers x << up, u = (x << up) * 2^-32
+  const uint32_t up = 31u - a.bits;  // the table is staged pre-shifted: integers x << up, u = (x << up) * 2^-31
 
   float W[kPoints];
 #pragma unroll
@@ -266,7 +267,7 @@ __global__ void sobol_points_kernel(const uint32_t* __restrict__ dirnums, const 
 // Inspection: the FP32 normals the QMC kernel derives from given Sobol integers.
 __global__ void sobol_normals_kernel(const uint32_t* __restrict__ x, uint64_t n, uint32_t bits, float* __restrict__ out) {
   for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (uint64_t)gridDim.x * blockDim.x)
-    out[idx] = inverse_normal_from_sobol(x[idx] << (32u - bits));
+    out[idx] = inverse_normal_from_sobol(x[idx] << (31u - bits));
 }
 
 }  // namespace b200mc
