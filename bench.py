@@ -218,6 +218,17 @@ def reference_extras(ref):
     return out
 
 
+def _host_versions():
+    out = {"cpu_count": os.cpu_count(), "numpy": np.__version__}
+    try:
+        import numba
+
+        out["numba"], out["numba_threads"] = numba.__version__, int(numba.get_num_threads())
+    except Exception:
+        out["numba"] = None
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -267,7 +278,7 @@ def run_reference_arm(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "reference_other_backends": extras}
+            "gpu_launches": 0, "reference_other_backends": extras, "host": _host_versions()}
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     os.close(real_stdout)

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200MC_ABI_VERSION 8
+#define B200MC_ABI_VERSION 9
 #define B200MC_MAX_SCENARIOS 16
 
 typedef struct b200mc_engine b200mc_engine_t;
@@ -199,6 +199,8 @@ int b200mc_comm_connect(b200mc_engine_t* eng, int rank, int world, const void* h
 int b200mc_comm_connect_local(b200mc_engine_t* const* engines, int n);
 int b200mc_comm_disconnect(b200mc_engine_t* eng);
 int b200mc_comm_world(const b200mc_engine_t* eng);
+/* Bound on the in-kernel wait for a peer rank's records (default 20 000 ms); a launch that exceeds it returns B200MC_ERR_COMM. */
+int b200mc_comm_set_timeout_ms(b200mc_engine_t* eng, uint32_t milliseconds);
 int b200mc_simulate_allreduce(b200mc_engine_t* eng, const b200mc_spec_t* spec, const b200mc_params_t* params_host,
                               uint32_t n_opt, uint32_t n_scen, uint64_t seed, uint32_t stream_base,
                               uint64_t path_begin, uint64_t n_paths, b200mc_moments_t* out_host);
@@ -351,6 +353,11 @@ uint64_t b200mc_kernel_launches(const b200mc_engine_t* eng);
  * adjacent lanes share each European path (0..3; < 0 = automatic); paths_per_thread: 1..32 (0 = automatic).  Prices do not
  * depend on the shape beyond FP32 summation order (~1e-7 relative). */
 int b200mc_set_plan(b200mc_engine_t* eng, int split_shift, uint32_t paths_per_thread);
+/* The tile shape the planner gives a fused launch on a device of `sm_count` SMs - a pure function of its arguments (no engine,
+ * no device: the host logic is testable without a GPU).  A tile = one CTA of 256 threads; a thread owns paths_per_thread paths,
+ * or 2^split_shift adjacent lanes share each path (European launches that would leave most SMs idle). */
+int b200mc_plan_tiles(int sm_count, const b200mc_spec_t* spec, uint32_t n_opt, uint32_t n_scen, uint64_t n_paths,
+                      int control_variate, uint32_t* tiles, uint32_t* paths_per_thread, uint32_t* split_shift);
 /* The tile shape of the most recent b200mc_simulate* launch: tiles per option, paths per thread, split shift. */
 int b200mc_last_plan(b200mc_engine_t* eng, uint32_t* tiles, uint32_t* paths_per_thread, uint32_t* split_shift);
 /* When enabled, every simulation / from-normals kernel is bracketed by a CUDA event pair on the

@@ -18,7 +18,7 @@ from .exceptions import AccelerationError, MonteCarloError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200mc.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_SCENARIOS = 16
 
 EUROPEAN, ASIAN_ARITH, ASIAN_GEOM, BARRIER, LOOKBACK, CLIQUET, AUTOCALLABLE = range(7)
@@ -84,6 +84,7 @@ SIGNATURES = {
     "b200mc_comm_connect_local": (C.c_int, [C.POINTER(_P), C.c_int]),
     "b200mc_comm_disconnect": (C.c_int, [_P]),
     "b200mc_comm_world": (C.c_int, [_P]),
+    "b200mc_comm_set_timeout_ms": (C.c_int, [_P, C.c_uint32]),
     "b200mc_simulate_control_variate": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
                                                   C.c_uint64, C.c_uint64, _P]),
     "b200mc_simulate_structured": (C.c_int, [_P, C.POINTER(Spec), C.POINTER(Product), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
@@ -107,6 +108,8 @@ SIGNATURES = {
     "b200mc_measure_peaks": (C.c_int, [_P, C.POINTER(Peaks)]),
     "b200mc_kernel_launches": (C.c_uint64, [_P]),
     "b200mc_set_plan": (C.c_int, [_P, C.c_int, C.c_uint32]),
+    "b200mc_plan_tiles": (C.c_int, [C.c_int, C.POINTER(Spec), C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(C.c_uint32),
+                                    C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "b200mc_last_plan": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "b200mc_set_kernel_timing": (C.c_int, [_P, C.c_int]),
     "b200mc_kernel_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
@@ -292,6 +295,9 @@ class Engine:
 
     def comm_disconnect(self):
         self._check(self._lib.b200mc_comm_disconnect(self._h), "b200mc_comm_disconnect")
+
+    def comm_set_timeout_ms(self, milliseconds: int):
+        self._check(self._lib.b200mc_comm_set_timeout_ms(self._h, int(milliseconds)), "b200mc_comm_set_timeout_ms")
 
     def comm_world(self) -> int:
         return int(self._lib.b200mc_comm_world(self._h))
@@ -493,6 +499,16 @@ class Engine:
         out = np.empty((ck.shape[0], 4), dtype=np.uint32)
         self._check(self._lib.b200mc_philox_raw(self._h, ck.ctypes.data, ck.shape[0], out.ctypes.data), "b200mc_philox_raw")
         return out
+
+
+def plan_tiles(spec: Spec, n_opt: int, n_scen: int, n_paths: int, *, sm_count: int = 148, control_variate: bool = False) -> dict:
+    """The planner's tile shape for a fused launch (pure host function of the library; needs no device)."""
+    t, p, sft = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    rc = load_library().b200mc_plan_tiles(int(sm_count), C.byref(spec), int(n_opt), int(n_scen), int(n_paths), int(bool(control_variate)),
+                                          C.byref(t), C.byref(p), C.byref(sft))
+    if rc != 0:
+        raise MonteCarloError("b200mc_plan_tiles: bad argument")
+    return {"tiles": int(t.value), "paths_per_thread": int(p.value), "split_shift": int(sft.value)}
 
 
 def connect_local(engines) -> None:

@@ -62,6 +62,7 @@ struct b200mc_engine {
     char* peer[kMaxRanks] = {};       // peer[rank] == block
     bool ipc_opened[kMaxRanks] = {};  // peers mapped with cudaIpcOpenMemHandle (to be closed)
     unsigned long long epoch = 0;
+    unsigned long long timeout_ns = kXchgTimeoutNs;
     uint32_t* launch_ticket = nullptr;
   } comm;
   int plan_split_shift = -1;  // b200mc_set_plan: -1 / 0 = automatic
@@ -185,11 +186,11 @@ struct TilePlan {
   uint32_t tiles = 1, ppt = 1, split_shift = 0;
 };
 
-TilePlan plan_tiles(const b200mc_engine* e, uint32_t n_opt, uint64_t n_paths, uint32_t n_steps, uint32_t ns, bool path_dependent,
-                    bool may_split = false) {
+TilePlan plan_tiles(int sm_count, int pin_split_shift, uint32_t pin_ppt, uint32_t n_opt, uint64_t n_paths, uint32_t n_steps, uint32_t ns,
+                    bool path_dependent, bool may_split) {
   const int resident = ns <= 2 ? 6 : ns == 4 ? 3 : 2;    // CTAs per SM the register budgets below allow
   constexpr double kSaturatingCtas = 3.0;
-  const double n_sm = (double)e->prop.multiProcessorCount;
+  const double n_sm = (double)sm_count;
   // issued instructions per path: step loop (+ per-scenario state updates of the path-dependent kinds) + payoff epilogue
   const double per_path_loop = (11.0 + (path_dependent ? 3.5 * ns : 0.0)) * n_steps;
   const double per_path_payoff = 14.0 * ns;
@@ -209,17 +210,17 @@ TilePlan plan_tiles(const b200mc_engine* e, uint32_t n_opt, uint64_t n_paths, ui
   uint32_t max_shift = 0;
   if (may_split)
     while ((1u << (max_shift + 1)) <= (uint32_t)kMaxSplit && calls >= (4u << max_shift)) ++max_shift;  // >= 2 calls per lane
-  const uint32_t lo = e->plan_split_shift >= 0 ? std::min<uint32_t>((uint32_t)e->plan_split_shift, max_shift) : auto_shift;
+  const uint32_t lo = pin_split_shift >= 0 ? std::min<uint32_t>((uint32_t)pin_split_shift, max_shift) : auto_shift;
   const uint32_t hi = lo;
   for (uint32_t shift = lo; shift <= hi; ++shift) {
     const uint32_t lanes = 1u << shift;
     const uint64_t per_pass = (uint64_t)kBlock >> shift;
     const double per_path = per_path_loop / lanes + per_path_payoff + 8.0 * shift;  // + the butterfly
     for (uint32_t p = 1; p <= (uint32_t)kMaxPathsPerThread; ++p) {
-      if (e->plan_ppt && p != e->plan_ppt) continue;
+      if (pin_ppt && p != pin_ppt) continue;
       const uint64_t t = (n_paths + per_pass * p - 1) / (per_pass * p);
       const uint64_t p_even = (n_paths + per_pass * t - 1) / (per_pass * t);  // spread evenly over t tiles
-      if (p_even != p && !e->plan_ppt) continue;                              // same tiling as a smaller p
+      if (p_even != p && !pin_ppt) continue;                                  // same tiling as a smaller p
       const double ctas = (double)t * n_opt;
       const double per_sm = std::ceil(ctas / n_sm);
       const double concurrency = std::min(per_sm, (double)resident);
@@ -229,6 +230,11 @@ TilePlan plan_tiles(const b200mc_engine* e, uint32_t n_opt, uint64_t n_paths, ui
     }
   }
   return plan;
+}
+
+TilePlan plan_tiles(const b200mc_engine* e, uint32_t n_opt, uint64_t n_paths, uint32_t n_steps, uint32_t ns, bool path_dependent,
+                    bool may_split = false) {
+  return plan_tiles(e->prop.multiProcessorCount, e->plan_split_shift, e->plan_ppt, n_opt, n_paths, n_steps, ns, path_dependent, may_split);
 }
 
 // __launch_bounds__ minBlocksPerSM per kernel family, picked from measurements on B200
@@ -364,6 +370,7 @@ int enqueue_simulation(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc
     a.fold.x.slot_bytes = kXchgSlotBytes;
     a.fold.x.launch_ticket = e->comm.launch_ticket;
     a.fold.x.timed_out = (unsigned int*)(e->mapped_dev + kMappedTimeoutOffset);
+    a.fold.x.timeout_ns = e->comm.timeout_ns;
   }
   a.path_begin = path_begin;
   a.n_paths = n_paths;
@@ -745,6 +752,13 @@ int b200mc_comm_disconnect(b200mc_engine_t* e) {
 }
 
 int b200mc_comm_world(const b200mc_engine_t* e) { return e ? e->comm.world : 0; }
+
+int b200mc_comm_set_timeout_ms(b200mc_engine_t* e, uint32_t milliseconds) {
+  if (!e || milliseconds == 0) return fail(e, B200MC_ERR_INVALID, "timeout must be >= 1 ms");
+  std::lock_guard<std::mutex> g(e->mutex);
+  e->comm.timeout_ns = (unsigned long long)milliseconds * 1000000ull;
+  return 0;
+}
 
 int b200mc_simulate_control_variate(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc_params_t* params_host,
                                     uint32_t n_opt, uint32_t n_scen, uint64_t seed, uint32_t stream_base, uint64_t path_begin,
@@ -1331,6 +1345,17 @@ int b200mc_set_plan(b200mc_engine_t* e, int split_shift, uint32_t paths_per_thre
   if (split_shift > 3 || paths_per_thread > (uint32_t)kMaxPathsPerThread) return fail(e, B200MC_ERR_INVALID, "split_shift must be <= 3, paths_per_thread <= %d", kMaxPathsPerThread);
   e->plan_split_shift = split_shift < 0 ? -1 : split_shift;
   e->plan_ppt = paths_per_thread;
+  return 0;
+}
+
+int b200mc_plan_tiles(int sm_count, const b200mc_spec_t* spec, uint32_t n_opt, uint32_t n_scen, uint64_t n_paths, int control_variate,
+                      uint32_t* tiles, uint32_t* paths_per_thread, uint32_t* split_shift) {
+  if (!spec || !tiles || !paths_per_thread || !split_shift || sm_count < 1 || n_opt == 0 || n_paths == 0 || n_scen == 0 ||
+      n_scen > B200MC_MAX_SCENARIOS || spec->n_steps == 0)
+    return B200MC_ERR_INVALID;
+  const bool european = spec->kind == B200MC_EUROPEAN;
+  const TilePlan plan = plan_tiles(sm_count, -1, 0, n_opt, n_paths, spec->n_steps, pad_scenarios(n_scen), !european, european && !control_variate);
+  *tiles = plan.tiles, *paths_per_thread = plan.ppt, *split_shift = plan.split_shift;
   return 0;
 }
 

@@ -55,9 +55,10 @@ struct XchgArgs {
   char* peer[kMaxRanks];      // exchange blocks by rank; peer[rank] is this rank's own
   size_t slot_bytes;
   uint32_t* launch_ticket;    // options of this launch whose records are complete; zero between launches
-  unsigned int* timed_out;    // mapped host word, set to 1 if a peer's flag did not arrive within kXchgTimeoutNs
+  unsigned int* timed_out;    // mapped host word, set to 1 if a peer's flag did not arrive within timeout_ns
+  unsigned long long timeout_ns;
 };
-constexpr unsigned long long kXchgTimeoutNs = 20ull * 1000 * 1000 * 1000;
+constexpr unsigned long long kXchgTimeoutNs = 20ull * 1000 * 1000 * 1000;  // default bound on the wait for a peer
 
 // Where a launch's results go.
 struct FoldArgs {
@@ -393,7 +394,7 @@ __device__ __forceinline__ void finish_tile(const float (&acc)[NM * NS], const u
       do {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      } while (seen != f.x.epoch && t1 - t0 < kXchgTimeoutNs);
+      } while (seen != f.x.epoch && t1 - t0 < f.x.timeout_ns);
       if (seen != f.x.epoch) *reinterpret_cast<volatile unsigned int*>(f.x.timed_out) = 1u;
     }
     __syncthreads();

@@ -125,6 +125,34 @@ def test_fused_allreduce_between_two_engines_of_one_device():
         a.close(), b.close()
 
 
+def test_a_missing_peer_is_an_error_not_a_hang():
+    """Failure detection of the in-kernel exchange: if a connected rank never launches, the waiting kernel gives up after the
+    configured bound and the call fails with AccelerationError(backend="nvlink") (B200MC_ERR_COMM); the engine refuses further
+    exchanges until the communicator is rebuilt, after which everything works again."""
+    import time
+
+    import optionslab_b200 as ob
+    from optionslab_b200 import _ffi
+
+    a, b = _ffi.Engine(0), _ffi.Engine(0)
+    try:
+        _ffi.connect_local([a, b])
+        a.comm_set_timeout_ms(150)
+        spec = _ffi.make_spec(_ffi.EUROPEAN, 16, antithetic=True)
+        params = _ffi.make_params(**P).reshape(1, 1)
+        t0 = time.perf_counter()
+        with pytest.raises(ob.AccelerationError, match="timed out"):
+            a.simulate(spec, params, 3, 10_000, allreduce=True)  # rank 1 (engine b) never shows up
+        assert 0.1 < time.perf_counter() - t0 < 5.0
+        with pytest.raises(ob.AccelerationError, match="reconnect"):
+            a.simulate(spec, params, 3, 10_000, allreduce=True)
+        _ffi.connect_local([a, b])  # rebuild: flags, epochs and the time-out word start over
+        got = _fused_pair([a, b], spec, params, 3, 20_000, 10_000)
+        assert got[0].tobytes() == got[1].tobytes() and got[0]["n"][0, 0] == 40_000
+    finally:
+        a.close(), b.close()
+
+
 def test_local_devices_mode_on_two_gpus():
     """One process driving two GPUs from threads (distributed.local_devices): same global paths; the GBM launches add
     up their records in the kernel tail over peer memory, the other model families on the host."""

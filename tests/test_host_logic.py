@@ -225,3 +225,34 @@ def test_monte_carlo_convergence_study_contract():
     grow = iter([0.0, 1.0] * 2 + [0.0, 10.0] * 6)
     assert ob.monte_carlo_convergence_test(lambda n: next(grow), n_trials=4, base_sims=10)["converging"] is False
     assert ob.monte_carlo_convergence_test(lambda n: 1.0, n_trials=3, base_sims=10)["converging"] is True
+
+
+# ---- the launch planner (a pure host function of the library: b200mc_plan_tiles) --------------------------------------
+def test_tile_plans_cover_the_paths_and_follow_the_measured_rules():
+    from optionslab_b200 import _ffi
+
+    euro = _ffi.make_spec(_ffi.EUROPEAN, 252, antithetic=True)
+    asian = _ffi.make_spec(_ffi.ASIAN_ARITH, 252)
+    for spec, n_opt, n_scen, n_paths in [(euro, 1, 1, 1), (euro, 1, 1, 257), (euro, 1, 1, 10_000), (euro, 1, 1, 100_000), (euro, 1, 14, 1_000_000),
+                                         (euro, 4096, 1, 1_000_000), (euro, 4096, 3, 100_000), (asian, 1, 1, 4_000_000), (asian, 1, 14, 200_000),
+                                         (_ffi.make_spec(_ffi.BARRIER, 365), 1, 1, 16_000_000), (euro, 1, 1, 2**33)]:
+        plan = _ffi.plan_tiles(spec, n_opt, n_scen, n_paths)
+        per_tile = (256 >> plan["split_shift"]) * plan["paths_per_thread"]
+        assert 1 <= plan["paths_per_thread"] <= 32 and 0 <= plan["split_shift"] <= 3
+        assert plan["tiles"] * per_tile >= n_paths > (plan["tiles"] - 1) * per_tile          # every path in exactly one tile, no empty tile
+        assert plan == _ffi.plan_tiles(spec, n_opt, n_scen, n_paths)                           # a pure function: same call, same shape
+        if spec.kind != _ffi.EUROPEAN:
+            assert plan["split_shift"] == 0                                                    # path-dependent state: one thread per path
+    # lane split only while one thread per path leaves most SMs without a CTA (profiles/r02_plan_sweep.jsonl)
+    assert _ffi.plan_tiles(euro, 1, 1, 10_000)["split_shift"] >= 1
+    assert _ffi.plan_tiles(euro, 1, 1, 1_000)["split_shift"] == 3
+    assert _ffi.plan_tiles(euro, 1, 1, 30_000)["split_shift"] == 0 and _ffi.plan_tiles(euro, 1, 1, 100_000)["split_shift"] == 0
+    assert _ffi.plan_tiles(euro, 64, 1, 1_000)["split_shift"] == 0                             # 64 options fill the chip by themselves
+    assert _ffi.plan_tiles(euro, 1, 1, 10_000, control_variate=True)["split_shift"] == 0       # the control-variate kernel has no split form
+    assert _ffi.plan_tiles(_ffi.make_spec(_ffi.EUROPEAN, 8, antithetic=True), 1, 1, 1_000)["split_shift"] == 0  # one Philox call: nothing to split
+    # large grids amortise the per-CTA work over many paths per thread; the shape scales with the SM count
+    assert _ffi.plan_tiles(euro, 4096, 1, 1_000_000)["paths_per_thread"] >= 16
+    small, big = _ffi.plan_tiles(euro, 1, 1, 4_000, sm_count=16), _ffi.plan_tiles(euro, 1, 1, 4_000, sm_count=148)
+    assert small["split_shift"] <= big["split_shift"]
+    with pytest.raises(Exception):
+        _ffi.plan_tiles(euro, 1, 17, 1000)
