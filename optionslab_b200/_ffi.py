@@ -17,7 +17,7 @@ import numpy as np
 from .exceptions import AccelerationError, MonteCarloError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200mc.so")
+LIB_PATH = os.environ.get("B200MC_LIB") or os.path.join(_HERE, "libb200mc.so")  # B200MC_LIB: another build of the SAME library (A/B timing)
 ABI_VERSION = 9
 MAX_SCENARIOS = 16
 
