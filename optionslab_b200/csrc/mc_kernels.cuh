@@ -142,8 +142,12 @@ __device__ __forceinline__ Coef scen_coef(const SimArgs& a, uint32_t opt, uint32
   return q;
 }
 
+// max(+-(e - kappa), 0) with the option type as DATA (a sign), not as a branch: is_put is a launch argument, and written as
+// is_put ? max(kappa - e, 0) : max(e - kappa, 0) the compiler evaluates both sides and selects - 2 FADD + 2 FMNMX + a select
+// per sample, a quarter of the multi-scenario epilogue.  fma(+-1, e, -+kappa) rounds once, exactly like the subtraction.
 __device__ __forceinline__ float vanilla(float e, float kappa, bool is_put) {
-  return is_put ? fmaxf(kappa - e, 0.0f) : fmaxf(e - kappa, 0.0f);
+  const float s = is_put ? -1.0f : 1.0f;
+  return fmaxf(fmaf(s, e, -s * kappa), 0.0f);
 }
 
 // ---- per-sample accumulation ------------------------------------------------------------------------
