@@ -12,7 +12,7 @@ out = {"lib": os.path.basename(_ffi.LIB_PATH)}
 for n_scen, n_paths in ((14, 1_000_000), (8, 1_000_000), (3, 1_000_000), (14, 100_000)):
     params = np.stack([_ffi.make_params(**dict(P, sigma=0.2 + 0.001 * k)) for k in range(n_scen)]).reshape(1, n_scen)
     row = {}
-    for ppt in (0, 1, 2, 3, 4, 5, 6, 8):
+    for ppt in (0, 1, 2, 3, 4, 6, 8, 9, 14):
         eng.set_plan(0, ppt)
         eng.simulate(spec, params, 42, n_paths)
         eng.set_kernel_timing(True)
