@@ -470,6 +470,13 @@ __device__ __forceinline__ void consume_call(const u32x4& x, F&& f) {
 template <int UNROLL = 1, bool SQUARED = false, class F>
 __device__ __forceinline__ void for_each_pair(uint64_t path, uint32_t n_steps, uint32_t stream, const PhiloxKeys& rk, F&& f,
                                               uint32_t j0 = 0u, uint32_t j1 = 0xffffffffu) {
+  if (n_steps == 1u) {  // single-step paths: one 64-bit draw (normal.cuh, box_muller_single)
+    if (j0 == 0u) {
+      const u32x4 x = draw4(path, 0u, stream, rk);
+      f(box_muller_single<SQUARED>(x.x, x.y), 1);
+    }
+    return;
+  }
   const uint32_t full = n_steps >> 3;
   const uint32_t stop = j1 < full ? j1 : full;
   uint32_t j = j0;

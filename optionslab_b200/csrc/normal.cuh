@@ -27,6 +27,14 @@
 //           -- both fail a Kolmogorov-Smirnov test at 1e7 draws; this layout passes at 3e7,
 //           tests/test_philox_oracle.py, and a 1e10-draw binned chi-square on the device, tests/test_gpu_rng.py).
 //   z_cos = kRadScale*rad*cos(theta), z_sin = kRadScale*rad*sin(theta)
+//
+// Single-step paths (n_steps == 1: the reference's DEFAULT, monte_carlo.py:59, gbm_numpy.py:56-83) are the one place where an
+// option's value is a direct functional of ONE draw's tail, and the one place where a draw is not on the hot loop.  Their
+// single normal therefore spends 64 bits (box_muller_single): the radius takes the WHOLE first word of the path's stream,
+// u = (w0 + 1) * 2^-32 in (0, 1] (FP32 conversion: 24 significant bits, i.e. full relative resolution where u is small - the
+// tail - and a 2^-24 grid near 1), cap sqrt(64 ln 2) = 6.66 sigma; the angle takes the top 23 bits of the second word.
+// P(z > 5) is then exact to the sampling error at 2^32 draws instead of 3.7% thin.  Every other step count keeps the
+// 32-bit-per-pair layout above (a sum of >= 2 draws no longer sees a single draw's far tail).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -79,6 +87,22 @@ __device__ __forceinline__ NormalPair box_muller(uint32_t w) {
   const float u = 2.0f - __uint_as_float((w >> 9) | 0x3f800000u);
   p.rad = SQUARED ? -mufu_lg2(u) : mufu_sqrt(-mufu_lg2(u));
   const float turns = __uint_as_float((__byte_perm(w, 0u, 0x0123) >> 9) | 0x3f800000u);
+  const float theta = fmaf(turns, kTwoPi, kMinusThreePi);
+  p.cs = mufu_cos(theta);
+  p.sn = mufu_sin(theta);
+  return p;
+}
+
+// The one normal of a single-step path from the first two words of its stream (see the header).  rad is divided by the
+// 2^23-grid normalisation the kernels fold into their diffusion coefficient (this grid needs none: E[-2 ln u] = 2 to 1e-8).
+template <bool SQUARED = false>
+__device__ __forceinline__ NormalPair box_muller_single(uint32_t w0, uint32_t w1) {
+  NormalPair p;
+  const float u = fmaf(__uint2float_rn(w0), 2.3283064365386963e-10f, 2.3283064365386963e-10f);  // (w0 + 1) / 2^32, <= 1
+  const float r2 = -mufu_lg2(u);
+  constexpr float kInvNorm = (float)(1.0 / kRadNormD), kInvNorm2 = (float)(1.0 / (kRadNormD * kRadNormD));
+  p.rad = SQUARED ? r2 * kInvNorm2 : mufu_sqrt(r2) * kInvNorm;
+  const float turns = __uint_as_float((w1 >> 9) | 0x3f800000u);
   const float theta = fmaf(turns, kTwoPi, kMinusThreePi);
   p.cs = mufu_cos(theta);
   p.sn = mufu_sin(theta);

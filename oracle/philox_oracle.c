@@ -60,9 +60,21 @@ static void pair_to_normals(uint32_t w, double* z_cos, double* z_sin) {
   *z_sin = radius * sin(theta);
 }
 
+/* The ONE normal of a single-step path (normal.cuh, box_muller_single): radius from the whole first word,
+ * u = (w0 + 1) * 2^-32 evaluated as the device does (FP32 conversion of w0, one FP32 fma), angle from the top 23 bits of
+ * the second word; no grid normalisation. */
+static double single_step_normal(uint32_t w0, uint32_t w1) {
+  const float two_pi_f = 6.28318530717958647692f;
+  const float minus_three_pi_f = -9.42477796076937971538f;
+  float fu = fmaf((float)w0, 0x1p-32f, 0x1p-32f);
+  double theta = mantissa_to_1_2(w1 >> 9) * (double)two_pi_f + (double)minus_three_pi_f;
+  return sqrt(-2.0 * log((double)fu)) * cos(theta);
+}
+
 /* out[(p - path_begin) * n_steps + s] = normal for step s of global path p.
  * Word stream of a path: Philox outputs of counters (path_lo, j, path_hi, stream), j = 0,1,2,...
- * Word n = 4j + i -> steps 2n (cos) and 2n+1 (sin)  (see optionslab_b200/csrc/normal.cuh). */
+ * Word n = 4j + i -> steps 2n (cos) and 2n+1 (sin)  (see optionslab_b200/csrc/normal.cuh); n_steps == 1: words 0 and 1 make
+ * the path's one normal. */
 void b200mc_oracle_normals(uint64_t seed, uint32_t stream, uint64_t path_begin, uint64_t n_paths,
                            uint32_t n_steps, double* out) {
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
@@ -74,6 +86,10 @@ void b200mc_oracle_normals(uint64_t seed, uint32_t stream, uint64_t path_begin, 
     for (uint32_t j = 0; j < n_calls; ++j) {
       uint32_t ctr[4] = {(uint32_t)p, j, (uint32_t)(p >> 32), stream};
       philox4x32_10(ctr, key, w + 4u * j);
+    }
+    if (n_steps == 1u) {
+      out[i] = single_step_normal(w[0], w[1]);
+      continue;
     }
     for (uint32_t n = 0; n < n_pairs; ++n) {
       double z[2];

@@ -131,16 +131,29 @@ def test_joint_law_of_the_two_normals_of_one_word(engine):
 
 def test_single_step_strike_sweep_at_2_to_the_32_samples(engine):
     """The reference's default is ONE exact step (monte_carlo.py:59): the price of an out-of-the-money option is then a direct
-    functional of a single draw's tail.  Strikes S*exp(k sigma sqrt(T)), k = -5 .. 5 in steps of 1/4, 2^32 samples each:
-    within 4 standard errors of Black-Scholes for |k| <= 4.25; further out the 2^23-point radius grid under-weights the tail
-    by a known amount (call struck 4.5 sigma out: -1.2%, 5 sigma out: -7.8% of a price of 6e-6 on a spot of 100), which the
-    bound allows for."""
+    functional of a single draw's tail.  Strikes S*exp(k sigma sqrt(T)), k = -5 .. 5 in steps of 1/4, 2^32 samples each: within
+    4 standard errors of Black-Scholes everywhere - single-step paths draw their one normal from 64 bits (normal.cuh,
+    box_muller_single); with the 32-bit-per-pair layout of the multi-step streams the +-5 sigma strikes came out 11-21% low."""
     from tools import rng_evidence as ev
 
     rows = ev.strike_sweep(engine)
     assert len(rows) >= 41
     for r in rows:
-        k = abs(r["k_sigma"])
-        grid_deficit = 0.0 if k <= 4.25 else 0.02 if k <= 4.5 else 0.05 if k <= 4.75 else 0.10
-        assert abs(r["price"] - r["bs"]) <= 4 * r["std_error"] + grid_deficit * r["bs"], r
+        assert abs(r["price"] - r["bs"]) <= 4 * r["std_error"], r
         assert r["samples"] == 2.0 ** 32
+
+
+def test_single_step_draw_has_a_full_tail(engine):
+    """2^32 single-step draws binned on the device: chi-square over ALL 256 bins against the normal law (no thin tail to
+    excuse), +-4 / +-5 sigma counts within Poisson error, and mass beyond the 5.65 sigma cap of the 23-bit radius grid."""
+    from tools import rng_evidence as ev
+
+    st = ev.single_step_statistics(engine)
+    n = st["draws"]
+    assert n == 2.0 ** 32
+    assert abs(st["mean"]) < 5 / np.sqrt(n) and abs(st["second_moment"] - 1) < 5 * np.sqrt(2 / n) and abs(st["fourth_moment"] - 3) < 5 * np.sqrt(96 / n)
+    assert abs(st["chi2_z_all_256_bins_vs_normal_law"]["z_score"]) < 5, st["chi2_z_all_256_bins_vs_normal_law"]
+    for name, t in st["tails"].items():
+        assert abs(t["count"] - t["normal_law"]) < 5 * np.sqrt(t["normal_law"]), (name, t)
+    far = st["beyond_the_23_bit_cap"]["|z|>5.625"]
+    assert far["count"] > 0 and abs(far["count"] - far["normal_law"]) < 5 * np.sqrt(far["normal_law"]) + 3, far

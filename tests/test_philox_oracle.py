@@ -99,6 +99,29 @@ def test_normal_mapping_ks_at_3e7_draws_and_symmetric_tails():
         assert abs(tail - expect) < 5 * np.sqrt(expect)
 
 
+def test_single_step_paths_draw_one_64_bit_normal():
+    """n_steps == 1 (the reference's default): the path's one normal takes the whole first word for the radius
+    (u = (w0 + 1) 2^-32, FP32-converted as on the device) and the top 23 bits of the second word for the angle
+    (normal.cuh, box_muller_single).  Contract restated from the raw Philox words, then moments / KS / tails."""
+    from scipy import stats
+
+    seed, n = 31, 4_000_000
+    z = po.normals(seed, n, 1).ravel()
+    for path in (0, 1, 12345, n - 1):
+        w = po.philox4x32_10([path, 0, 0, 0], [seed, 0])
+        u = np.float32(np.float32(w[0]) * np.float32(2.0**-32) + np.float32(2.0**-32))  # fmaf: exact product, one rounding
+        turns = np.frombuffer(np.uint32((int(w[1]) >> 9) | 0x3F800000).tobytes(), dtype=np.float32)[0]
+        theta = float(turns) * float(np.float32(6.28318530717958647692)) + float(np.float32(-9.42477796076937971538))
+        assert z[path] == pytest.approx(np.sqrt(-2.0 * np.log(float(u))) * np.cos(theta), rel=1e-12, abs=1e-15)
+    assert abs(z.mean()) < 4 / np.sqrt(n) and abs(z.var() - 1) < 4 * np.sqrt(2 / n) and abs((z**4).mean() - 3) < 4 * np.sqrt(96 / n)
+    assert stats.kstest(z, "norm").pvalue > 1e-3
+    expect = n * stats.norm.sf(3.5)
+    for tail in ((z > 3.5).sum(), (z < -3.5).sum()):
+        assert abs(tail - expect) < 5 * np.sqrt(expect)
+    # a two-step path is NOT the single-step draw followed by another one: the layouts differ (32 vs 64 bits)
+    assert not np.allclose(po.normals(seed, 16, 2)[:, 0], z[:16])
+
+
 def test_word_to_pair_mapping_matches_the_documented_contract():
     """normal.cuh: word n = 4j+i of a path -> steps 2n, 2n+1; radius mantissa = top 23 bits, angle mantissa =
     top 23 bits of the byte-reversed word (turns), radius normalised so that the 2^23-point grid has E[r^2] = 2."""

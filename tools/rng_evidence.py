@@ -12,7 +12,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-# The radius takes 2^23 equally spaced u = j / 2^23 (normal.cuh), so beyond ~4.5 sigma the law thins out:
+# Multi-step streams: the radius takes 2^23 equally spaced u = j / 2^23 (normal.cuh), so beyond ~4.5 sigma the law thins out:
 # P(z > c) relative to the normal law, by summing arccos(c / r_j) / pi over the grid (the angle is continuous to 2^-23).
 GRID_TAIL_RATIO = {4.0: 1 - 4.9e-4, 4.5: 1 - 4.0e-3, 5.0: 1 - 3.74e-2}
 
@@ -90,6 +90,28 @@ def stream_statistics(eng, seed=2026, n_paths=1 << 25, n_steps=320):
     }
 
 
+def single_step_statistics(eng, seed=5, n_paths=1 << 32):
+    """The 64-bit single-step draw (n_steps == 1, normal.cuh box_muller_single) at 2^32 draws: moments, body chi-square and
+    tail counts against the NORMAL law - this draw has no thin tail (cap 6.66 sigma)."""
+    st = eng.rng_statistics(seed, n_paths, 1)
+    m = st["moments"]
+    n = m[11]
+    edges = np.linspace(-6.0, 6.0, 257)
+    cdf = np.array([_phi(x) for x in edges])
+    pz = np.diff(cdf)
+    pz[0] += cdf[0]
+    pz[-1] += 1.0 - cdf[-1]
+    chi, df = chi_square(st["hist_z"], pz, n)
+    sf = lambda c: 0.5 * math.erfc(c / math.sqrt(2.0))
+    beyond = {f"|z|>{c}": {"count": int(sum(int(st["hist_z"][i]) for i in range(256) if edges[i] >= c or edges[i + 1] <= -c)),
+                           "normal_law": 2 * n * sf(c)} for c in (5.25, 5.625)}
+    return {"draws": n, "mean": m[0] / n, "second_moment": m[1] / n, "fourth_moment": m[3] / n,
+            "chi2_z_all_256_bins_vs_normal_law": {"chi2": chi, "df": df, "z_score": (chi - df) / math.sqrt(2 * df)},
+            "tails": {name: {"count": int(c), "normal_law": n * sf(x)} for name, c, x in
+                      (("z>4", st["tails"][0], 4.0), ("z>5", st["tails"][1], 5.0), ("z<-4", st["tails"][2], 4.0), ("z<-5", st["tails"][3], 5.0))},
+            "beyond_the_23_bit_cap": beyond}
+
+
 def bs_price(S, K, T, r, sigma, call=True):
     d1 = (math.log(S / K) + (r + 0.5 * sigma * sigma) * T) / (sigma * math.sqrt(T))
     d2 = d1 - sigma * math.sqrt(T)
@@ -136,6 +158,7 @@ def main():
                          "2^32 points one 32-bit word can produce); the 1.07e10-draw run holds 5.4e9 pairs - more than there are distinct "
                          "points - so its joint chi-square measures the lattice of a 32-bit-per-pair generator, mostly in the corners beyond "
                          "r = 4.4 where one radius atom meets 512 equally spaced angles (arc spacing 0.11)",
+           "single_step_draw_2^32_draws": single_step_statistics(eng),
            "strike_sweep_single_step_2^32_samples": strike_sweep(eng)}
     print(json.dumps(out, indent=1))
 
