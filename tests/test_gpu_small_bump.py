@@ -124,3 +124,11 @@ def test_control_variate_sums_follow_the_fp64_strike(engine):
         assert m["sum_payoff"] == pytest.approx(pay.sum(), rel=2e-6)
         assert m["sum_payoff_terminal"] == pytest.approx((pay * terminal).sum(), rel=2e-6)
         assert m["sum_terminal"] == pytest.approx(terminal.sum(), rel=2e-6)
+    # a batch (parameters through HBM, two scenarios per option): the control-variate launch and the plain launch agree on the payoff sums
+    strikes = np.array([95.0, 100.0, 105.0])
+    params = np.stack([_ffi.make_params(100.0 + b, strikes, T, R, SIGMA) for b in (H, -H)], axis=1)
+    spec = _ffi.make_spec(_ffi.EUROPEAN, n_steps, antithetic=True)
+    cv = engine.simulate(spec, params, seed, n_paths, control_variate=True)
+    plain = engine.simulate(spec, params, seed, n_paths)
+    assert cv.shape == (3, 2) and np.array_equal(cv["sum_payoff"], plain["sum"]) and np.array_equal(cv["sum_payoff_sq"], plain["sum_sq"])
+    assert np.all(cv["sum_terminal"][:, 0] > cv["sum_terminal"][:, 1])  # S + h against S - h on the same draws

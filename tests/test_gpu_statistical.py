@@ -173,6 +173,25 @@ def test_lane_split_plans_price_the_same_draws(engine):
                     if base is None:
                         base = m
                     assert m["sum"] == pytest.approx(base["sum"], rel=2e-6) and m["sum_sq"] == pytest.approx(base["sum_sq"], rel=4e-6)
+    # more than 1024 tiles per option: the fold takes its second level (groups of 1024 tiles, then the group totals)
+    n_paths, n_steps, seed = 300_000, 16, 8
+    Z = po.normals(seed, n_paths, n_steps)
+    want = orc.vanilla_payoffs(orc.gbm_terminal_from_normals(P["S"], P["T"], P["r"], P["sigma"], 0.0, Z), P["K"], "call")
+    spec = _ffi.make_spec(_ffi.EUROPEAN, n_steps, antithetic=True)
+    many = np.stack([_ffi.make_params(**dict(P, sigma=0.2 + 0.0 * k)) for k in range(14)]).reshape(1, 14)
+    for params in (_ffi.make_params(**P).reshape(1, 1), many):
+        engine.set_plan(0, 1)
+        try:
+            fine = engine.simulate(spec, params, seed, n_paths)[0]
+            assert engine.last_plan()["tiles"] == 1172
+        finally:
+            engine.set_plan()
+        auto = engine.simulate(spec, params, seed, n_paths)[0]
+        assert np.all(fine["n"] == 2 * n_paths)
+        np.testing.assert_allclose(fine["sum"], want.sum(), rtol=3e-4)
+        np.testing.assert_allclose(fine["sum"], auto["sum"], rtol=2e-6)
+        np.testing.assert_allclose(fine["sum_sq"], auto["sum_sq"], rtol=4e-6)
+        assert np.all(fine["sum"] == fine["sum"][0])  # identical scenarios of one launch: identical bits
     # the automatic plan of an under-filled launch does split, and repeats bit for bit
     spec = _ffi.make_spec(_ffi.EUROPEAN, 252, antithetic=True)
     a = engine.simulate(spec, _ffi.make_params(**P).reshape(1, 1), 1, 10_000)
