@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200MC_ABI_VERSION 9
+#define B200MC_ABI_VERSION 10
 #define B200MC_MAX_SCENARIOS 16
 
 typedef struct b200mc_engine b200mc_engine_t;
@@ -199,6 +199,11 @@ int b200mc_comm_connect(b200mc_engine_t* eng, int rank, int world, const void* h
 int b200mc_comm_connect_local(b200mc_engine_t* const* engines, int n);
 int b200mc_comm_disconnect(b200mc_engine_t* eng);
 int b200mc_comm_world(const b200mc_engine_t* eng);
+/* Collective mode: while on, EVERY fused launch of a host entry point (b200mc_simulate, _control_variate, _structured, _heston,
+ * _jump_diffusion, _sobol) on a connected engine is a collective call - this rank's path / point range in, the moments of all
+ * ranks' ranges out, n_paths (n_points) may be 0 - exactly like b200mc_simulate_allreduce.  Meant to be switched on around one
+ * call by the sharding layer (optionslab_b200/distributed.py); off by default and after (re)connecting. */
+int b200mc_comm_set_collective(b200mc_engine_t* eng, int on);
 /* Bound on the in-kernel wait for a peer rank's records (default 20 000 ms); a launch that exceeds it returns B200MC_ERR_COMM. */
 int b200mc_comm_set_timeout_ms(b200mc_engine_t* eng, uint32_t milliseconds);
 int b200mc_simulate_allreduce(b200mc_engine_t* eng, const b200mc_spec_t* spec, const b200mc_params_t* params_host,

@@ -18,7 +18,7 @@ from .exceptions import AccelerationError, MonteCarloError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200MC_LIB") or os.path.join(_HERE, "libb200mc.so")  # B200MC_LIB: another build of the SAME library (A/B timing)
-ABI_VERSION = 9
+ABI_VERSION = 10
 MAX_SCENARIOS = 16
 
 EUROPEAN, ASIAN_ARITH, ASIAN_GEOM, BARRIER, LOOKBACK, CLIQUET, AUTOCALLABLE = range(7)
@@ -85,6 +85,7 @@ SIGNATURES = {
     "b200mc_comm_disconnect": (C.c_int, [_P]),
     "b200mc_comm_world": (C.c_int, [_P]),
     "b200mc_comm_set_timeout_ms": (C.c_int, [_P, C.c_uint32]),
+    "b200mc_comm_set_collective": (C.c_int, [_P, C.c_int]),
     "b200mc_simulate_control_variate": (C.c_int, [_P, C.POINTER(Spec), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
                                                   C.c_uint64, C.c_uint64, _P]),
     "b200mc_simulate_structured": (C.c_int, [_P, C.POINTER(Spec), C.POINTER(Product), _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
@@ -295,6 +296,10 @@ class Engine:
 
     def comm_disconnect(self):
         self._check(self._lib.b200mc_comm_disconnect(self._h), "b200mc_comm_disconnect")
+
+    def comm_set_collective(self, on: bool):
+        """While on, every fused launch of this engine's host entry points adds up the connected ranks' moments in its tail."""
+        self._check(self._lib.b200mc_comm_set_collective(self._h, int(bool(on))), "b200mc_comm_set_collective")
 
     def comm_set_timeout_ms(self, milliseconds: int):
         self._check(self._lib.b200mc_comm_set_timeout_ms(self._h, int(milliseconds)), "b200mc_comm_set_timeout_ms")

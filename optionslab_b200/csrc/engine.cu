@@ -64,6 +64,7 @@ struct b200mc_engine {
     unsigned long long epoch = 0;
     unsigned long long timeout_ns = kXchgTimeoutNs;
     uint32_t* launch_ticket = nullptr;
+    bool collective = false;          // b200mc_comm_set_collective: every fused launch of a host entry point exchanges
   } comm;
   int plan_split_shift = -1;  // b200mc_set_plan: -1 / 0 = automatic
   uint32_t plan_ppt = 0;
@@ -171,6 +172,33 @@ int order_after(b200mc_engine* e, cudaStream_t stream) {
   e->last_own = stream == e->stream;
   e->last_valid = true;
   if (!e->last_own) CU_TRY(e, cudaEventRecord(e->order_ev, stream));  // a caller's stream may be gone by the next call: record now
+  return 0;
+}
+
+// Is this call collective?  (explicitly - b200mc_simulate_allreduce - or because the caller switched the engine to
+// collective mode around it; unconnected engines never are.)
+bool exchanging(const b200mc_engine* e, bool asked) { return (asked || e->comm.collective) && e->comm.world > 1; }
+
+// The exchange part of a launch's FoldArgs: checks, peer table, the next epoch.  Every rank must make the same calls.
+int setup_exchange(b200mc_engine* e, FoldArgs& f, size_t record_bytes) {
+  if (record_bytes > kXchgSlotBytes - kXchgHeaderBytes)
+    return fail(e, B200MC_ERR_COMM, "%zu bytes of moment records exceed the exchange slot (%zu)", record_bytes, kXchgSlotBytes - kXchgHeaderBytes);
+  if (*(volatile unsigned int*)(e->mapped_host + kMappedTimeoutOffset))
+    return fail(e, B200MC_ERR_COMM, "an earlier fused all-reduce timed out waiting for a peer rank; reconnect the communicator");
+  f.x.world = (uint32_t)e->comm.world;
+  f.x.rank = (uint32_t)e->comm.rank;
+  f.x.epoch = ++e->comm.epoch;
+  for (int r = 0; r < e->comm.world; ++r) f.x.peer[r] = e->comm.peer[r];
+  f.x.slot_bytes = kXchgSlotBytes;
+  f.x.launch_ticket = e->comm.launch_ticket;
+  f.x.timed_out = (unsigned int*)(e->mapped_dev + kMappedTimeoutOffset);
+  f.x.timeout_ns = e->comm.timeout_ns;
+  return 0;
+}
+
+int check_exchange_done(b200mc_engine* e, bool exchange) {  // after the launch has completed
+  if (exchange && *(volatile unsigned int*)(e->mapped_host + kMappedTimeoutOffset))
+    return fail(e, B200MC_ERR_COMM, "fused all-reduce timed out waiting for a peer rank");
   return 0;
 }
 
@@ -318,7 +346,7 @@ int enqueue_simulation(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc
                        void* out_dev, cudaStream_t stream, bool time_it, bool cv = false, bool allreduce = false) {
   if (int rc = check_spec(e, spec)) return rc;
   if ((!params_dev && !inline_params) || !out_dev) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
-  const bool exchange = allreduce && e->comm.world > 1;
+  const bool exchange = exchanging(e, allreduce);
   // a rank whose share of the paths is empty still takes part in the exchange (it contributes zero records)
   if (n_opt == 0 || (n_paths == 0 && !exchange)) return fail(e, B200MC_ERR_INVALID, "n_opt and n_paths must be >= 1");
   if (n_scen == 0 || n_scen > B200MC_MAX_SCENARIOS)
@@ -328,13 +356,6 @@ int enqueue_simulation(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc
   if (cv && spec->kind != B200MC_EUROPEAN) return fail(e, B200MC_ERR_INVALID, "the control variate is defined for the European payoff only");
   const uint32_t ns = pad_scenarios(n_scen);
   TilePlan plan = plan_tiles(e, n_opt, std::max<uint64_t>(n_paths, 1), spec->n_steps, ns, spec->kind != B200MC_EUROPEAN, spec->kind == B200MC_EUROPEAN && !cv);
-  if (exchange) {
-    const size_t record_bytes = (size_t)n_opt * n_scen * (cv ? sizeof(b200mc_cv_moments_t) : sizeof(b200mc_moments_t));
-    if (record_bytes > kXchgSlotBytes - kXchgHeaderBytes)
-      return fail(e, B200MC_ERR_COMM, "%zu bytes of moment records exceed the exchange slot (%zu)", record_bytes, kXchgSlotBytes - kXchgHeaderBytes);
-    if (*(volatile unsigned int*)(e->mapped_host + kMappedTimeoutOffset))
-      return fail(e, B200MC_ERR_COMM, "an earlier fused all-reduce timed out waiting for a peer rank; reconnect the communicator");
-  }
   const uint64_t ctas = (uint64_t)plan.tiles * n_opt;
   if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
   e->last_plan[0] = plan.tiles, e->last_plan[1] = plan.ppt, e->last_plan[2] = plan.split_shift;
@@ -362,16 +383,8 @@ int enqueue_simulation(b200mc_engine* e, const b200mc_spec_t* spec, const b200mc
     a.fold.done = (unsigned long long*)(e->mapped_dev + kMappedRecordBytes);
     a.fold.seq = ++e->seq;
   }
-  if (exchange) {
-    a.fold.x.world = (uint32_t)e->comm.world;
-    a.fold.x.rank = (uint32_t)e->comm.rank;
-    a.fold.x.epoch = ++e->comm.epoch;
-    for (int r = 0; r < e->comm.world; ++r) a.fold.x.peer[r] = e->comm.peer[r];
-    a.fold.x.slot_bytes = kXchgSlotBytes;
-    a.fold.x.launch_ticket = e->comm.launch_ticket;
-    a.fold.x.timed_out = (unsigned int*)(e->mapped_dev + kMappedTimeoutOffset);
-    a.fold.x.timeout_ns = e->comm.timeout_ns;
-  }
+  if (exchange)
+    if (int rc = setup_exchange(e, a.fold, (size_t)n_opt * n_scen * (cv ? sizeof(b200mc_cv_moments_t) : sizeof(b200mc_moments_t)))) return rc;
   a.path_begin = path_begin;
   a.n_paths = n_paths;
   a.n_opt = n_opt;
@@ -614,8 +627,7 @@ static int simulate_host(b200mc_engine_t* e, const b200mc_spec_t* spec, const b2
                                     e->stream, e->timing, cv, allreduce))
       return rc;
     if (int rc = wait_mapped(e, e->seq)) return rc;
-    if (allreduce && *(volatile unsigned int*)(e->mapped_host + kMappedTimeoutOffset))
-      return fail(e, B200MC_ERR_COMM, "fused all-reduce timed out waiting for a peer rank");
+    if (int rc = check_exchange_done(e, exchanging(e, allreduce))) return rc;
     memcpy(out_host, e->mapped_host, out_bytes);
     return 0;
   }
@@ -631,8 +643,7 @@ static int simulate_host(b200mc_engine_t* e, const b200mc_spec_t* spec, const b2
     return rc;
   CU_TRY(e, cudaMemcpyAsync(pin_out, e->moments_dev.ptr, out_bytes, cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
-  if (allreduce && *(volatile unsigned int*)(e->mapped_host + kMappedTimeoutOffset))
-    return fail(e, B200MC_ERR_COMM, "fused all-reduce timed out waiting for a peer rank");
+  if (int rc = check_exchange_done(e, exchanging(e, allreduce))) return rc;
   memcpy(out_host, pin_out, out_bytes);
   return 0;
 }
@@ -667,7 +678,7 @@ static int comm_reset(b200mc_engine_t* e) {  // forget the peers; flags back to 
     if (e->comm.ipc_opened[r] && e->comm.peer[r]) cudaIpcCloseMemHandle(e->comm.peer[r]);
     e->comm.peer[r] = nullptr, e->comm.ipc_opened[r] = false;
   }
-  e->comm.world = 0, e->comm.rank = 0, e->comm.epoch = 0;
+  e->comm.world = 0, e->comm.rank = 0, e->comm.epoch = 0, e->comm.collective = false;
   if (e->comm.block) {
     CU_TRY(e, cudaMemset(e->comm.block, 0, kXchgHeaderBytes));
     CU_TRY(e, cudaMemset(e->comm.block + kXchgSlotBytes, 0, kXchgHeaderBytes));
@@ -753,6 +764,13 @@ int b200mc_comm_disconnect(b200mc_engine_t* e) {
 
 int b200mc_comm_world(const b200mc_engine_t* e) { return e ? e->comm.world : 0; }
 
+int b200mc_comm_set_collective(b200mc_engine_t* e, int on) {
+  if (!e) return B200MC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(e->mutex);
+  e->comm.collective = on != 0;
+  return 0;
+}
+
 int b200mc_comm_set_timeout_ms(b200mc_engine_t* e, uint32_t milliseconds) {
   if (!e || milliseconds == 0) return fail(e, B200MC_ERR_INVALID, "timeout must be >= 1 ms");
   std::lock_guard<std::mutex> g(e->mutex);
@@ -775,7 +793,8 @@ int b200mc_simulate_structured(b200mc_engine_t* e, const b200mc_spec_t* spec, co
   uint32_t period, n_events, sim_steps;
   if (int rc = check_structured(e, spec, product, &period, &n_events, &sim_steps)) return rc;
   if (!params_host || !out_host) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
-  if (n_opt == 0 || n_paths == 0 || n_scen == 0 || n_scen > B200MC_MAX_SCENARIOS) return fail(e, B200MC_ERR_INVALID, "bad n_opt / n_scen / n_paths");
+  const bool exchange = exchanging(e, false);
+  if (n_opt == 0 || (n_paths == 0 && !exchange) || n_scen == 0 || n_scen > B200MC_MAX_SCENARIOS) return fail(e, B200MC_ERR_INVALID, "bad n_opt / n_scen / n_paths");
   CU_TRY(e, cudaSetDevice(e->device));
   const size_t n = (size_t)n_opt * n_scen;
   const size_t in_bytes = n * sizeof(b200mc_params_t), out_bytes = n * sizeof(b200mc_moments_t);
@@ -788,7 +807,7 @@ int b200mc_simulate_structured(b200mc_engine_t* e, const b200mc_spec_t* spec, co
   CU_TRY(e, cudaMemcpyAsync(e->params_dev.ptr, pin_in, in_bytes, cudaMemcpyHostToDevice, e->stream));
 
   const uint32_t ns = pad_scenarios(n_scen);
-  const TilePlan plan = plan_tiles(e, n_opt, n_paths, sim_steps, ns, true);
+  const TilePlan plan = plan_tiles(e, n_opt, std::max<uint64_t>(n_paths, 1), sim_steps, ns, true);
   const uint32_t tiles = plan.tiles;
   const uint64_t ctas = (uint64_t)tiles * n_opt;
   if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
@@ -800,6 +819,9 @@ int b200mc_simulate_structured(b200mc_engine_t* e, const b200mc_spec_t* spec, co
   a.sim.fold.tickets = (uint32_t*)e->tickets.ptr;
   a.sim.fold.out = e->moments_dev.ptr;
   a.sim.fold.samples = (double)n_paths;
+  a.sim.fold.n_opt = n_opt;
+  if (exchange)
+    if (int rc = setup_exchange(e, a.sim.fold, out_bytes)) return rc;
   a.sim.path_begin = path_begin, a.sim.n_paths = n_paths;
   a.sim.n_opt = n_opt, a.sim.n_scen = n_scen, a.sim.tiles = tiles, a.sim.paths_per_thread = plan.ppt, a.sim.n_steps = spec->n_steps;
   a.sim.rk = philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32));
@@ -820,6 +842,7 @@ int b200mc_simulate_structured(b200mc_engine_t* e, const b200mc_spec_t* spec, co
   if (int rc = order_after(e, e->stream)) return rc;
   CU_TRY(e, cudaMemcpyAsync(pin_out, e->moments_dev.ptr, out_bytes, cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
+  if (int rc = check_exchange_done(e, exchange)) return rc;
   memcpy(out_host, pin_out, out_bytes);
   return 0;
 }
@@ -923,7 +946,8 @@ static int simulate_model_host(b200mc_engine_t* e, const void* block_a, size_t b
                                uint32_t n_opt, uint32_t n_steps, uint32_t per_step_cost, uint64_t n_paths, b200mc_moments_t* out_host,
                                Launch&& launch) {
   if (!block_a || !out_host) return fail(e, B200MC_ERR_INVALID, "params/out pointer is null");
-  if (n_opt == 0 || n_paths == 0 || n_steps == 0) return fail(e, B200MC_ERR_INVALID, "n_opt, n_paths and n_steps must be >= 1");
+  const bool exchange = exchanging(e, false);
+  if (n_opt == 0 || (n_paths == 0 && !exchange) || n_steps == 0) return fail(e, B200MC_ERR_INVALID, "n_opt, n_paths and n_steps must be >= 1");
   CU_TRY(e, cudaSetDevice(e->device));
   const size_t in_bytes = bytes_a + bytes_b, out_bytes = (size_t)n_opt * sizeof(b200mc_moments_t);
   if (int rc = reserve(e, e->params_dev, in_bytes)) return rc;
@@ -934,7 +958,7 @@ static int simulate_model_host(b200mc_engine_t* e, const void* block_a, size_t b
   memcpy(pin_in, block_a, bytes_a);
   if (bytes_b) memcpy(pin_in + bytes_a, block_b, bytes_b);
   CU_TRY(e, cudaMemcpyAsync(e->params_dev.ptr, pin_in, in_bytes, cudaMemcpyHostToDevice, e->stream));
-  const TilePlan plan = plan_tiles(e, n_opt, n_paths, n_steps * per_step_cost, 1, false);
+  const TilePlan plan = plan_tiles(e, n_opt, std::max<uint64_t>(n_paths, 1), n_steps * per_step_cost, 1, false);
   const uint32_t tiles = plan.tiles, ppt = plan.ppt;
   const uint64_t ctas = (uint64_t)tiles * n_opt;
   if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
@@ -945,6 +969,9 @@ static int simulate_model_host(b200mc_engine_t* e, const void* block_a, size_t b
   fold.tickets = (uint32_t*)e->tickets.ptr;
   fold.out = e->moments_dev.ptr;
   fold.samples = (double)n_paths;
+  fold.n_opt = n_opt;
+  if (exchange)
+    if (int rc = setup_exchange(e, fold, out_bytes)) return rc;
   const int slot = (int)(e->timed % b200mc_engine::kRing);
   if (e->timing) CU_TRY(e, cudaEventRecord(e->ring0[slot], e->stream));
   launch((const char*)e->params_dev.ptr, (const char*)e->params_dev.ptr + bytes_a, fold, tiles, ppt, dim3((unsigned)ctas));
@@ -957,6 +984,7 @@ static int simulate_model_host(b200mc_engine_t* e, const void* block_a, size_t b
   if (int rc = order_after(e, e->stream)) return rc;
   CU_TRY(e, cudaMemcpyAsync(pin_out, e->moments_dev.ptr, out_bytes, cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
+  if (int rc = check_exchange_done(e, exchange)) return rc;
   memcpy(out_host, pin_out, out_bytes);
   return 0;
 }
@@ -1106,8 +1134,9 @@ static int sobol_run(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc
   if (n_opt == 0 || n_scen == 0 || n_scen > B200MC_MAX_SCENARIOS) return fail(e, B200MC_ERR_INVALID, "bad n_opt / n_scen");
   if (int rc = check_sobol_table(e, dirnums_host, shift_host, spec->n_steps, bits)) return rc;
   constexpr uint64_t kAlign = 1ull << kSobolAlignShift;
-  if (n_points == 0) return fail(e, B200MC_ERR_INVALID, "n_points must be >= 1");
-  if (point_begin % kAlign != 0)
+  const bool exchange = exchanging(e, false) && !terminal_host;
+  if (n_points == 0 && !exchange) return fail(e, B200MC_ERR_INVALID, "n_points must be >= 1");
+  if (n_points != 0 && point_begin % kAlign != 0)
     return fail(e, B200MC_ERR_INVALID, "point_begin must be a multiple of %llu (one full-size CTA of Sobol points)", (unsigned long long)kAlign);
   if (point_begin + n_points > (1ull << bits))
     return fail(e, B200MC_ERR_INVALID, "points [%llu, %llu) exceed the 2^%u points of the sequence", (unsigned long long)point_begin,
@@ -1139,14 +1168,14 @@ static int sobol_run(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc
   double best_balance = -1.0;
   for (int cand_pb = kSobolMaxPointBits; cand_pb >= 0 && best_balance < 0.95; cand_pb -= 2) {
     for (uint32_t cand_ds = 1; cand_ds <= 4 && cand_ds <= chunks && best_balance < 0.95; cand_ds *= 2) {
-      const double ctas_c = std::ceil((double)n_points / (double)((uint64_t)kBlock << cand_pb)) * n_opt * cand_ds;
+      const double ctas_c = std::ceil((double)std::max<uint64_t>(n_points, 1) / (double)((uint64_t)kBlock << cand_pb)) * n_opt * cand_ds;
       const double balance = (ctas_c / n_sm) / std::ceil(ctas_c / n_sm);
       if (balance > best_balance + 0.05) best_balance = balance, pb = cand_pb, dsplit = cand_ds;
     }
   }
   if (terminal_host) dsplit = 1;  // the terminal-price output is written by the CTA that owns all dimensions
   const uint64_t tile_points = (uint64_t)kBlock << pb;
-  const uint64_t tiles = (n_points + tile_points - 1) / tile_points;
+  const uint64_t tiles = (std::max<uint64_t>(n_points, 1) + tile_points - 1) / tile_points;
   const uint64_t ctas = tiles * n_opt * dsplit;
   if (ctas > 0x7fffffffull) return fail(e, B200MC_ERR_INVALID, "problem too large for one launch (%llu CTAs)", (unsigned long long)ctas);
   if (dsplit > 1) {
@@ -1165,6 +1194,9 @@ static int sobol_run(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc
   a.fold.tickets = (uint32_t*)e->tickets.ptr;
   a.fold.out = e->moments_dev.ptr;
   a.fold.samples = (double)n_points;
+  a.fold.n_opt = n_opt;
+  if (exchange)
+    if (int rc = setup_exchange(e, a.fold, out_bytes)) return rc;
   a.dsplit = dsplit;
   a.wpart = (float*)e->qmc_wpart.ptr;
   a.tile_tickets = (uint32_t*)e->qmc_tickets.ptr;
@@ -1207,6 +1239,7 @@ static int sobol_run(b200mc_engine_t* e, const b200mc_spec_t* spec, const b200mc
   CU_TRY(e, cudaMemcpyAsync(pin_out, e->moments_dev.ptr, out_bytes, cudaMemcpyDeviceToHost, e->stream));
   if (terminal_host) CU_TRY(e, cudaMemcpyAsync(terminal_host, e->scratch_b.ptr, terminal_bytes, cudaMemcpyDeviceToHost, e->stream));
   CU_TRY(e, cudaStreamSynchronize(e->stream));
+  if (int rc = check_exchange_done(e, exchange)) return rc;
   memcpy(out_host, pin_out, out_bytes);
   return 0;
 }

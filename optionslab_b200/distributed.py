@@ -10,12 +10,13 @@ Every (option, path) is independent: rank g of G simulates glob
 draws are disjoint by construction and independent of G — and the only exchanged data are the
 FP64 (sum, sum^2, n) triples.
 
-The exchange itself: on NVLink-connected GPUs (the NCCL backend under torchrun, or ``local_devices``) the fused GBM
-launches (European / Asian / barrier / lookback: ``b200mc_simulate_allreduce``) add up the ranks' records in the TAIL OF
-THE SIMULATION KERNEL over peer memory — the finishing CTA of every rank reads its peers' exchange blocks in rank order,
-so there is no collective launch and no host hop between the kernel and the result (include/b200mc.h, "multi-GPU").
-``torch.distributed`` then only carries the 64-byte IPC handles at ``init()`` time.  Everything else (the other model
-families, gloo in the CPU tests, ``B200MC_FUSED_ALLREDUCE=0``) sums the moment records with one ``all_reduce``.
+The exchange itself: on NVLink-connected GPUs (the NCCL backend under torchrun, or ``local_devices``) every fused launch -
+European / Asian / barrier / lookback (``b200mc_simulate_allreduce``), control variate, structured products, Heston, jump
+diffusions, Sobol QMC (their ordinary entry points with the engine in collective mode) - adds up the ranks' records in the
+TAIL OF THE SIMULATION KERNEL over peer memory: the finishing CTA of every rank reads its peers' exchange blocks in rank
+order, so there is no collective launch and no host hop between the kernel and the result (include/b200mc.h,
+"multi-GPU").  ``torch.distributed`` then only carries the 64-byte IPC handles at ``init()`` time.  Gloo (the CPU tests),
+unconnected devices and ``B200MC_FUSED_ALLREDUCE=0`` sum the moment records with one ``all_reduce`` / on the host.
 """
 
 from __future__ import annotations
@@ -218,23 +219,36 @@ def fused_exchange() -> bool:
     return _ctx is not None and _ctx.world_size > 1 and _ctx.fused
 
 
+def _collective(eng, fn, begin, count, fused_fn):
+    """One rank's share of a collective call on connected engines: the all-reduce happens in the kernel's tail.  ``fused_fn``
+    asks for it explicitly (b200mc_simulate_allreduce); every other family runs its ordinary entry point with the engine in
+    collective mode for the duration of the call (b200mc_comm_set_collective)."""
+    if fused_fn is not None:
+        return fused_fn(eng, begin, count)
+    eng.comm_set_collective(True)
+    try:
+        return fn(eng, begin, count)
+    finally:
+        eng.comm_set_collective(False)
+
+
 def run_sharded(fn, n_units: int, empty, partition=partition_paths, fused_fn=None) -> np.ndarray:
     """Run ``fn(engine, begin, count) -> moments`` over this process's share of ``n_units`` global paths (or Sobol points)
-    and return the moments of ALL units: plain call when unsharded, threads + host sum under ``local_devices``, partition +
-    all-reduce under a process group.  ``empty()`` builds the zero moments of a shard that received no unit.
-    ``fused_fn(engine, begin, count)`` - when given and the engines are connected - runs the same shard with the
-    all-reduce fused into the kernel and returns the total directly (it is called on every rank, empty shards included)."""
+    and return the moments of ALL units: plain call when unsharded; on connected engines (NVLink: torchrun with the NCCL
+    backend, or ``local_devices``) every rank / device runs its share - empty shares included - and the kernel's tail adds up
+    the moments over peer memory; otherwise (gloo, unconnected devices) partition + ``all_reduce`` / host-side sum, where
+    ``empty()`` builds the zero moments of a shard that received no unit."""
     from . import _ffi
 
     ctx = _ctx
-    fused = fused_fn is not None and fused_exchange()
+    fused = fused_exchange()
     if _local is not None and len(_local) > 1:
         from concurrent.futures import ThreadPoolExecutor
 
         def one(i):
             begin, count = partition(n_units, i, len(_local))
             if fused:
-                return fused_fn(_ffi.get_engine(_local[i]), begin, count)
+                return _collective(_ffi.get_engine(_local[i]), fn, begin, count, fused_fn)
             return fn(_ffi.get_engine(_local[i]), begin, count) if count > 0 else empty()
 
         with ThreadPoolExecutor(max_workers=len(_local)) as pool:
@@ -251,6 +265,6 @@ def run_sharded(fn, n_units: int, empty, partition=partition_paths, fused_fn=Non
         return fn(eng, 0, n_units)
     begin, count = partition(n_units, ctx.rank, ctx.world_size)
     if fused:
-        return fused_fn(eng, begin, count)
+        return _collective(eng, fn, begin, count, fused_fn)
     local = fn(eng, begin, count) if count > 0 else empty()
     return allreduce_moments(local, ctx)

@@ -32,7 +32,7 @@ def simulate(spec: _ffi.Spec, params: np.ndarray, seed: int, n_paths: int, *, st
     if n_paths < 1:
         raise MonteCarloError("n_paths must be >= 1")
     dtype = _ffi.CV_MOMENTS_DTYPE if control_variate else _ffi.MOMENTS_DTYPE
-    fused = None if control_variate else (
+    fused = None if control_variate else (  # (the control-variate launch exchanges through the engine's collective mode)
         lambda eng, begin, count: eng.simulate(spec, params, seed, count, stream_base=stream_base, path_begin=begin, allreduce=True))
     return distributed.run_sharded(
         lambda eng, begin, count: eng.simulate(spec, params, seed, count, stream_base=stream_base, path_begin=begin,

@@ -125,6 +125,63 @@ def test_fused_allreduce_between_two_engines_of_one_device():
         a.close(), b.close()
 
 
+def test_collective_mode_covers_every_fused_family():
+    """b200mc_comm_set_collective: with the engine in collective mode the ORDINARY entry points of the other kernel families -
+    control variate, structured products, Heston, jump diffusions, Sobol QMC - add up the connected ranks' records in their
+    kernel tail too (what distributed.run_sharded switches on around each call).  Two engine handles on cuda:0: both ranks end
+    with identical bits, equal to the field-wise sum of two plain launches over the same ranges; an empty share included."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from optionslab_b200 import _ffi, sobol
+
+    a, b = _ffi.Engine(0), _ffi.Engine(0)
+    plain = _ffi.get_engine(0)
+    engines = [a, b]
+
+    def both(call, ranges):
+        def one(i):
+            engines[i].comm_set_collective(True)
+            try:
+                return call(engines[i], *ranges[i])
+            finally:
+                engines[i].comm_set_collective(False)
+
+        with ThreadPoolExecutor(max_workers=2) as pool:
+            return list(pool.map(one, range(2)))
+
+    hes = np.zeros(2, dtype=_ffi.HESTON_PARAMS_DTYPE)
+    for i, K in enumerate((100.0, 105.0)):
+        hes[i] = (100.0, K, 1.0, 0.05, 0.01, 2.0, 0.04, 0.3, -0.7, 0.04, (0.0, 0.0))
+    gbm = _ffi.make_params(100.0, np.array([95.0, 100.0]), 1.0, 0.05, 0.2, 0.01)
+    jumps = np.zeros(2, dtype=_ffi.JUMP_PARAMS_DTYPE)
+    jumps["model"], jumps["lambda_j"], jumps["a"], jumps["b"], jumps["c"] = _ffi.JUMP_KOU, 2.0, 0.4, 10.0, 5.0
+    table, shift, bits = sobol.sobol_table(16, 5)
+    euro = _ffi.make_spec(_ffi.EUROPEAN, 16, antithetic=True)
+    qmc = _ffi.make_spec(_ffi.EUROPEAN, 16)
+    product = _ffi.Product(0.05, -0.05, 0.30, 0.0, 4, 0)
+    grid2 = gbm.reshape(2, 1)
+    cases = {
+        "control variate": (lambda e, lo, n: e.simulate(euro, grid2, 9, n, path_begin=lo, control_variate=True), [(0, 30_000), (30_000, 20_001)]),
+        "cliquet": (lambda e, lo, n: e.simulate_structured(_ffi.make_spec(_ffi.CLIQUET, 16), product, grid2, 9, n, path_begin=lo), [(0, 25_000), (25_000, 25_000)]),
+        "heston": (lambda e, lo, n: e.simulate_heston(hes, False, 16, 9, n, path_begin=lo), [(0, 1), (1, 49_999)]),
+        "kou": (lambda e, lo, n: e.simulate_jump_diffusion(gbm, jumps, True, 16, 9, n, path_begin=lo), [(0, 40_000), (40_000, 0)]),  # rank 1 empty
+        "sobol": (lambda e, lo, n: e.simulate_sobol(qmc, grid2, table, shift, bits, n, point_begin=lo), [(0, 8192), (8192, 8192 + 77)]),
+    }
+    try:
+        _ffi.connect_local(engines)
+        for name, (call, ranges) in cases.items():
+            for rep in range(2):
+                got = both(call, ranges)
+                assert got[0].tobytes() == got[1].tobytes(), name
+                parts = [call(plain, lo, n) for lo, n in ranges if n > 0]
+                for field in got[0].dtype.names:
+                    np.testing.assert_allclose(got[0][field], sum(p[field] for p in parts), rtol=1e-12, err_msg=f"{name}.{field}")
+        # outside collective mode the same entry points stay local even on connected engines
+        assert a.simulate_heston(hes, False, 16, 9, 1000).tobytes() == plain.simulate_heston(hes, False, 16, 9, 1000).tobytes()
+    finally:
+        a.close(), b.close()
+
+
 def test_a_missing_peer_is_an_error_not_a_hang():
     """Failure detection of the in-kernel exchange: if a connected rank never launches, the waiting kernel gives up after the
     configured bound and the call fails with AccelerationError(backend="nvlink") (B200MC_ERR_COMM); the engine refuses further

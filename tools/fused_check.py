@@ -29,6 +29,18 @@ def prices():
     out["delta_gamma"] = list(uni.delta_gamma(**P, option_type="call", seed=4))
     out["greeks"] = dict(ob.MonteCarloPricer(100_001, 12, seed=2).greeks(**P, option_type="call"))
     out["tiny"] = ob.MonteCarloPricer(3, 4, seed=1).price(**P, option_type="put")  # fewer paths than ranks: empty shards
+    # the other fused families exchange through the engine's collective mode
+    out["control_variate"] = ob.MonteCarloPricer(200_003, 16, seed=6).price_with_control_variate(**P, option_type="call")
+    out["autocall"] = float(ob.AutocallableOption(**P, seed=8).price(200_003, 24, 6))
+    out["cliquet"] = float(ob.CliquetOption(**P, seed=8).price(200_003, 24, 6))
+    hes = ob.HestonPricer(kappa=2.0, theta=0.04, sigma_v=0.3, rho=-0.7, v0=0.04)
+    out["heston"] = hes.price_monte_carlo(100.0, 100.0, 1.0, 0.05, 0.01, "call", 200_003, 20, seed=4)
+    out["kou"] = ob.KouJumpDiffusion(2.0, 0.4, 10.0, 5.0).price_monte_carlo(100.0, 100.0, 1.0, 0.05, 0.2, "call", 0.01, 200_003, 20, seed=4)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out["qmc"] = ob.MonteCarloPricer((1 << 16) + 5, 16, seed=42, method=ob.MCMethod.QMC).price(**P, option_type="call")
     return out
 
 
