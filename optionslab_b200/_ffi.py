@@ -529,10 +529,24 @@ _engines = {}
 _engines_lock = threading.Lock()
 
 
+_default_device: Optional[int] = None
+
+
+def default_device() -> int:
+    """This process's device: B200MC_DEVICE, else LOCAL_RANK (torchrun), else 0 - read once."""
+    global _default_device
+    if _default_device is None:
+        _default_device = int(os.environ.get("B200MC_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    return _default_device
+
+
 def get_engine(device: Optional[int] = None) -> Engine:
     """Process-wide engine per device (created on first use)."""
     if device is None:
-        device = int(os.environ.get("B200MC_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        device = default_device()
+        eng = _engines.get(device)  # the latency path comes through here on every call: no lock when the engine exists
+        if eng is not None and eng._h is not None:
+            return eng
     with _engines_lock:
         eng = _engines.get(device)
         if eng is None or eng._h is None:
