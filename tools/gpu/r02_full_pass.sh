@@ -17,7 +17,8 @@ cp gpurun_out/r02_ncu_european.txt profiles/r02_ncu_european.txt
 python bench.py --steps 5 --warmup 3 > gpurun_out/r02_bench_n1.json 2> gpurun_out/bench.err; echo "bench exit $?"; cut -c1-600 gpurun_out/r02_bench_n1.json; tail -5 gpurun_out/bench.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_reference_arm.json 2>> gpurun_out/bench.err; echo "ref exit $?"; cut -c1-900 gpurun_out/r02_bench_reference_arm.json
 python tools/bench_configs.py > gpurun_out/plain3.log 2>&1; echo "configs exit $?"; cut -c1-300 gpurun_out/plain3.log
-ncu --set full --clock-control none -k "regex:pathdep_kernel|qmc_european_kernel|heston_kernel|jump_kernel|structured_kernel" -c 24 -f -o /tmp/prof_other_r02 python tools/bench_configs.py > gpurun_out/ncu_full2.log 2>&1
+cp gpurun_out/configs_r02.json gpurun_out/r02_configs.json
+ncu --set full --clock-control none -k "regex:pathdep_kernel|qmc_european_kernel|heston_kernel|jump_kernel|structured_kernel|from_normals" -c 40 -f -o /tmp/prof_other_r02 python tools/bench_configs.py --profile > gpurun_out/ncu_full2.log 2>&1
 echo "ncu other exit $?"
 python tools/ncu_summary.py /tmp/prof_other_r02.ncu-rep > gpurun_out/r02_ncu_other_kernels.txt 2>&1
 python tools/small_configs.py 4 > /dev/null 2>&1 &&
