@@ -272,7 +272,14 @@ constexpr int kMinBlocksSmall = 6;    // European, 1-2 scenarios (40-47 register
 constexpr int kMinBlocksPathdep = 6;  // Asian / barrier / lookback, 1-2 scenarios (<= 40 registers)
 constexpr int kMinBlocksAsian = 6;    // arithmetic Asian, 1-2 scenarios (profiles/r01_variants14*)
 constexpr int kMinBlocksStructured = 5;  // cliquet / autocallable, 1-2 scenarios (47-48 registers)
-constexpr int kMinBlocksWide = 2;     // 4-16 scenarios (<= 128 registers)
+#ifndef B200MC_WIDE_MINB
+#define B200MC_WIDE_MINB 2
+#endif
+#ifndef B200MC_WIDE_UNROLL
+#define B200MC_WIDE_UNROLL 1
+#endif
+constexpr int kMinBlocksWide = B200MC_WIDE_MINB;  // 4-16 scenarios (<= 128 registers)
+constexpr int kUnrollWide = B200MC_WIDE_UNROLL;   // Philox calls in flight per thread of the 4-16 scenario European launches
 
 template <int NS>
 cudaError_t launch_european(const SimArgs& a, bool anti, bool cv, dim3 grid, cudaStream_t s) {
@@ -284,8 +291,9 @@ cudaError_t launch_european(const SimArgs& a, bool anti, bool cv, dim3 grid, cud
     if (anti) european_kernel<NS, true, kMinBlocks, false, 1, true><<<grid, kBlock, 0, s>>>(a);
     else european_kernel<NS, false, kMinBlocks, false, 1, true><<<grid, kBlock, 0, s>>>(a);
   } else {
-    if (anti) european_kernel<NS, true, kMinBlocks><<<grid, kBlock, 0, s>>>(a);
-    else european_kernel<NS, false, kMinBlocks><<<grid, kBlock, 0, s>>>(a);
+    constexpr int kUnroll = NS <= 2 ? 1 : kUnrollWide;
+    if (anti) european_kernel<NS, true, kMinBlocks, false, kUnroll><<<grid, kBlock, 0, s>>>(a);
+    else european_kernel<NS, false, kMinBlocks, false, kUnroll><<<grid, kBlock, 0, s>>>(a);
   }
   return cudaGetLastError();
 }
