@@ -47,9 +47,10 @@ WORKLOAD = (f"C5: {N_OPT}-option European call grid ({N_STRIKES} strikes 60..140
             f"S=100 r=0.05 sigma=0.2) x {N_PATHS} paths x {N_STEPS} steps, each option simulated independently "
             f"(antithetic, own Philox stream)")
 # Instruction budget of the dominant kernel (european_kernel<1,true> inner loop, counted from the shipped SASS
-# with cuobjdump - tools/sass_loop.py, profiles/r02_sass_loops.txt): 86 issued instructions per Philox call = 8 path-steps,
-# of which 16 MUFU, 16 IMAD.WIDE (fmaheavy pipe), 18 LOP3 + 8 LEA.HI + 4 PRMT (ALU pipe), 20 FP32.
-INSTR_PER_STEP, MUFU_PER_STEP, IMAD_PER_STEP, LOP_PER_STEP = 86 / 8, 2.0, 2.0, 30 / 8
+# with cuobjdump - tools/sass_loop.py, profiles/r02_sass_loops.txt): 78 issued instructions per Philox call = 8 path-steps,
+# of which 12 MUFU (LG2, SQRT and ONE SIN per Box-Muller pair: the terminal price adds a pair's two normals, and
+# rad (cos + sin) = sqrt(2) rad sin(theta + pi/4)), 16 IMAD.WIDE (fmaheavy pipe), 18 LOP3 + 8 LEA.HI + 4 PRMT (ALU pipe), 16 FP32.
+INSTR_PER_STEP, MUFU_PER_STEP, IMAD_PER_STEP, LOP_PER_STEP = 78 / 8, 1.5, 2.0, 30 / 8
 IMAD_WIDE_DISPATCH_CYCLES = 4.0  # scratch/variants15.cu: 16 IMAD.WIDE / IMAD.HI (+ XORs, loop) per warp take 69.7 / 66.0 SMSP cycles; charged 4
 ASIAN_INSTR_PER_STEP = 119 / 8  # pathdep_kernel<ASIAN_ARITH,1> small-move loop (tools/sass_loop.py --all): 16 FFMA2 + 4 FMUL2 + 32 FP32, 16 MUFU per 8 steps
 
@@ -290,7 +291,7 @@ def run_reference_arm(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 # MUFU per path-step of each kernel family (profiles/r02_sass_loops.txt): the XU pipe is the roof of all of them
-CONFIG_MUFU = {"european": 2.0, "asian": 2.0, "barrier": 2.0}
+CONFIG_MUFU = {"european": 1.5, "asian": 2.0, "barrier": 2.0}
 NCU_CAPTURE = os.path.join(ROOT, "profiles", "r02_ncu_european.txt")
 
 

@@ -456,18 +456,25 @@ __device__ __forceinline__ u32x4 draw4(uint64_t path, uint32_t call, uint32_t st
 // trailing odd step.  One Philox call = 4 words = 4 pairs = 8 steps (layout documented in normal.cuh).
 // UNROLL calls are drawn before any is consumed, so their multiply chains interleave on the fmaheavy
 // pipe; which UNROLL wins depends on the consumer's register appetite (profiles/r01_variants.txt).
-template <bool SQUARED, class F>
+// PAIRSUM: the consumer only adds a pair's two normals; full pairs arrive as box_muller_pair_sum (cs = sin(theta + pi/4),
+// n_use = 2), a trailing odd step as the plain cosine branch (n_use = 1).
+template <bool SQUARED, bool PAIRSUM>
+__device__ __forceinline__ NormalPair full_pair(uint32_t w) {
+  if (PAIRSUM) return box_muller_pair_sum<SQUARED>(w);
+  return box_muller<SQUARED>(w);
+}
+template <bool SQUARED, bool PAIRSUM, class F>
 __device__ __forceinline__ void consume_call(const u32x4& x, F&& f) {
-  f(box_muller<SQUARED>(x.x), 2);
-  f(box_muller<SQUARED>(x.y), 2);
-  f(box_muller<SQUARED>(x.z), 2);
-  f(box_muller<SQUARED>(x.w), 2);
+  f(full_pair<SQUARED, PAIRSUM>(x.x), 2);
+  f(full_pair<SQUARED, PAIRSUM>(x.y), 2);
+  f(full_pair<SQUARED, PAIRSUM>(x.z), 2);
+  f(full_pair<SQUARED, PAIRSUM>(x.w), 2);
 }
 
 // SQUARED: the pairs carry rad^2 = -log2(u) instead of rad (see box_muller).
 // [j0, j1): the Philox calls of the path this thread visits (default: all of them; the lane-split European kernel
 // hands each lane of a group its own range).  The trailing 1..7 steps belong to call index n_steps / 8.
-template <int UNROLL = 1, bool SQUARED = false, class F>
+template <int UNROLL = 1, bool SQUARED = false, bool PAIRSUM = false, class F>
 __device__ __forceinline__ void for_each_pair(uint64_t path, uint32_t n_steps, uint32_t stream, const PhiloxKeys& rk, F&& f,
                                               uint32_t j0 = 0u, uint32_t j1 = 0xffffffffu) {
   if (n_steps == 1u) {  // single-step paths: one 64-bit draw (normal.cuh, box_muller_single)
@@ -486,17 +493,21 @@ __device__ __forceinline__ void for_each_pair(uint64_t path, uint32_t n_steps, u
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) x[u] = draw4(path, j + u, stream, rk);
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) consume_call<SQUARED>(x[u], f);
+      for (int u = 0; u < UNROLL; ++u) consume_call<SQUARED, PAIRSUM>(x[u], f);
     }
   }
   // (plain #pragma unroll 2 / 4 of this loop measures 2.5% / 2% slower on the European kernel: profiles/r01_variants16_ffma2.txt)
-  for (; j < stop; ++j) consume_call<SQUARED>(draw4(path, j, stream, rk), f);
+  for (; j < stop; ++j) consume_call<SQUARED, PAIRSUM>(draw4(path, j, stream, rk), f);
   const int rem = (int)(n_steps & 7u);
   if (rem && j0 <= full && j1 > full) {  // 1..7 trailing steps: same word layout, only the pairs that are needed
     const u32x4 x = draw4(path, full, stream, rk);
-    f(box_muller<SQUARED>(x.x), rem >= 2 ? 2 : 1);
-    if (rem > 2) f(box_muller<SQUARED>(x.y), rem >= 4 ? 2 : 1);
-    if (rem > 4) f(box_muller<SQUARED>(x.z), rem >= 6 ? 2 : 1);
+    // (a pair whose second step is not needed is always the plain cosine branch)
+    if (rem >= 2) f(full_pair<SQUARED, PAIRSUM>(x.x), 2);
+    else f(box_muller<SQUARED>(x.x), 1);
+    if (rem >= 4) f(full_pair<SQUARED, PAIRSUM>(x.y), 2);
+    else if (rem > 2) f(box_muller<SQUARED>(x.y), 1);
+    if (rem >= 6) f(full_pair<SQUARED, PAIRSUM>(x.z), 2);
+    else if (rem > 4) f(box_muller<SQUARED>(x.z), 1);
     if (rem > 6) f(box_muller<SQUARED>(x.w), 1);
   }
 }
@@ -522,18 +533,20 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 }
 
 // ================================ European (terminal payoff) ====================================
-// W' = sum over steps of rad*cos / rad*sin (log2-radius units); everything else happens once per path.
-// (Accumulating the two branches in the halves of one packed FFMA2 register saves 4 issue slots per 8 steps and
-// measures 0.6% slower: the European loop is not issue-bound.  profiles/r01_variants16_ffma2.txt)
+// W = sum over steps of rad*cos / rad*sin (log2-radius units); everything else happens once per path.
+// The terminal price only ever sees the SUM of a pair's two normals, rad (cos + sin) = sqrt(2) rad sin(theta + pi/4): one
+// MUFU.SIN and one FFMA per pair instead of COS + SIN and two (box_muller_pair_sum: 3 MUFU per two path-steps instead of 4,
+// 78 instructions per Philox call instead of 86).  The loop adds up rad * sin(theta + pi/4), a trailing odd step enters with
+// the weight 1 / sqrt(2), and sqrt(2) is applied once per path.  The draws - and the value of W up to FP32 rounding - are
+// those of the step-by-step kernels (normals_kernel, the path-dependent kinds, the FP64 oracle).
 template <int UNROLL = 1>
 __device__ __forceinline__ float terminal_sum(uint64_t path, uint32_t n_steps, uint32_t stream, const PhiloxKeys& rk,
                                               uint32_t j0 = 0u, uint32_t j1 = 0xffffffffu) {
   float W = 0.0f;
-  for_each_pair<UNROLL>(path, n_steps, stream, rk, [&](const NormalPair& p, int n_use) {
-    W = fmaf(p.rad, p.cs, W);
-    if (n_use > 1) W = fmaf(p.rad, p.sn, W);
+  for_each_pair<UNROLL, false, true>(path, n_steps, stream, rk, [&](const NormalPair& p, int n_use) {
+    W = fmaf(n_use > 1 ? p.rad : p.rad * 0.70710678118654752440f, p.cs, W);
   }, j0, j1);
-  return W;
+  return W * 1.41421356237309504880f;
 }
 
 // CV = true additionally accumulates sum S_T, sum S_T^2 and sum payoff*S_T per scenario (the

@@ -93,6 +93,22 @@ __device__ __forceinline__ NormalPair box_muller(uint32_t w) {
   return p;
 }
 
+// The SUM of a pair's two normals, for consumers that only ever add them (the terminal log-price of the European kernels):
+//   rad cos(theta) + rad sin(theta) = sqrt(2) rad sin(theta + pi/4)
+// - the same number the two branches add up to, from ONE MUFU.SIN instead of COS + SIN and one FFMA instead of two.  The
+// pair comes back with cs = sin(theta + pi/4) (the caller owns the factor sqrt(2)) and sn = 0.
+constexpr float kMinusElevenQuarterPi = -8.63937979737193138115f;  // -3 pi + pi / 4
+template <bool SQUARED = false>
+__device__ __forceinline__ NormalPair box_muller_pair_sum(uint32_t w) {
+  NormalPair p;
+  const float u = 2.0f - __uint_as_float((w >> 9) | 0x3f800000u);
+  p.rad = SQUARED ? -mufu_lg2(u) : mufu_sqrt(-mufu_lg2(u));
+  const float turns = __uint_as_float((__byte_perm(w, 0u, 0x0123) >> 9) | 0x3f800000u);
+  p.cs = mufu_sin(fmaf(turns, kTwoPi, kMinusElevenQuarterPi));
+  p.sn = 0.0f;
+  return p;
+}
+
 // The one normal of a single-step path from the first two words of its stream (see the header).  rad is divided by the
 // 2^23-grid normalisation the kernels fold into their diffusion coefficient (this grid needs none: E[-2 ln u] = 2 to 1e-8).
 template <bool SQUARED = false>
