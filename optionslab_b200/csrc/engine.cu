@@ -268,7 +268,13 @@ TilePlan plan_tiles(const b200mc_engine* e, uint32_t n_opt, uint64_t n_paths, ui
 // __launch_bounds__ minBlocksPerSM per kernel family, picked from measurements on B200
 // (profiles/r01_variants.txt): the schedulers want the three Philox chains of a superblock
 // interleaved, which needs ~60-75 registers; squeezing below 48 costs 5-10%.
-constexpr int kMinBlocksSmall = 6;    // European, 1-2 scenarios (40-47 registers)
+#ifndef B200MC_SMALL_MINB
+#define B200MC_SMALL_MINB 6
+#endif
+#ifndef B200MC_SMALL_UNROLL
+#define B200MC_SMALL_UNROLL 1
+#endif
+constexpr int kMinBlocksSmall = B200MC_SMALL_MINB;  // European, 1-2 scenarios (40-47 registers)
 constexpr int kMinBlocksPathdep = 6;  // Asian / barrier / lookback, 1-2 scenarios (<= 40 registers)
 constexpr int kMinBlocksAsian = 6;    // arithmetic Asian, 1-2 scenarios (profiles/r01_variants14*)
 constexpr int kMinBlocksStructured = 5;  // cliquet / autocallable, 1-2 scenarios (47-48 registers)
@@ -291,7 +297,7 @@ cudaError_t launch_european(const SimArgs& a, bool anti, bool cv, dim3 grid, cud
     if (anti) european_kernel<NS, true, kMinBlocks, false, 1, true><<<grid, kBlock, 0, s>>>(a);
     else european_kernel<NS, false, kMinBlocks, false, 1, true><<<grid, kBlock, 0, s>>>(a);
   } else {
-    constexpr int kUnroll = NS <= 2 ? 1 : kUnrollWide;
+    constexpr int kUnroll = NS <= 2 ? B200MC_SMALL_UNROLL : kUnrollWide;
     if (anti) european_kernel<NS, true, kMinBlocks, false, kUnroll><<<grid, kBlock, 0, s>>>(a);
     else european_kernel<NS, false, kMinBlocks, false, kUnroll><<<grid, kBlock, 0, s>>>(a);
   }
