@@ -12,7 +12,7 @@ of the simulation kernel over NVLink peer memory (b200mc_simulate_allreduce_devi
 only if the engines could not be connected).
 
 The JSON line also carries: `e2e` (MonteCarloPricerUni.price_batch with host arrays in / prices out, same step count),
-`roofline` (XU and dispatch fractions of the peaks measured live by b200mc_measure_peaks next to the paper peak, HBM
+`roofline` (XU, issue and FMA-pipe fractions of the peaks measured live by b200mc_measure_peaks next to the paper peak, HBM
 figure, DRAM traffic read from the committed ncu capture), `cpu_baseline` (the UNMODIFIED reference installed in
 oracle/_ref - its Numba batch backend on all host threads - on a bounded sample; the NumPy restatement if that install
 is absent), `configs` (BASELINE.json configs C1-C4, the Greeks launch and the Asian grid through the public API: kernel
@@ -51,7 +51,7 @@ WORKLOAD = (f"C5: {N_OPT}-option European call grid ({N_STRIKES} strikes 60..140
 # of which 12 MUFU (LG2, SQRT and ONE SIN per Box-Muller pair: the terminal price adds a pair's two normals, and
 # rad (cos + sin) = sqrt(2) rad sin(theta + pi/4)), 16 IMAD.WIDE (fmaheavy pipe), 18 LOP3 + 8 LEA.HI + 4 PRMT (ALU pipe), 16 FP32.
 INSTR_PER_STEP, MUFU_PER_STEP, IMAD_PER_STEP, LOP_PER_STEP = 78 / 8, 1.5, 2.0, 30 / 8
-IMAD_WIDE_DISPATCH_CYCLES = 4.0  # scratch/variants15.cu: 16 IMAD.WIDE / IMAD.HI (+ XORs, loop) per warp take 69.7 / 66.0 SMSP cycles; charged 4
+IMAD_WIDE_PIPE_CYCLES, FP32_PER_STEP = 4.35, 16 / 8  # scratch/variants15.cu: 16 IMAD.WIDE (+ XORs, loop) per warp take 69.7 SMSP cycles
 ASIAN_INSTR_PER_STEP = 119 / 8  # pathdep_kernel<ASIAN_ARITH,1> small-move loop (tools/sass_loop.py --all): 16 FFMA2 + 4 FMUL2 + 32 FP32, 16 MUFU per 8 steps
 
 
@@ -565,9 +565,9 @@ def run_engine_arm(args):
             "imad_frac": kernel_rate * IMAD_PER_STEP / peaks["imad_wide_per_s"],
             "alu_frac": kernel_rate * LOP_PER_STEP / peaks["lop3_per_s"],
             "vs_rng_only_probe": kernel_rate / peaks["normals_per_s"],
-            # dispatch-port view (profiles/r01_variants15_fma_pipe_model.txt): an IMAD.WIDE holds an SMSP's dispatch port for
-            # ~4 cycles (measured 4.1-4.4 including loop overhead), every other instruction for 1; fraction of the measured issue peak under that weighting
-            "dispatch_frac": kernel_rate * (INSTR_PER_STEP + IMAD_PER_STEP * (IMAD_WIDE_DISPATCH_CYCLES - 1.0)) / peaks["issue_per_s"],
+            # FMA-pipe view (profiles/r01_variants15_fma_pipe_model.txt): per SMSP a warp-wide IMAD.WIDE occupies the FMA pipe for
+            # ~4.35 cycles, an FP32 instruction for 1.04, and they add up; fraction of the pipe's cycles (= the measured issue peak)
+            "fma_pipe_frac": kernel_rate * (IMAD_PER_STEP * IMAD_WIDE_PIPE_CYCLES + FP32_PER_STEP * 1.04) / peaks["issue_per_s"],
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size (N=1), read from the committed ncu --set
             # full capture of this bench command (the tile partials stay in the 126 MB L2 and are folded there by the same
             # kernel); algorithmic: 262 KB of parameters in + 98 KB of moments out
