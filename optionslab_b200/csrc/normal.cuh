@@ -28,6 +28,9 @@
 //           tests/test_philox_oracle.py, and a 1e10-draw binned chi-square on the device, tests/test_gpu_rng.py).
 //   z_cos = kRadScale*rad*cos(theta), z_sin = kRadScale*rad*sin(theta)
 //
+// Consumers that only ever ADD the two normals of a pair (the terminal log-price of the European kernels) take them as ONE
+// term, z_cos + z_sin = sqrt(2) * kRadScale*rad*sin(theta + pi/4) (box_muller_pair_sum): the same value from 3 MUFU.
+//
 // Single-step paths (n_steps == 1: the reference's DEFAULT, monte_carlo.py:59, gbm_numpy.py:56-83) are the one place where an
 // option's value is a direct functional of ONE draw's tail, and the one place where a draw is not on the hot loop.  Their
 // single normal therefore spends 64 bits (box_muller_single): the radius takes the WHOLE first word of the path's stream,
