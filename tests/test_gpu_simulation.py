@@ -62,3 +62,19 @@ def test_simulate_gbm_qmc_matches_scipy_points(n_points, n_steps):
     assert np.array_equal(both[:n_points], got) and np.array_equal(via_pricer, got)
     prod = P["S"] ** 2 * np.exp(2 * (P["r"] - P["q"] - 0.5 * P["sigma"] ** 2) * P["T"])
     np.testing.assert_allclose(both[:n_points] * both[n_points:], prod, rtol=3e-6)
+
+
+@pytest.mark.parametrize("n_steps", [2, 5, 8, 9, 252, 365])
+def test_pair_sum_terminal_equals_the_step_by_step_device_normals(n_steps):
+    """The terminal kernels take a Box-Muller pair as one term, sqrt(2) r sin(theta + pi/4) (normal.cuh, box_muller_pair_sum);
+    b200mc_normals evaluates both branches of the same words.  The two describe the same draws: the terminal prices equal the
+    FP64 terminal of the DEVICE's own step-by-step normals to FP32 rounding, odd tails included."""
+    from optionslab_b200 import _ffi
+
+    n, seed = 20_000, 77
+    eng = _ffi.get_engine(0)
+    Z = eng.generate_normals(seed, n, n_steps).astype(np.float64)
+    want = orc.gbm_terminal_from_normals(P["S"], P["T"], P["r"], P["sigma"], P["q"], Z)
+    got = sim.simulate_gbm_numpy(**P, n_paths=n, n_steps=n_steps, seed=seed)
+    # MUFU.SIN on theta + pi/4 vs MUFU.COS + MUFU.SIN on theta: ~5e-7 absolute per pair on the unit circle
+    np.testing.assert_allclose(got, want, rtol=3e-6)
