@@ -609,6 +609,8 @@ def run_engine_arm(args):
                                          else "by one NCCL all-reduce per step" if world > 1 else "(single rank: no exchange)"),
                        "l2": "256 MiB memset between steps (inside the timed region); the kernel's HBM input is 262 KB"},
             "options_per_sec": N_OPT * args.steps / elapsed_s,
+            # path-steps count independent normal streams; the antithetic mirrors ride on the same draws
+            "trajectory_steps_per_sec": 2.0 * work_per_step * args.steps / elapsed_s,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(params_np.nbytes),
                     "d2h_bytes_per_step": int(N_OPT * 24), "steps": e2e_steps, "api": "MonteCarloPricerUni.price_batch (numpy in/out)"},
             "gpu_launches": int(launches),
