@@ -551,6 +551,9 @@ def run_engine_arm(args):
         roofline = {
             "bound": bound,
             "kernel": "european_kernel<NS=1,ANTI>",
+            "kernel_note": "every path-step's normal is drawn (one 32-bit Philox word per Box-Muller pair = two steps); the terminal "
+                           "log-price adds a pair's two normals as sqrt(2) r sin(theta + pi/4) - the same value as r cos(theta) + "
+                           "r sin(theta), 3 MUFU per pair instead of 4 (DESIGN.md, 'pair sum')",
             "kernel_ms": ktime["mean_ms"], "kernel_ms_min": ktime["min_ms"], "kernels_timed": ktime["count"],
             "achieved": kernel_rate * (MUFU_PER_STEP if bound == "xu" else INSTR_PER_STEP),
             "peak": peaks["mufu_per_s"] if bound == "xu" else peaks["issue_per_s"],
