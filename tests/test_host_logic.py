@@ -250,6 +250,10 @@ def test_tile_plans_cover_the_paths_and_follow_the_measured_rules():
     assert _ffi.plan_tiles(euro, 64, 1, 1_000)["split_shift"] == 0                             # 64 options fill the chip by themselves
     assert _ffi.plan_tiles(euro, 1, 1, 10_000, control_variate=True)["split_shift"] == 0       # the control-variate kernel has no split form
     assert _ffi.plan_tiles(_ffi.make_spec(_ffi.EUROPEAN, 8, antithetic=True), 1, 1, 1_000)["split_shift"] == 0  # one Philox call: nothing to split
+    # 8-16 scenario European launches (two 8-warp CTAs per SM): one wave of the 2 x 148 CTA slots when the paths allow it, one CTA
+    # per SM for the reference's own sizes (profiles/r02_wide_plan_check.jsonl)
+    assert _ffi.plan_tiles(euro, 1, 14, 1_000_000)["tiles"] <= 296 and _ffi.plan_tiles(euro, 1, 8, 2_000_000)["tiles"] <= 296
+    assert _ffi.plan_tiles(euro, 1, 14, 100_000)["tiles"] <= 148 and _ffi.plan_tiles(euro, 1, 14, 100_000)["split_shift"] == 0
     # large grids amortise the per-CTA work over many paths per thread; the shape scales with the SM count
     assert _ffi.plan_tiles(euro, 4096, 1, 1_000_000)["paths_per_thread"] >= 16
     small, big = _ffi.plan_tiles(euro, 1, 1, 4_000, sm_count=16), _ffi.plan_tiles(euro, 1, 1, 4_000, sm_count=148)

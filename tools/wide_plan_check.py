@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""The planner's shape for the 8 / 14 scenario European launches against pinned alternatives: kernel us (min of 15) per size."""
+import json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from optionslab_b200 import _ffi
+P = dict(S=100.0, K=100.0, T=1.0, r=0.05, sigma=0.2)
+eng = _ffi.get_engine(0)
+spec = _ffi.make_spec(_ffi.EUROPEAN, 252, antithetic=True)
+for n_scen in (14, 8):
+    params = np.stack([_ffi.make_params(**dict(P, sigma=0.2 + 0.001 * k)) for k in range(n_scen)]).reshape(1, n_scen)
+    for n_paths in (30_000, 100_000, 200_000, 300_000, 500_000, 1_000_000, 2_000_000, 4_000_000):
+        row = {"n_scen": n_scen, "n_paths": n_paths}
+        for ppt in (0, 1, 2, 3, 4, 5, 7, 9, 14, 27):
+            if ppt and ppt * 256 > n_paths * 2:
+                continue
+            eng.set_plan(0, ppt)
+            eng.simulate(spec, params, 42, n_paths)
+            if ppt == 0:
+                row["auto_plan"] = eng.last_plan()
+            eng.set_kernel_timing(True)
+            for _ in range(15):
+                eng.simulate(spec, params, 42, n_paths)
+            row[f"p{ppt}"] = round(eng.kernel_timing()["min_ms"] * 1e3, 1)
+            eng.set_kernel_timing(False)
+        eng.set_plan()
+        print(json.dumps(row), flush=True)
