@@ -224,7 +224,7 @@ TilePlan plan_tiles(int sm_count, int pin_split_shift, uint32_t pin_ppt, uint32_
   const double per_path_payoff = 14.0 * ns;
   const double per_cta = 500.0 + 60.0 * ns;              // coefficient set-up + FP64 block reduction
   const uint32_t calls = (n_steps + 7u) >> 3;
-  const bool wide_european = ns >= 8 && !path_dependent;
+  const bool wide = ns >= 8;
   double best = 0.0;
   TilePlan plan;
   // Lane split (european_kernel<SPLIT>): measured on B200 (profiles/r02_plan_sweep.jsonl) it pays only while one thread
@@ -255,13 +255,14 @@ TilePlan plan_tiles(int sm_count, int pin_split_shift, uint32_t pin_ppt, uint32_
       const double concurrency = std::min(per_sm, (double)resident);
       const double eff = std::min(1.0, concurrency / kSaturatingCtas);
       double cost = (per_sm + 0.3 * resident) * ((double)p * per_path + per_cta) / eff;
-      if (wide_european && shift == 0) {
-        // 8-16 scenario European launches (two 8-warp CTAs per SM), measured on B200 (profiles/r02_experiments.txt #10): one CTA
-        // alone on an SM already runs at 1 / 1.19 of the pace of two (a pass of a lone CTA takes w, of each of two co-resident
-        // CTAs 1.68 w), and every CTA costs ~3 us of prologue + 48-value FP64 reduction + ticket.  The busiest SM works
-        // through its per_sm CTAs two at a time, a left-over one alone.
+      if (wide && shift == 0) {
+        // 8-16 scenario launches (two 8-warp CTAs per SM), measured on B200 (profiles/r02_experiments.txt #10,
+        // profiles/r02_wide_plan_check.jsonl): a lone CTA runs a pass in w; each of two co-resident CTAs takes 1.68 w in the
+        // European kernel (two CTAs = 1.19x the throughput of one) and 1.92 w in the path-dependent kinds (14 independent
+        // update chains per thread saturate the FMA pipe from 8 warps: co-residency buys 4 %); every CTA costs ~3 us of
+        // prologue + FP64 reduction + ticket.  The busiest SM works through its per_sm CTAs two at a time, a left-over one alone.
         const double pairs = std::floor(per_sm / 2.0), lone = per_sm - 2.0 * pairs;
-        cost = (double)p * per_path * (1.68 * pairs + lone) + per_cta * (pairs + lone);
+        cost = (double)p * per_path * ((path_dependent ? 1.92 : 1.68) * pairs + lone) + per_cta * (pairs + lone);
       }
       if (best == 0.0 || cost < best * 0.999) best = cost, plan.ppt = p, plan.tiles = (uint32_t)t, plan.split_shift = shift;
     }
