@@ -13,9 +13,9 @@ spec = {"european": lambda: _ffi.make_spec(_ffi.EUROPEAN, N_STEPS, antithetic=Tr
         "barrier": lambda: _ffi.make_spec(_ffi.BARRIER, N_STEPS)}[KIND]()
 for n_scen in ([int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else (14, 8)):
     params = np.stack([_ffi.make_params(**dict(P, sigma=0.2 + 0.001 * k), barrier=120.0) for k in range(n_scen)]).reshape(1, n_scen)
-    for n_paths in (30_000, 100_000, 200_000, 300_000, 500_000, 1_000_000, 2_000_000, 4_000_000):
+    for n_paths in (30_000, 100_000, 200_000, 300_000, 500_000, 1_000_000, 2_000_000, 4_000_000) + ((16_000_000,) if "--big" in sys.argv else ()):
         row = {"kind": KIND, "n_scen": n_scen, "n_paths": n_paths, "n_steps": N_STEPS}
-        for ppt in (0, 1, 2, 3, 4, 5, 7, 9, 14, 27):
+        for ppt in (0, 1, 2, 3, 4, 5, 7, 9, 14, 27, 32):
             if ppt and ppt * 256 > n_paths * 2:
                 continue
             eng.set_plan(0, ppt)
