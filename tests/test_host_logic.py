@@ -260,3 +260,35 @@ def test_tile_plans_cover_the_paths_and_follow_the_measured_rules():
     assert small["split_shift"] <= big["split_shift"]
     with pytest.raises(Exception):
         _ffi.plan_tiles(euro, 1, 17, 1000)
+
+
+# ---- bench.py helpers that the driver's bench run depends on (no GPU) ---------------------------------------------------------
+def test_bench_reads_roofline_traffic_from_the_committed_capture_and_its_budgets_match_the_shipped_sass(tmp_path):
+    import importlib.util
+    import os
+    import re
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    traffic, source = bench.traffic_from_capture()
+    assert source == os.path.join("profiles", "r02_ncu_european.txt")
+    assert 360_448 <= traffic < 8 * 360_448            # at least the algorithmic bytes (parameters in, moments out), same order
+    with pytest.raises(SystemExit):
+        bench.traffic_from_capture(str(tmp_path / "missing.txt"))
+    (tmp_path / "empty.txt").write_text("== void other_kernel()\ndram__bytes_read.sum 1 byte\n")
+    with pytest.raises(SystemExit):
+        bench.traffic_from_capture(str(tmp_path / "empty.txt"))
+    # the per-path-step budget bench.py multiplies the kernel rate by is the one of the SHIPPED binary (tools/sass_loop.py)
+    import shutil
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH: SASS budget not re-counted")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "sass_loop.py"), "european_kernelILi1ELb1ELi6ELb0ELi1ELb0"],
+                         capture_output=True, text=True).stdout
+    m = re.search(r"loop 0x[0-9a-f]+\.\.0x[0-9a-f]+: (\d+) instructions, (\d+) MUFU", out)
+    assert m, out
+    assert int(m.group(1)) / 8 == pytest.approx(bench.INSTR_PER_STEP) and int(m.group(2)) / 8 == pytest.approx(bench.MUFU_PER_STEP)
