@@ -52,7 +52,7 @@ WORKLOAD = (f"C5: {N_OPT}-option European call grid ({N_STRIKES} strikes 60..140
 # rad (cos + sin) = sqrt(2) rad sin(theta + pi/4)), 16 IMAD.WIDE (fmaheavy pipe), 18 LOP3 + 8 LEA.HI + 4 PRMT (ALU pipe), 16 FP32.
 INSTR_PER_STEP, MUFU_PER_STEP, IMAD_PER_STEP, LOP_PER_STEP = 78 / 8, 1.5, 2.0, 30 / 8
 IMAD_WIDE_PIPE_CYCLES, FP32_PER_STEP = 4.35, 16 / 8  # scratch/variants15.cu: 16 IMAD.WIDE (+ XORs, loop) per warp take 69.7 SMSP cycles
-ASIAN_INSTR_PER_STEP = 119 / 8  # pathdep_kernel<ASIAN_ARITH,1> small-move loop (tools/sass_loop.py --all): 16 FFMA2 + 4 FMUL2 + 32 FP32, 16 MUFU per 8 steps
+ASIAN_INSTR_PER_STEP = 117 / 8  # pathdep_kernel<ASIAN_ARITH,1> small-move loop (tools/sass_loop.py --all): 20 FFMA2 + 28 FP32, 16 MUFU per 8 steps
 
 
 def grid_params():

@@ -663,18 +663,31 @@ __device__ __forceinline__ void advance_pair(const NormalPair& p, int n_use, con
 constexpr float kRadMax = 4.79583152331271954f;  // sqrt(23): u >= 2^-23 (normal.cuh)
 constexpr float kSmallMove = 0.25f;
 
+// -> 2^x - 1 + plus (plus = 0 or 2, see advance_pair_small)
 template <int DEG = 5>
-__device__ __forceinline__ float exp2m1_small(float x) {
+__device__ __forceinline__ float exp2m1_small(float x, float plus = 0.0f) {
   float t = DEG >= 5 ? fmaf(x, 1.3333558146e-3f, 9.6181291076e-3f) : 9.6181291076e-3f;  // ln2^5/120, ln2^4/24
   if (DEG >= 4) t = fmaf(x, t, 5.5504108665e-2f);                                         // ln2^3/6
   else t = 5.5504108665e-2f;
   t = fmaf(x, t, 2.4022650696e-1f);                                                       // ln2^2/2
   t = fmaf(x, t, 6.9314718056e-1f);                                                       // ln2
-  return x * t;
+  return fmaf(x, t, plus);
 }
 
 // DEG = kSmallPacked4 (shipped) / kSmallPacked5: packed degree 4 / 5.  DEG = 3..5: scalar Horner forms (4+ scenarios, scratch/variants14.cu).
 constexpr int kSmallPacked5 = -5, kSmallPacked4 = -4;
+
+// One pair of the multiplicative update: y0 = 2^x0 - 1, y1p2 = 2^x1 + 1 (the same three roundings in the packed and scalar forms).
+__device__ __forceinline__ void pair_update(float& s, float& sum, float y0, float y1p2, int n_use) {
+  const float s1 = fmaf(s, y0, s);
+  if (n_use > 1) {
+    sum = fmaf(s1, y1p2, sum);
+    s = fmaf(s1, y1p2, -s1);
+  } else {
+    sum += s1;
+    s = s1;
+  }
+}
 
 template <int NS, int DEG = kSmallPacked4>
 __device__ __forceinline__ void advance_pair_small(const NormalPair& p, int n_use, const Coef (&q)[NS], float (&s)[NS], float (&aux)[NS]) {
@@ -691,25 +704,17 @@ __device__ __forceinline__ void advance_pair_small(const NormalPair& p, int n_us
       t = fma2(x, t, c3);
       t = fma2(x, t, c2);
       t = fma2(x, t, c1);
-      float y0, y1;
-      unpack2(mul2(x, t), y0, y1);
-      s[k] = fmaf(s[k], y0, s[k]);
-      aux[k] += s[k];
-      if (n_use > 1) {
-        s[k] = fmaf(s[k], y1, s[k]);
-        aux[k] += s[k];
-      }
+      // (y0, y1 + 2) = (2^x0 - 1, 2^x1 + 1): with s1 = s * 2^x0 the pair adds s1 + s2 = s1 * (2^x1 + 1) to the running sum and
+      // leaves s2 = s1 * (2^x1 + 1) - s1 - three FMAs instead of two FMAs and two adds
+      float y0, y1p2;
+      unpack2(fma2(x, t, pack2(0.0f, 2.0f)), y0, y1p2);
+      pair_update(s[k], aux[k], y0, y1p2, n_use);
     }
   } else {
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
       const float rc = p.rad * q[k].c;
-      s[k] = fmaf(s[k], exp2m1_small<DEG>(fmaf(rc, p.cs, q[k].d)), s[k]);
-      aux[k] += s[k];
-      if (n_use > 1) {
-        s[k] = fmaf(s[k], exp2m1_small<DEG>(fmaf(rc, p.sn, q[k].d)), s[k]);
-        aux[k] += s[k];
-      }
+      pair_update(s[k], aux[k], exp2m1_small<DEG>(fmaf(rc, p.cs, q[k].d)), exp2m1_small<DEG>(fmaf(rc, p.sn, q[k].d), 2.0f), n_use);
     }
   }
 }
