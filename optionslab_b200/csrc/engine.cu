@@ -225,6 +225,8 @@ TilePlan plan_tiles(int sm_count, int pin_split_shift, uint32_t pin_ppt, uint32_
   const double per_cta = 500.0 + 60.0 * ns;              // coefficient set-up + FP64 block reduction
   const uint32_t calls = (n_steps + 7u) >> 3;
   const bool wide = ns >= 8;
+  // (only launches of up to 16 single-pass CTAs per SM: beyond that the general model's finer tiles balance better, measured)
+  const bool mid_european = (ns == 3 || ns == 4) && !path_dependent && std::ceil((double)n_paths / kBlock) * n_opt <= 16.0 * n_sm;
   double best = 0.0;
   TilePlan plan;
   // Lane split (european_kernel<SPLIT>): measured on B200 (profiles/r02_plan_sweep.jsonl) it pays only while one thread
@@ -263,6 +265,12 @@ TilePlan plan_tiles(int sm_count, int pin_split_shift, uint32_t pin_ppt, uint32_
         // prologue + FP64 reduction + ticket.  The busiest SM works through its per_sm CTAs two at a time, a left-over one alone.
         const double pairs = std::floor(per_sm / 2.0), lone = per_sm - 2.0 * pairs;
         cost = (double)p * per_path * ((path_dependent ? 1.92 : 1.68) * pairs + lone) + per_cta * (pairs + lone);
+      }
+      if (mid_european && shift == 0) {
+        // 3-4 scenario European launches (70 registers: three 8-warp CTAs per SM), same measurements: two co-resident CTAs take
+        // 1.6 w each, three 2.45 w - the third buys nothing - so the best shapes put two CTAs on an SM
+        const double triples = std::floor(per_sm / 3.0), rem = per_sm - 3.0 * triples;
+        cost = (double)p * per_path * (2.45 * triples + (rem == 2.0 ? 1.6 : rem)) + per_cta * (triples + (rem > 0.0 ? 1.0 : 0.0));
       }
       if (best == 0.0 || cost < best * 0.999) best = cost, plan.ppt = p, plan.tiles = (uint32_t)t, plan.split_shift = shift;
     }
